@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: differentiable MPM substeps, forward + backward, particle-substeps / s.
+
+  python bench.py --gpus N --steps K --warmup W [--workload move100k] [--impl reference]
+
+One "step" = one fwd+bwd episode of the workload (H env steps x S substeps forward with the loss after every env
+step, then the full adjoint back to the action gradient) = N_particles * H * S particle-substeps.
+
+  value  whole-job particle-substeps/s with the particle state already resident in HBM (device-timed, CUDA events);
+  e2e    the same episode through the public API (`Solver.forward`): host float64 state -> device, per-env-step loss
+         read-back, action gradient read-back;
+  roofline      dominant kernel: algorithmic bytes per launch / mean CUDA-event duration, against MEASURED_PEAKS.json;
+  cpu_baseline  the float64 oracle (a restatement of the reference's Taichi kernels; Taichi itself is not
+                installable here) timed on this box's host cores on a bounded sample of the same workload.
+
+--impl reference times that oracle alone (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-substeps/sec fwd+bwd"
+UNIT = "particle-substeps/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on for one GPU
+    "move100k": dict(scene="move.yml", n=100_000, quality=2, horizon=50,
+                     desc="Move-v1 geometry, 100k particles, 128^3 grid, 50 env steps x 39 substeps, fwd+bwd action gradient"),
+    # north_star roofline target size
+    "move1m": dict(scene="move.yml", n=1_000_000, quality=2, horizon=10,
+                   desc="Move-v1 geometry, 1M particles, 128^3 grid, 10 env steps x 39 substeps, fwd+bwd"),
+    # BASELINE.json configs[0] (the reference's own CPU-runnable case), here as fwd+bwd
+    "move10k": dict(scene="move.yml", n=10_000, quality=1, horizon=50,
+                    desc="Move-v1 stock, 10k particles, 64^3 grid, 50 env steps x 19 substeps, fwd+bwd"),
+    "rope1m": dict(scene="rope.yml", n=1_000_000, quality=4, horizon=2,
+                   desc="Rope-v1 geometry, 1M particles, 256^3 grid, 2 env steps x 79 substeps, fwd+bwd"),
+}
+
+
+def build_cfg(w):
+    from plasticinelab_b200.envs.scene import load_variants
+    from plasticinelab_b200 import _capi
+    cfg = load_variants(w["scene"], 1)
+    cfg.SIMULATOR.quality = w["quality"]
+    cfg.SHAPES[0]["n_particles"] = w["n"]
+    S = _capi.sim_constants(dict(cfg.SIMULATOR))["substeps"]
+    cfg.SIMULATOR.max_steps = w["horizon"] * S + 2
+    return cfg, S
+
+
+def actions_for(w, A):
+    return np.random.RandomState(0).uniform(-0.01, 0.01, (w["horizon"], A))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                p = [t.strip() for t in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# algorithmic bytes per launch of each kernel: (bytes per particle, bytes per active node), float32 scalars
+# (DESIGN.md "Kernels"; the sums are 204 N + 56 A forward and the engine's own 420 N + 128 A backward)
+KERNEL_BYTES = {
+    "p2g": (132, 16), "grid_fwd": (0, 28), "g2p": (72, 12), "p2g_recompute": (96, 16), "grid_fwd_recompute": (0, 28),
+    "g2p_bwd": (84, 24), "grid_bwd": (0, 44), "p2g_bwd": (240, 16),
+}
+
+
+def oracle_sample(cfg, w, S, n_sub, threads):
+    """Bounded CPU sample: n_sub fwd+bwd substeps of the same scene with the float64 oracle (torch CPU)."""
+    import torch
+    from oracle.plb_oracle import OracleEnv
+    from plasticinelab_b200.engine.shapes import Shapes
+    torch.set_num_threads(threads)
+    x0, _ = Shapes(cfg.SHAPES).get()
+    oenv = OracleEnv(cfg, x0, None)
+    sim = oenv.sim
+    sim.set_softness(666.0)
+    A = oenv.action_dims[-1]
+    acts = torch.as_tensor(actions_for(w, A)[:1])
+    frames = oenv.trajectory(oenv.initial_prims(), acts)
+    fr = [[t.detach() for t in f] for f in frames]
+    state = oenv.initial_state()
+    t0 = time.perf_counter()
+    states = [state]
+    with torch.no_grad():
+        for s in range(n_sub):
+            state = sim.substep(state, fr[s], fr[s + 1])
+            states.append(state)
+    adj = tuple(torch.ones_like(t) for t in state)
+    for s in reversed(range(n_sub)):
+        adj, _, _ = sim.substep_vjp(states[s], fr[s], fr[s + 1], adj)
+    dt = time.perf_counter() - t0
+    return len(x0) * n_sub / dt, dt
+
+
+def run_reference(args, w, rank):
+    if rank != 0:
+        return
+    cfg, S = build_cfg(w)
+    threads = os.cpu_count() or 1
+    n_sub = max(1, int(os.environ.get("PLB_BENCH_CPU_SUBSTEPS", "2" if w["n"] >= 1_000_000 else "4")))
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, dt = oracle_sample(cfg, w, S, n_sub, threads)
+        if i >= args.warmup:
+            vals.append(v); times.append(dt)
+    value = float(np.mean(vals))
+    sample = f"{n_sub} fwd+bwd substeps of the workload scene per step (float64 torch-CPU oracle, {threads} threads)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": w["desc"], "n_particles": w["n"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="move100k", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    import torch
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from plasticinelab_b200 import _capi
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.optimizer.solver import Solver
+
+    cfg, S = build_cfg(w)
+    torch.cuda.set_device(local_rank)
+    env = TaichiEnv(cfg, dtype=args.dtype, device=local_rank)
+    env.initialize()
+    env.loss.set_weights(10, 10, 1, False)
+    eng = env.engine
+    eng.call("plb_set_stream", C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    N, H = env.n_particles, w["horizon"]
+    A = env.primitives.action_dim
+    actions = actions_for(w, A)
+    pinned_actions = torch.from_numpy(actions).pin_memory()
+    host_state = env.get_state()["state"]
+    solver = Solver(env, None, None, n_iters=1, softness=666.0, horizon=H)
+    solver.total_steps = 0
+    grad_out = np.zeros((H, max(A, 1)))
+
+    def episode_device():
+        """state resident in HBM (frame 0), no host read-back except the final action gradient"""
+        env.simulator.cur = 0
+        env._is_copy = False
+        for p in env.primitives:
+            p.set_state(0, p.init_state)
+        eng.call("plb_zero_grads")
+        a = pinned_actions.numpy()
+        for i in range(H):
+            eng.call("plb_set_action", i, S, _capi.dptr(np.ascontiguousarray(a[i])), A)
+            eng.call("plb_kinematics", i * S, S)
+            eng.call("plb_step_fwd", i * S, i * S, S)
+            eng.call("plb_loss_fwd", (i + 1) * S, (i + 1) * S, None)
+        for i in reversed(range(H)):
+            eng.call("plb_loss_bwd", (i + 1) * S, (i + 1) * S)
+            eng.call("plb_step_bwd", i * S, i * S, S)
+        eng.call("plb_get_action_grad", H, S, _capi.dptr(grad_out))
+
+    def episode_e2e():
+        return solver.forward(host_state, pinned_actions.numpy())
+
+    def timed(fn, k):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms
+
+    env.primitives.set_softness(666.0)
+    for _ in range(args.warmup):
+        episode_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.lib.plb_launch_count(eng.h)
+    eng.call("plb_profile_enable", 1)
+    ms_dev = timed(episode_device, args.steps)
+    launches = eng.lib.plb_launch_count(eng.h) - l0
+    kms = np.zeros(16)
+    kcnt = (C.c_longlong * 16)()
+    nk = eng.lib.plb_profile_read(eng.h, 16, _capi.dptr(kms), kcnt)
+    eng.call("plb_profile_enable", 0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end through the public API
+    episode_e2e()
+    ms_e2e = timed(episode_e2e, args.steps)
+
+    units_per_step = N * H * S
+    value = world * units_per_step * args.steps / (ms_dev * 1e-3)
+    e2e_value = world * units_per_step * args.steps / (ms_e2e * 1e-3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel + of the fused substep
+    na = C.c_longlong()
+    eng.call("plb_count_active", (H // 2) * S, C.byref(na))
+    n_active = int(na.value)
+    peak, peak_src = measured_peak_gbs()
+    names = [eng.lib.plb_kernel_name(i).decode() for i in range(nk)]
+    per_kernel = {names[i]: {"launches": int(kcnt[i]), "total_ms": float(kms[i]), "avg_us": 1e3 * float(kms[i]) / max(int(kcnt[i]), 1)}
+                  for i in range(nk) if kcnt[i] > 0}
+    sub = {k: v for k, v in per_kernel.items() if k in KERNEL_BYTES}
+    dom = max(sub, key=lambda k: sub[k]["total_ms"])
+    bpp, bpn = KERNEL_BYTES[dom]
+    sc = 2 if args.dtype == "float64" else 1
+    alg_bytes = sc * (bpp * N + bpn * n_active)
+    achieved = alg_bytes / (sub[dom]["avg_us"] * 1e-6) / 1e9
+    fused_bytes = sc * (504 * N + 168 * n_active)
+    fused_gbs = fused_bytes * (H * S * args.steps) / (ms_dev * 1e-3) / 1e9
+    kernel_ms_total = sum(v["total_ms"] for v in per_kernel.values())
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_us": sub[dom]["avg_us"], "share_of_kernel_time": sub[dom]["total_ms"] / max(kernel_ms_total, 1e-9),
+                "n_active_nodes": n_active,
+                "fused_substep": {"algorithmic_bytes": fused_bytes, "achieved": fused_gbs, "frac": fused_gbs / peak,
+                                  "formula": "(504 N + 168 N_active) B per fwd+bwd substep (SURVEY.md 8d)"},
+                "kernels": per_kernel}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_sub = 2 if N >= 1_000_000 else 4
+        v, dt = oracle_sample(cfg, w, S, n_sub, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_sub} fwd+bwd substeps of the same scene, float64 torch-CPU oracle ({dt:.1f} s)"}
+
+    state_bytes = 24 * N * 8
+    h2d = state_bytes + actions.nbytes + H * S * 2 * 8 * 8 * len(env.primitives)
+    d2h = (H + 1) * 64 + grad_out.nbytes + 8
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": w["desc"], "n_particles": N, "n_grid": env.simulator.n_grid,
+                       "substeps_per_env_step": S, "env_steps": H, "particle_substeps_per_step": units_per_step,
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one env per GPU)",
+                       "l2": "inputs larger than L2: every substep reads a different trajectory frame "
+                             f"({(H * S + 1) * 96 * N / 1e9:.1f} GB trajectory per episode)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

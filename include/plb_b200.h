@@ -1,0 +1,164 @@
+/* plb_b200.h -- C ABI of the B200-native differentiable MPM engine.
+ *
+ * The reference (hzaskywalker/PlasticineLab) has no FFI: its engine is Python + Taichi JIT kernels.  This
+ * header declares the boundary a replacement engine exports underneath the reference's Python object surface
+ * (SURVEY.md section 8b).  Each entry point names the reference interface it replaces (file:line relative to
+ * the reference checkout).  Everything is `extern "C"`, plain pointers and sizes, no torch/CUDA types:
+ * streams travel as `void*` (a cudaStream_t), device buffers are owned by the engine.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative plb_status on failure; plb_last_error() gives the text;
+ *   - host arrays are float64, row-major, laid out exactly like the numpy arrays of the reference
+ *     (x,v: [N][3]; F,C: [N][3][3]; primitive state: 7 or 8 doubles = position, quaternion wxyz[, gap]);
+ *   - `slot` indexes the engine's particle-frame storage (0 .. max_frames-1); `pf` indexes primitive frames
+ *     (0 .. max_prim_frames-1).  The reference uses one index f for both (fields shaped [max_steps, ...],
+ *     plb/engine/mpm_simulator.py:35-38, plb/engine/primitive/primive_base.py:36-37); keeping them apart lets
+ *     the host run env-step checkpointing (plb/optimizer/long_term_gradient.ipynb cell 4) in a small window;
+ *   - calls are asynchronous on the engine's stream unless they return data to the host;
+ *   - one host thread per engine; one engine per GPU.
+ */
+#ifndef PLB_B200_H
+#define PLB_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plb_engine plb_engine;
+
+typedef enum {
+    PLB_OK = 0,
+    PLB_ERR_INVALID = -1,      /* bad argument / state */
+    PLB_ERR_CUDA = -2,         /* CUDA runtime error */
+    PLB_ERR_NOMEM = -3,
+    PLB_ERR_UNSUPPORTED = -4
+} plb_status;
+
+enum { PLB_F32 = 0, PLB_F64 = 1 };
+
+/* primitive shapes: plb/engine/primitive/primitives.py:17-257 */
+enum { PLB_SPHERE = 0, PLB_CAPSULE = 1, PLB_ROLLINGPIN = 2, PLB_CHOPSTICKS = 3, PLB_CYLINDER = 4,
+       PLB_TORUS = 5, PLB_BOX = 6 };
+
+#define PLB_MAX_PRIMITIVES 8
+#define PLB_MAX_ACTION_DIM 7
+
+/* One rigid manipulator; fields = the reference's per-primitive cfg (primive_base.py:208-224, primitives.py). */
+typedef struct {
+    int    type;                 /* PLB_SPHERE ... */
+    double params[4];            /* sphere: radius | capsule/rollingpin/chopsticks: h, r | cylinder: h, r |
+                                    torus: tx, ty | box: size xyz */
+    double friction;
+    double init_state[8];        /* init_pos(3), init_rot(4), init_gap */
+    double lower_bound[3];
+    double upper_bound[3];
+    int    action_dim;           /* 0 = static */
+    double action_scale[PLB_MAX_ACTION_DIM];
+    double minimal_gap;          /* chopsticks */
+} plb_primitive_desc;
+
+/* Simulator configuration = derived constants of MPMSimulator.__init__ (mpm_simulator.py:6-50). */
+typedef struct {
+    int    dtype;                /* PLB_F32 (production) or PLB_F64 (parity mode; the reference is f64 only) */
+    int    n_particles;
+    int    n_grid;               /* int(128 * quality / 2) */
+    int    substeps;             /* int(2e-3 // dt), informational */
+    int    max_frames;           /* particle frame slots to allocate */
+    int    max_prim_frames;      /* primitive trajectory length */
+    double dt, dx, p_vol, p_mass;
+    double E, nu;                /* -> mu, lam (uniform material) */
+    double yield_stress;
+    double ground_friction;
+    double gravity[3];
+    int    n_primitives;
+    int    device;               /* CUDA device ordinal */
+    int    kernel_variant;       /* 0 = default (fastest available), 1 = simple reference kernels */
+} plb_config;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+/* replaces TaichiEnv.__init__/initialize + ti.init (plb/engine/taichi_env.py:6,10-58) */
+int  plb_create(const plb_config* cfg, const plb_primitive_desc* prims, plb_engine** out);
+int  plb_destroy(plb_engine* e);
+const char* plb_last_error(const plb_engine* e);      /* e may be NULL: error of the last failed plb_create */
+int  plb_set_stream(plb_engine* e, void* cuda_stream);
+int  plb_synchronize(plb_engine* e);
+int  plb_abi_version(void);
+
+/* ---- particle state ------------------------------------------------------------------------------------- */
+/* MPMSimulator.initialize material fill, mpm_simulator.py:53-57; NULL = keep the uniform value */
+int  plb_set_materials(plb_engine* e, const double* mu, const double* lam, const double* yield_stress);
+/* MPMSimulator.setframe / readframe / get_x / get_v, mpm_simulator.py:282-363 (any pointer may be NULL) */
+int  plb_set_frame(plb_engine* e, int slot, const double* x, const double* v, const double* F, const double* C);
+int  plb_get_frame(plb_engine* e, int slot, double* x, double* v, double* F, double* C);
+/* MPMSimulator.copyframe, mpm_simulator.py:303-312 (particles only; primitives: plb_copy_primitive_frame) */
+int  plb_copy_frame(plb_engine* e, int src_slot, int dst_slot);
+/* device-side access for torch interop: pointer to the frame's first scalar, padded particle count, scalar size */
+int  plb_frame_device_ptr(plb_engine* e, int slot, void** ptr, long long* n_pad, int* scalar_bytes);
+
+/* ---- primitives ----------------------------------------------------------------------------------------- */
+/* Primitive.set_state / get_state, primive_base.py:143-150 (+ Chopsticks gap, primitives.py:133-146) */
+int  plb_set_primitive_state(plb_engine* e, int pf, int k, const double* state8);
+int  plb_get_primitive_state(plb_engine* e, int pf, int k, double* state8);
+int  plb_copy_primitive_frame(plb_engine* e, int src_pf, int dst_pf);
+/* Primitives.set_softness, primitives.py:303-305 */
+int  plb_set_softness(plb_engine* e, double softness);
+/* Primitives.set_action -> set_velocity, primitives.py:289-293, primive_base.py:184-198: clips to [-1,1], fills the
+   per-substep velocities of frames [step*S, (step+1)*S) */
+int  plb_set_action(plb_engine* e, int step, int n_substeps, const double* action, int action_len);
+/* forward_kinematics for frames pf .. pf+n-1 -> pf+1 .. pf+n (primive_base.py:117-121, primitives.py:66-80,94-98),
+   then uploads the poses */
+int  plb_kinematics(plb_engine* e, int pf, int n);
+
+/* ---- simulation ----------------------------------------------------------------------------------------- */
+/* MPMSimulator.substep(s), mpm_simulator.py:245-257: state[slot_in] -> state[slot_out] with poses pf, pf+1 */
+int  plb_substep_fwd(plb_engine* e, int slot_in, int slot_out, int pf);
+/* n consecutive substeps slot0+i -> slot0+i+1, poses pf0+i (MPMSimulator.step's loop, mpm_simulator.py:373-374) */
+int  plb_step_fwd(plb_engine* e, int slot0, int pf0, int n);
+/* MPMSimulator.substep_grad(s), mpm_simulator.py:260-278: adjoint(frame s+1) -> adjoint(frame s); adds the pose
+   adjoints of frames pf, pf+1 to the primitive-gradient buffer */
+int  plb_substep_bwd(plb_engine* e, int slot_in, int pf);
+int  plb_step_bwd(plb_engine* e, int slot0, int pf0, int n);      /* substeps slot0+n-1 .. slot0 */
+
+/* ---- adjoint state (ti.Tape bookkeeping, plb/optimizer/solver.py:36) -------------------------------------- */
+int  plb_zero_grads(plb_engine* e);                    /* particle adjoint, primitive gradients, loss value */
+int  plb_set_adjoint(plb_engine* e, const double* gx, const double* gv, const double* gF, const double* gC);
+int  plb_get_adjoint(plb_engine* e, double* gx, double* gv, double* gF, double* gC);
+/* d loss / d pose for primitive frames [pf0, pf0+n): out[n][n_primitives][8] */
+int  plb_get_primitive_grads(plb_engine* e, int pf0, int n, double* out);
+/* Primitives.get_grad(n) (primitives.py:295-301): chains the pose adjoints through forward_kinematics.grad and
+   set_velocity.grad; out[n_steps][sum action_dim] */
+int  plb_get_action_grad(plb_engine* e, int n_steps, int n_substeps, double* out);
+
+/* ---- loss (plb/engine/losses/loss.py) --------------------------------------------------------------------- */
+/* Loss.load_target_density + update_target (loss.py:46-66,81-106).  density: [n_grid^3] float64.
+   sdf may be NULL: the engine then builds it on the device with the reference's sweep. */
+int  plb_set_target(plb_engine* e, const double* density, const double* sdf);
+int  plb_get_target_sdf(plb_engine* e, double* sdf);
+/* Loss.set_weights (loss.py:68-72); contact_grad_all = 1 reproduces the reference's autodiff of atomic_min */
+int  plb_set_loss_weights(plb_engine* e, double sdf, double density, double contact, int soft_contact,
+                          int contact_grad_all);
+/* Loss.compute_loss_kernel(f) + iou (loss.py:186-208,239-254).  Adds the step loss to the accumulated loss.
+   out8 (may be NULL = stay asynchronous): accumulated loss, contact, density, sdf, iou, step loss, 0, 0 */
+int  plb_loss_fwd(plb_engine* e, int slot, int pf, double* out8);
+/* Loss.compute_loss_kernel.grad(f) (loss.py:210-237): seeds the particle adjoint (frame = slot) and pose grads */
+int  plb_loss_bwd(plb_engine* e, int slot, int pf);
+int  plb_get_loss(plb_engine* e, double* accumulated);     /* loss.loss[None] */
+int  plb_clear_loss(plb_engine* e);                        /* Loss.clear_loss (loss.py:181-183) */
+
+/* ---- introspection for tests / profiling ------------------------------------------------------------------ */
+/* copies the dense grids of the last substep: any of in4/out4 may be NULL; [n_grid^3][4] float64 */
+int  plb_debug_get_grid(plb_engine* e, double* in4, double* out4);
+/* number of kernels this engine has launched since creation */
+long long plb_launch_count(const plb_engine* e);
+/* per-kernel device time, measured with CUDA events on the engine's stream around every launch while enabled.
+   plb_profile_read: synchronises, fills total_ms[i] / counts[i] for kernel ids 0..n-1, returns the number of ids. */
+int  plb_profile_enable(plb_engine* e, int on);
+int  plb_profile_read(plb_engine* e, int n, double* total_ms, long long* counts);
+const char* plb_kernel_name(int kernel_id);
+/* nodes with mass > 1e-12 after the most recent forward P2G of plb_count_active (synchronous) */
+int  plb_count_active(plb_engine* e, int slot, long long* n_active);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLB_B200_H */

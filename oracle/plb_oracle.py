@@ -478,9 +478,13 @@ class OracleSim:
         eps_hat = eps - eps.sum(-1, keepdim=True) / 3
         eps_norm = torch.sqrt((eps_hat * eps_hat).sum(-1) + 1e-8)
         dgamma = eps_norm - self.yield_stress / (2 * self.mu)
-        eps_new = eps - (dgamma / eps_norm)[:, None] * eps_hat
-        F_yield = U @ torch.diag_embed(torch.exp(eps_new)) @ V.transpose(-1, -2)
-        new_F = torch.where((dgamma > 0)[:, None, None], F_yield, F_tmp)
+        with torch.no_grad():
+            yidx = (dgamma > 0).nonzero()[:, 0]          # the yield branch is evaluated on yielding rows only
+        new_F = F_tmp
+        if len(yidx) > 0:
+            eps_new = eps[yidx] - (dgamma[yidx] / eps_norm[yidx])[:, None] * eps_hat[yidx]
+            F_yield = U[yidx] @ torch.diag_embed(torch.exp(eps_new)) @ V[yidx].transpose(-1, -2)
+            new_F = F_tmp.index_copy(0, yidx, F_yield)
         # stress (:166-174)
         J = torch.linalg.det(new_F)
         r = U @ V.transpose(-1, -2)
@@ -633,6 +637,21 @@ class OracleLoss:
         grads = torch.autograd.grad(total, [xl] + pf, allow_unused=True)
         grads = [torch.zeros_like(i) if g is None else g for g, i in zip(grads, [xl] + pf)]
         return grads[0], grads[1:]
+
+
+def build_target_sdf_c(density: np.ndarray, dx: float) -> np.ndarray:
+    """Same sweep in plain C (oracle/oracle_c.c, built by __graft_entry__.build_oracle); bit-identical to the numpy
+    statement below (tests/test_oracle.py) and ~50x faster."""
+    import ctypes
+    import os
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_build', 'liboracle_c.so')
+    lib = ctypes.CDLL(so)
+    d = np.ascontiguousarray(density, dtype=np.float64)
+    out = np.zeros_like(d)
+    rc = lib.oracle_build_target_sdf(int(d.shape[0]), ctypes.c_double(dx), d.ctypes.data_as(ctypes.c_void_p),
+                                     out.ctypes.data_as(ctypes.c_void_p))
+    assert rc > 0
+    return out
 
 
 def build_target_sdf(density: np.ndarray, dx: float, inf: float = 1000.0) -> np.ndarray:

@@ -1,0 +1,360 @@
+// Per-thread bodies of the simulation kernels ("one particle" / "one node"), shared by
+//   * the __global__ kernels in plb_kernels.cu (sm_100a), and
+//   * tests/host/emul.cpp, which runs them sequentially on the CPU for parity against the oracle.
+//
+// HBM layout of one particle frame (n = padded particle count, scalar type T, 24 n scalars, exact packing):
+//   group A (written by G2P):  A0[n] = (x0,x1,x2,v0)  A1[n] = (v1,v2,C00,C01)  A2[n] = (C02,C10,C11,C12)
+//                              a3[n] = C20   a4[n] = C21   a5[n] = C22
+//   group B (written by P2G):  B0[n] = (F00,F01,F02,F10)  B1[n] = (F11,F12,F20,F21)  b2[n] = F22
+// A warp reads each Vec4 plane as one fully coalesced 512 B (float) request and each scalar plane as 128 B.
+// Adjoint frames use the same layout.  Grids are Vec4 per node: grid_in = (momentum xyz, mass),
+// grid_out = (velocity xyz, 0) and likewise for their adjoints, linear index (i * n + j) * n + k.
+#pragma once
+#include "plb_grid.cuh"
+
+namespace plb {
+
+template <class T> struct FramePtr {
+    Vec4<T>* A0; Vec4<T>* A1; Vec4<T>* A2; T* a3; T* a4; T* a5;
+    Vec4<T>* B0; Vec4<T>* B1; T* b2;
+};
+
+template <class T> PLB_HD FramePtr<T> frame_at(T* base, long long f, long long n_pad) {
+    T* b = base + f * 24 * n_pad;
+    FramePtr<T> r;
+    r.A0 = reinterpret_cast<Vec4<T>*>(b);
+    r.A1 = reinterpret_cast<Vec4<T>*>(b + 4 * n_pad);
+    r.A2 = reinterpret_cast<Vec4<T>*>(b + 8 * n_pad);
+    r.a3 = b + 12 * n_pad; r.a4 = b + 13 * n_pad; r.a5 = b + 14 * n_pad;
+    r.B0 = reinterpret_cast<Vec4<T>*>(b + 15 * n_pad);
+    r.B1 = reinterpret_cast<Vec4<T>*>(b + 19 * n_pad);
+    r.b2 = b + 23 * n_pad;
+    return r;
+}
+
+template <class T> struct Material { const T* mu; const T* lam; const T* ys; };   // null => uniform from SimConst
+
+// ---- plane access
+template <class T> PLB_HD void load_xvC(const FramePtr<T>& f, int p, V3<T>& x, V3<T>& v, M3<T>& C) {
+    Vec4<T> q0 = f.A0[p], q1 = f.A1[p], q2 = f.A2[p];
+    x = mk3<T>(q0.x, q0.y, q0.z);
+    v = mk3<T>(q0.w, q1.x, q1.y);
+    C.m[0][0] = q1.z; C.m[0][1] = q1.w; C.m[0][2] = q2.x;
+    C.m[1][0] = q2.y; C.m[1][1] = q2.z; C.m[1][2] = q2.w;
+    C.m[2][0] = f.a3[p]; C.m[2][1] = f.a4[p]; C.m[2][2] = f.a5[p];
+}
+template <class T> PLB_HD void store_xvC(const FramePtr<T>& f, int p, V3<T> x, V3<T> v, const M3<T>& C) {
+    f.A0[p] = mk4<T>(x.x, x.y, x.z, v.x);
+    f.A1[p] = mk4<T>(v.y, v.z, C.m[0][0], C.m[0][1]);
+    f.A2[p] = mk4<T>(C.m[0][2], C.m[1][0], C.m[1][1], C.m[1][2]);
+    f.a3[p] = C.m[2][0]; f.a4[p] = C.m[2][1]; f.a5[p] = C.m[2][2];
+}
+template <class T> PLB_HD M3<T> load_F(const FramePtr<T>& f, int p) {
+    Vec4<T> q0 = f.B0[p], q1 = f.B1[p];
+    M3<T> F;
+    F.m[0][0] = q0.x; F.m[0][1] = q0.y; F.m[0][2] = q0.z; F.m[1][0] = q0.w;
+    F.m[1][1] = q1.x; F.m[1][2] = q1.y; F.m[2][0] = q1.z; F.m[2][1] = q1.w;
+    F.m[2][2] = f.b2[p];
+    return F;
+}
+template <class T> PLB_HD void store_F(const FramePtr<T>& f, int p, const M3<T>& F) {
+    f.B0[p] = mk4<T>(F.m[0][0], F.m[0][1], F.m[0][2], F.m[1][0]);
+    f.B1[p] = mk4<T>(F.m[1][1], F.m[1][2], F.m[2][0], F.m[2][1]);
+    f.b2[p] = F.m[2][2];
+}
+template <class T> PLB_HD V3<T> load_x(const FramePtr<T>& f, int p) {
+    Vec4<T> q0 = f.A0[p];
+    return mk3<T>(q0.x, q0.y, q0.z);
+}
+
+// ---- scatter primitives: red.global on the device, plain adds in the sequential host emulation
+#if defined(__CUDA_ARCH__)
+PLB_D void scatter_add4(Vec4<float>* addr, Vec4<float> v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+PLB_D void scatter_add4(Vec4<double>* addr, Vec4<double> v) {
+    double* a = reinterpret_cast<double*>(addr);
+    atomicAdd(a + 0, v.x); atomicAdd(a + 1, v.y); atomicAdd(a + 2, v.z); atomicAdd(a + 3, v.w);
+}
+PLB_D void scatter_add1(float* addr, float v) { atomicAdd(addr, v); }
+PLB_D void scatter_add1(double* addr, double v) { atomicAdd(addr, v); }
+#else
+template <class T> inline void scatter_add4(Vec4<T>* addr, Vec4<T> v) { addr->x += v.x; addr->y += v.y; addr->z += v.z; addr->w += v.w; }
+template <class T> inline void scatter_add1(T* addr, T v) { *addr += v; }
+#endif
+
+template <class T> PLB_HD void load_material(const SimConst<T>& P, const Material<T>& mat, int p, T& mu, T& lam, T& ys) {
+    mu = mat.mu ? mat.mu[p] : P.mu;
+    lam = mat.lam ? mat.lam[p] : P.lam;
+    ys = mat.ys ? mat.ys[p] : P.yield_stress;
+}
+
+PLB_HD long long node_index(int n, int i, int j, int k) { return ((long long)i * n + j) * n + k; }
+
+// ================================================================================================
+// forward substep
+// ================================================================================================
+// P2G: F_tmp, SVD, return mapping, stress, 27-node scatter.  `out` may alias nothing (F[f+1] store skipped if !store_F_out).
+template <class T>
+PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,
+                     const Material<T>& mat, Vec4<T>* grid_in) {
+    V3<T> x, v; M3<T> C;
+    load_xvC(in, p, x, v, C);
+    M3<T> F = load_F(in, p);
+    T mu, lam, ys;
+    load_material(P, mat, p, mu, lam, ys);
+    M3<T> new_F, affine;
+    p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine);
+    if (store_F_out) store_F(out, p, new_F);
+    Stencil<T> st = make_stencil(x, P.inv_dx);
+    V3<T> mvel = P.p_mass * v;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
+                V3<T> dpos = mk3<T>((T(i) - st.fx.x) * P.dx, (T(j) - st.fx.y) * P.dx, (T(k) - st.fx.z) * P.dx);
+                V3<T> mom = w * (mvel + mv(affine, dpos));
+                scatter_add4(grid_in + node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k),
+                             mk4<T>(mom.x, mom.y, mom.z, w * P.p_mass));
+            }
+}
+
+// grid operator: grid_in -> grid_out; optionally zeroes grid_in for the next scatter
+template <class T>
+PLB_HD void grid_fwd_body(long long node, const SimConst<T>& P, const PrimSet<T>& prims, const Pose<T>* s0, const Pose<T>* s1,
+                          Vec4<T>* grid_in, Vec4<T>* grid_out, bool clear_in) {
+    Vec4<T> in4 = grid_in[node];
+    const int n = P.n_grid;
+    int k = (int)(node % n), j = (int)((node / n) % n), i = (int)(node / ((long long)n * n));
+    V3<T> v = grid_node_forward<T>(P, prims, s0, s1, i, j, k, in4);
+    grid_out[node] = mk4<T>(v.x, v.y, v.z, T(0));
+    if (clear_in && (in4.x != T(0) || in4.y != T(0) || in4.z != T(0) || in4.w != T(0)))
+        grid_in[node] = mk4<T>(T(0), T(0), T(0), T(0));
+}
+
+// G2P: 27-node gather, APIC C, advection
+template <class T>
+PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, const Vec4<T>* grid_out) {
+    V3<T> x = load_x(in, p);
+    Stencil<T> st = make_stencil(x, P.inv_dx);
+    V3<T> nv = zero3<T>();
+    M3<T> nC = zeroM<T>();
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
+                Vec4<T> g4 = grid_out[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
+                V3<T> gv = mk3<T>(g4.x, g4.y, g4.z);
+                V3<T> dpos = mk3<T>(T(i) - st.fx.x, T(j) - st.fx.y, T(k) - st.fx.z);
+                nv += w * gv;
+                nC += (T(4) * P.inv_dx * w) * outer(gv, dpos);
+            }
+    V3<T> nx = advect(P, x, nv);
+    store_xvC(out, p, nx, nv, nC);
+}
+
+// ================================================================================================
+// backward substep (after P2G + grid_fwd were recomputed for frame f)
+// ================================================================================================
+// g2p.grad: reads adjoint of (x,v,C)[f+1], scatters the adjoint of grid_out, writes the partial x-adjoint of frame f
+// into adj_cur.A0 (xyz lanes; the w lane is finished by p2g_bwd_body).
+template <class T>
+PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
+                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+    V3<T> x = load_x(in, p);
+    V3<T> gxn, gvn; M3<T> gCn;
+    load_xvC(adj_next, p, gxn, gvn, gCn);
+    Stencil<T> st = make_stencil(x, P.inv_dx);
+    // recompute new_v for the clamp masks of the advection
+    V3<T> nv = zero3<T>();
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
+                Vec4<T> g4 = grid_out[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
+                nv += w * mk3<T>(g4.x, g4.y, g4.z);
+            }
+    V3<T> gy = advect_backward(P, x, nv, gxn);
+    V3<T> gx = gy;
+    V3<T> gv = gvn + P.dt * gy;
+    T gw[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) gw[a][d] = T(0);
+    V3<T> gfx = zero3<T>();
+    const T c4 = T(4) * P.inv_dx;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
+                long long node = node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k);
+                Vec4<T> g4 = grid_out[node];
+                V3<T> gvn_ = mk3<T>(g4.x, g4.y, g4.z);
+                V3<T> dpos = mk3<T>(T(i) - st.fx.x, T(j) - st.fx.y, T(k) - st.fx.z);
+                V3<T> Cd = mv(gCn, dpos);                     // gC' dpos
+                V3<T> gg = w * (gv + c4 * Cd);                // adjoint of grid_out[node]
+                scatter_add4(g_out + node, mk4<T>(gg.x, gg.y, gg.z, T(0)));
+                T gwt = dot(gv, gvn_) + c4 * dot(gvn_, Cd);   // adjoint of the 3-D weight
+                V3<T> gd = (c4 * w) * mTv(gCn, gvn_);         // adjoint of dpos
+                gfx -= gd;
+                gw[i][0] += gwt * st.w[j][1] * st.w[k][2];
+                gw[j][1] += gwt * st.w[i][0] * st.w[k][2];
+                gw[k][2] += gwt * st.w[i][0] * st.w[j][1];
+            }
+    gx += stencil_backward(st, gw, gfx, P.inv_dx);
+    adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
+}
+
+// grid_op.grad for one node.  Reads grid_in (forward values) and g_out (adjoint of grid_out); writes g_in (adjoint of
+// grid_in).  Pose adjoints are returned through g0/g1/touched for the caller to reduce.
+template <class T>
+PLB_HD void grid_bwd_body(long long node, const SimConst<T>& P, const PrimSet<T>& prims, const Pose<T>* s0, const Pose<T>* s1,
+                          Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, bool clear,
+                          PoseGrad<T>* g0, PoseGrad<T>* g1, unsigned& touched) {
+    Vec4<T> in4 = grid_in[node];
+    Vec4<T> go = g_out[node];
+    const int n = P.n_grid;
+    int k = (int)(node % n), j = (int)((node / n) % n), i = (int)(node / ((long long)n * n));
+    Vec4<T> gi = grid_node_backward<T>(P, prims, s0, s1, i, j, k, in4, mk3<T>(go.x, go.y, go.z), g0, g1, touched);
+    g_in[node] = gi;
+    if (clear) {
+        if (in4.x != T(0) || in4.y != T(0) || in4.z != T(0) || in4.w != T(0)) grid_in[node] = mk4<T>(T(0), T(0), T(0), T(0));
+        if (go.x != T(0) || go.y != T(0) || go.z != T(0)) g_out[node] = mk4<T>(T(0), T(0), T(0), T(0));
+    }
+}
+
+// p2g.grad + svd_grad + compute_F_tmp.grad: gathers g_in at 27 nodes, finishes the adjoint of frame f in adj_cur.
+template <class T>
+PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
+                         const FramePtr<T>& adj_cur, const Material<T>& mat, const Vec4<T>* g_in) {
+    V3<T> x, v; M3<T> C;
+    load_xvC(in, p, x, v, C);
+    M3<T> F = load_F(in, p);
+    T mu, lam, ys;
+    load_material(P, mat, p, mu, lam, ys);
+    M3<T> new_F, affine;
+    P2GState<T> keep;
+    p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine, &keep);
+    Stencil<T> st = make_stencil(x, P.inv_dx);
+    V3<T> mvel = P.p_mass * v;
+    V3<T> gv = zero3<T>();
+    M3<T> g_aff = zeroM<T>();
+    T gw[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) gw[a][d] = T(0);
+    V3<T> gfx = zero3<T>();
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
+                Vec4<T> g4 = g_in[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
+                V3<T> a = mk3<T>(g4.x, g4.y, g4.z);
+                V3<T> dpos = mk3<T>((T(i) - st.fx.x) * P.dx, (T(j) - st.fx.y) * P.dx, (T(k) - st.fx.z) * P.dx);
+                T gwt = dot(a, mvel + mv(affine, dpos)) + g4.w * P.p_mass;
+                gv += w * a;
+                g_aff += w * outer(a, dpos);
+                V3<T> gd = w * mTv(affine, a);
+                gfx -= P.dx * gd;
+                gw[i][0] += gwt * st.w[j][1] * st.w[k][2];
+                gw[j][1] += gwt * st.w[i][0] * st.w[k][2];
+                gw[k][2] += gwt * st.w[i][0] * st.w[j][1];
+            }
+    gv = P.p_mass * gv;
+    V3<T> gx = stencil_backward(st, gw, gfx, P.inv_dx);
+    Vec4<T> part = adj_cur.A0[p];                           // partial x-adjoint from g2p_bwd_body
+    gx += mk3<T>(part.x, part.y, part.z);
+    M3<T> gF_next = load_F(adj_next, p);
+    M3<T> gC, gF;
+    p2g_particle_backward<T>(P, C, F, mu, lam, keep, g_aff, gF_next, gC, gF);
+    store_xvC(adj_cur, p, gx, gv, gC);
+    store_F(adj_cur, p, gF);
+}
+
+// ================================================================================================
+// loss (plb/engine/losses/loss.py:116-153,186-237 ; mpm_simulator.py:382-392)
+// ================================================================================================
+template <class T>
+PLB_HD void loss_mass_body(int p, const SimConst<T>& P, const FramePtr<T>& in, T* grid_mass) {
+    V3<T> x = load_x(in, p);
+    Stencil<T> st = make_stencil(x, P.inv_dx);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
+                scatter_add1(grid_mass + node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k), w * P.p_mass);
+            }
+}
+
+struct LossWeights { double sdf, density, contact; int soft; };
+
+// Adjoint of the per-step loss wrt x[f] (added into adj.A0 xyz) and the primitive poses of frame f.
+// min_dist[k] (forward value of primitive k's min distance) seeds the contact term; with the reference's
+// atomic-min-as-add autodiff every particle with sdf > 0 receives 2 * min_dist * w_contact (contact_all = 1),
+// contact_all = 0 restricts it to the arg-min particle(s) (d == min_dist).
+template <class T>
+PLB_HD void loss_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj,
+                          const T* grid_mass, const T* target, const T* target_sdf, T w_sdf, T w_density, T w_contact,
+                          const PrimSet<T>& prims, const Pose<T>* s0, const double* min_dist, int contact_all,
+                          PoseGrad<T>* gpose, unsigned& touched) {
+    V3<T> x = load_x(in, p);
+    Stencil<T> st = make_stencil(x, P.inv_dx);
+    T gw[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) gw[a][d] = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                long long node = node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k);
+                T diff = grid_mass[node] - target[node];
+                T gm = w_density * sgn0(diff) + w_sdf * target_sdf[node];
+                T gwt = gm * P.p_mass;
+                gw[i][0] += gwt * st.w[j][1] * st.w[k][2];
+                gw[j][1] += gwt * st.w[i][0] * st.w[k][2];
+                gw[k][2] += gwt * st.w[i][0] * st.w[j][1];
+            }
+    V3<T> gx = stencil_backward(st, gw, zero3<T>(), P.inv_dx);
+    touched = 0;
+    for (int k = 0; k < P.n_prim; k++) {
+        if (!prims.s[k].movable) continue;
+        T d = prim_sdf(prims.s[k], s0[k], x);
+        if (!(T(0) < d)) continue;                           // max(sdf, 0): gradient only where 0 < sdf
+        T md = (T)min_dist[k];
+        if (!contact_all && d > md) continue;
+        T g = T(2) * md * w_contact;
+        if (g != T(0)) {
+            prim_sdf_vjp(prims.s[k], s0[k], x, g, gpose[k], &gx);
+            touched |= 1u << k;
+        }
+    }
+    Vec4<T> a0 = adj.A0[p];
+    adj.A0[p] = mk4<T>(a0.x + gx.x, a0.y + gx.y, a0.z + gx.z, a0.w);
+}
+
+}  // namespace plb

@@ -1,0 +1,644 @@
+// Engine object + C ABI (include/plb_b200.h).  Owns every device buffer, the primitive trajectories (host f64,
+// mirrored on the device) and the launch sequence of a forward / backward substep.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+#include "../../include/plb_b200.h"
+#include "plb_kernels.cuh"
+#include "plb_kinematics.hpp"
+#include "plb_setup.hpp"
+
+using namespace plb;
+
+static std::string g_create_error;
+
+#define PLB_CUDA(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            err = std::string(#expr) + ": " + cudaGetErrorString(_e);                                \
+            return PLB_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+#define PLB_REQUIRE(cond, msg)                                                                       \
+    do {                                                                                             \
+        if (!(cond)) { err = std::string(msg) + " [" #cond "]"; return PLB_ERR_INVALID; }            \
+    } while (0)
+
+enum KernelId { K_P2G = 0, K_GRID_FWD, K_G2P, K_P2G_RECOMPUTE, K_GRID_FWD_RECOMPUTE, K_G2P_BWD, K_GRID_BWD, K_P2G_BWD,
+                K_LOSS_FWD, K_LOSS_BWD, K_MISC, K_COUNT };
+static const char* kKernelNames[K_COUNT] = {"p2g", "grid_fwd", "g2p", "p2g_recompute", "grid_fwd_recompute", "g2p_bwd", "grid_bwd",
+                                            "p2g_bwd", "loss_fwd", "loss_bwd", "misc"};
+
+struct plb_engine {
+    std::string err;
+    // optional per-launch CUDA-event timing (bench.py's live roofline numbers); off by default
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_kid;
+    size_t prof_used = 0;
+    double prof_ms[K_COUNT] = {0};
+    long long prof_cnt[K_COUNT] = {0};
+    cudaStream_t prof_stream = 0;
+    void prof_begin(int kid) {
+        if (!prof_on) return;
+        if (prof_used * 2 + 2 > prof_ev.size()) {
+            size_t old = prof_ev.size();
+            prof_ev.resize(old + 8192);
+            for (size_t i = old; i < prof_ev.size(); i++) cudaEventCreate(&prof_ev[i]);
+        }
+        if (prof_kid.size() <= prof_used) prof_kid.resize(prof_used + 4096);
+        prof_kid[prof_used] = kid;
+        cudaEventRecord(prof_ev[prof_used * 2], prof_stream);
+    }
+    void prof_end() {
+        if (!prof_on) return;
+        cudaEventRecord(prof_ev[prof_used * 2 + 1], prof_stream);
+        prof_used++;
+    }
+    void prof_collect() {
+        cudaStreamSynchronize(prof_stream);
+        for (size_t i = 0; i < prof_used; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, prof_ev[i * 2], prof_ev[i * 2 + 1]);
+            prof_ms[prof_kid[i]] += ms;
+            prof_cnt[prof_kid[i]]++;
+        }
+        prof_used = 0;
+    }
+    virtual ~plb_engine() {}
+    virtual int init(const plb_config& c, const plb_primitive_desc* prims) = 0;
+    virtual int set_materials(const double* mu, const double* lam, const double* ys) = 0;
+    virtual int set_frame(int slot, const double* x, const double* v, const double* F, const double* C) = 0;
+    virtual int get_frame(int slot, double* x, double* v, double* F, double* C) = 0;
+    virtual int copy_frame(int src, int dst) = 0;
+    virtual int frame_ptr(int slot, void** ptr, long long* n_pad, int* sb) = 0;
+    virtual int set_prim_state(int pf, int k, const double* s) = 0;
+    virtual int get_prim_state(int pf, int k, double* s) = 0;
+    virtual int copy_prim_frame(int src, int dst) = 0;
+    virtual int set_softness(double s) = 0;
+    virtual int set_action(int step, int S, const double* a, int n) = 0;
+    virtual int kinematics(int pf, int n) = 0;
+    virtual int substep_fwd(int si, int so, int pf) = 0;
+    virtual int substep_bwd(int si, int pf) = 0;
+    virtual int zero_grads() = 0;
+    virtual int set_adjoint(const double* gx, const double* gv, const double* gF, const double* gC) = 0;
+    virtual int get_adjoint(double* gx, double* gv, double* gF, double* gC) = 0;
+    virtual int get_prim_grads(int pf0, int n, double* out) = 0;
+    virtual int get_action_grad(int n_steps, int S, double* out) = 0;
+    virtual int set_target(const double* density, const double* sdf) = 0;
+    virtual int get_target_sdf(double* sdf) = 0;
+    virtual int set_loss_weights(double sdf, double density, double contact, int soft, int all) = 0;
+    virtual int loss_fwd(int slot, int pf, double* out8) = 0;
+    virtual int loss_bwd(int slot, int pf) = 0;
+    virtual int get_loss(double* v) = 0;
+    virtual int clear_loss() = 0;
+    virtual int debug_get_grid(double* in4, double* out4) = 0;
+    virtual int count_active(int slot, long long* n) = 0;
+    virtual int set_stream(void* s) = 0;
+    virtual int synchronize() = 0;
+    long long launches = 0;
+};
+
+template <class T>
+struct Engine : plb_engine {
+    plb_config cfg{};
+    SimConst<T> P{};
+    PrimSet<T> prims{};
+    std::vector<kin::Desc> kdesc;
+    std::vector<plb_primitive_desc> pdesc;
+    cudaStream_t stream = 0;
+    long long n_pad = 0, n_nodes = 0;
+    int action_total = 0;
+    std::vector<int> action_off;
+
+    // device buffers
+    T* frames = nullptr;            // [max_frames][24][n_pad]
+    T* adj[2] = {nullptr, nullptr}; // ping-pong adjoint frames; adj[cur] holds the adjoint of frame `adj_frame`
+    int cur = 0;
+    Vec4<T>* grid_in = nullptr;     // (momentum, mass); zero between substeps
+    Vec4<T>* grid_out = nullptr;    // velocity after the grid operator
+    Vec4<T>* g_out = nullptr;       // adjoint of grid_out; zero between substeps
+    Vec4<T>* g_in = nullptr;        // adjoint of grid_in
+    T* mat_mu = nullptr; T* mat_lam = nullptr; T* mat_ys = nullptr;
+    T* grid_mass = nullptr; T* target = nullptr; T* target_sdf = nullptr;
+    double* d_stage = nullptr;      // staging for host<->device f64 AoS frames: 24 * n doubles
+    double* d_traj = nullptr;       // [max_prim_frames][PLB_MAX_PRIM][8]
+    double* d_prim_grad = nullptr;  // same shape
+    double* d_acc = nullptr;        // loss accumulators (kAccN) + [kAccN] running loss + [kAccN+1 ..] record(8)
+    unsigned long long* d_count = nullptr;
+    bool has_target = false;
+    double target_max = 0, target_sum = 0;
+    LossWeights lw{10.0, 10.0, 1.0, 0};
+    int contact_all = 1;
+
+    // host mirrors
+    std::vector<double> traj;       // poses
+    std::vector<double> vel;        // per frame per prim: v(3) w(3) gv(1) pad -> 8
+    std::vector<double> actions;    // per env step: action_total
+    int max_steps_actions = 0;
+
+    ~Engine() override {
+        cudaFree(frames); cudaFree(adj[0]); cudaFree(adj[1]); cudaFree(grid_in); cudaFree(grid_out); cudaFree(g_out);
+        cudaFree(g_in); cudaFree(mat_mu); cudaFree(mat_lam); cudaFree(mat_ys); cudaFree(grid_mass); cudaFree(target);
+        cudaFree(target_sdf); cudaFree(d_stage); cudaFree(d_traj); cudaFree(d_prim_grad); cudaFree(d_acc); cudaFree(d_count);
+    }
+
+    int blocks(long long n, int b = kBlock) const { return (int)((n + b - 1) / b); }
+    Material<T> material() const { Material<T> m; m.mu = mat_mu; m.lam = mat_lam; m.ys = mat_ys; return m; }
+    T* frame_base(int slot) const { return frames + (long long)slot * 24 * n_pad; }
+
+    int init(const plb_config& c, const plb_primitive_desc* pd) override {
+        cfg = c;
+        PLB_REQUIRE(c.n_particles > 0 && c.n_grid >= 8 && c.max_frames >= 2 && c.max_prim_frames >= 2, "bad sizes");
+        PLB_REQUIRE(c.n_primitives >= 0 && c.n_primitives <= PLB_MAX_PRIM, "too many primitives");
+        PLB_CUDA(cudaSetDevice(c.device));
+        n_pad = ((long long)c.n_particles + 31) / 32 * 32;
+        n_nodes = (long long)c.n_grid * c.n_grid * c.n_grid;
+        P = make_simconst<T>(c);
+
+        action_off.assign(1, 0);
+        traj.assign((size_t)c.max_prim_frames * PLB_MAX_PRIM * 8, 0.0);
+        vel.assign((size_t)c.max_prim_frames * PLB_MAX_PRIM * 8, 0.0);
+        for (int k = 0; k < c.n_primitives; k++) {
+            const plb_primitive_desc& d = pd[k];
+            pdesc.push_back(d);
+            prims.s[k] = make_primstatic<T>(d, 0.0);
+            kdesc.push_back(make_kindesc(d));
+            action_off.push_back(action_off.back() + d.action_dim);
+            for (int i = 0; i < 8; i++) traj[(size_t)k * 8 + i] = d.init_state[i];
+        }
+        action_total = action_off.back();
+        max_steps_actions = c.max_prim_frames;
+        actions.assign((size_t)max_steps_actions * std::max(action_total, 1), 0.0);
+
+        size_t fbytes = (size_t)c.max_frames * 24 * n_pad * sizeof(T);
+        PLB_CUDA(cudaMalloc(&frames, fbytes));
+        PLB_CUDA(cudaMemset(frames, 0, fbytes));
+        for (int i = 0; i < 2; i++) {
+            PLB_CUDA(cudaMalloc(&adj[i], (size_t)24 * n_pad * sizeof(T)));
+            PLB_CUDA(cudaMemset(adj[i], 0, (size_t)24 * n_pad * sizeof(T)));
+        }
+        size_t gbytes = (size_t)n_nodes * sizeof(Vec4<T>);
+        PLB_CUDA(cudaMalloc(&grid_in, gbytes));  PLB_CUDA(cudaMemset(grid_in, 0, gbytes));
+        PLB_CUDA(cudaMalloc(&grid_out, gbytes)); PLB_CUDA(cudaMemset(grid_out, 0, gbytes));
+        PLB_CUDA(cudaMalloc(&g_out, gbytes));    PLB_CUDA(cudaMemset(g_out, 0, gbytes));
+        PLB_CUDA(cudaMalloc(&g_in, gbytes));     PLB_CUDA(cudaMemset(g_in, 0, gbytes));
+        PLB_CUDA(cudaMalloc(&grid_mass, n_nodes * sizeof(T)));
+        PLB_CUDA(cudaMalloc(&target, n_nodes * sizeof(T)));       PLB_CUDA(cudaMemset(target, 0, n_nodes * sizeof(T)));
+        PLB_CUDA(cudaMalloc(&target_sdf, n_nodes * sizeof(T)));   PLB_CUDA(cudaMemset(target_sdf, 0, n_nodes * sizeof(T)));
+        PLB_CUDA(cudaMalloc(&d_stage, (size_t)24 * c.n_particles * sizeof(double)));
+        size_t tb = traj.size() * sizeof(double);
+        PLB_CUDA(cudaMalloc(&d_traj, tb));
+        PLB_CUDA(cudaMemcpy(d_traj, traj.data(), tb, cudaMemcpyHostToDevice));
+        PLB_CUDA(cudaMalloc(&d_prim_grad, tb));
+        PLB_CUDA(cudaMemset(d_prim_grad, 0, tb));
+        PLB_CUDA(cudaMalloc(&d_acc, (kAccN + 1 + 8) * sizeof(double)));
+        PLB_CUDA(cudaMemset(d_acc, 0, (kAccN + 1 + 8) * sizeof(double)));
+        PLB_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
+        return PLB_OK;
+    }
+
+    int set_stream(void* s) override { stream = (cudaStream_t)s; prof_stream = stream; return PLB_OK; }
+    int synchronize() override { PLB_CUDA(cudaStreamSynchronize(stream)); return PLB_OK; }
+
+    int check_slot(int s) { PLB_REQUIRE(s >= 0 && s < cfg.max_frames, "frame slot out of range"); return PLB_OK; }
+    int check_pf(int pf, int extra = 0) { PLB_REQUIRE(pf >= 0 && pf + extra < cfg.max_prim_frames, "primitive frame out of range"); return PLB_OK; }
+
+    int set_materials(const double* mu, const double* lam, const double* ys) override {
+        const double* src[3] = {mu, lam, ys};
+        T** dst[3] = {&mat_mu, &mat_lam, &mat_ys};
+        for (int i = 0; i < 3; i++) {
+            if (!src[i]) continue;
+            if (!*dst[i]) PLB_CUDA(cudaMalloc(dst[i], n_pad * sizeof(T)));
+            PLB_CUDA(cudaMemcpyAsync(d_stage, src[i], cfg.n_particles * sizeof(double), cudaMemcpyHostToDevice, stream));
+            k_convert<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, d_stage, *dst[i]);
+            launches++;
+            PLB_CUDA(cudaStreamSynchronize(stream));
+        }
+        return PLB_OK;
+    }
+
+    int upload_aos(const double* x, const double* v, const double* F, const double* C, double** dx, double** dv, double** dF, double** dC) {
+        size_t n = cfg.n_particles;
+        *dx = x ? d_stage : nullptr; *dv = v ? d_stage + 3 * n : nullptr;
+        *dF = F ? d_stage + 6 * n : nullptr; *dC = C ? d_stage + 15 * n : nullptr;
+        if (x) PLB_CUDA(cudaMemcpyAsync(*dx, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (v) PLB_CUDA(cudaMemcpyAsync(*dv, v, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (F) PLB_CUDA(cudaMemcpyAsync(*dF, F, 9 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (C) PLB_CUDA(cudaMemcpyAsync(*dC, C, 9 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        return PLB_OK;
+    }
+    int download_aos(T* frame, double* x, double* v, double* F, double* C) {
+        size_t n = cfg.n_particles;
+        double *dx = x ? d_stage : nullptr, *dv = v ? d_stage + 3 * n : nullptr, *dF = F ? d_stage + 6 * n : nullptr,
+               *dC = C ? d_stage + 15 * n : nullptr;
+        k_unpack_frame<T><<<blocks(n), kBlock, 0, stream>>>((int)n, n_pad, frame, dx, dv, dF, dC);
+        launches++;
+        if (x) PLB_CUDA(cudaMemcpyAsync(x, dx, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (v) PLB_CUDA(cudaMemcpyAsync(v, dv, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (F) PLB_CUDA(cudaMemcpyAsync(F, dF, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (C) PLB_CUDA(cudaMemcpyAsync(C, dC, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        return PLB_OK;
+    }
+
+    int set_frame(int slot, const double* x, const double* v, const double* F, const double* C) override {
+        if (int r = check_slot(slot)) return r;
+        double *dx, *dv, *dF, *dC;
+        if (int r = upload_aos(x, v, F, C, &dx, &dv, &dF, &dC)) return r;
+        k_pack_frame<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, n_pad, frame_base(slot), dx, dv, dF, dC);
+        launches++;
+        PLB_CUDA(cudaStreamSynchronize(stream));      // the host arrays may be reused by the caller
+        return PLB_OK;
+    }
+    int get_frame(int slot, double* x, double* v, double* F, double* C) override {
+        if (int r = check_slot(slot)) return r;
+        return download_aos(frame_base(slot), x, v, F, C);
+    }
+    int copy_frame(int src, int dst) override {
+        if (int r = check_slot(src)) return r;
+        if (int r = check_slot(dst)) return r;
+        if (src == dst) return PLB_OK;
+        PLB_CUDA(cudaMemcpyAsync(frame_base(dst), frame_base(src), (size_t)24 * n_pad * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        return PLB_OK;
+    }
+    int frame_ptr(int slot, void** ptr, long long* np, int* sb) override {
+        if (int r = check_slot(slot)) return r;
+        *ptr = frame_base(slot); *np = n_pad; *sb = (int)sizeof(T);
+        return PLB_OK;
+    }
+
+    // ---------------------------------------------------------------- primitives
+    double* pose(int pf, int k) { return traj.data() + ((size_t)pf * PLB_MAX_PRIM + k) * 8; }
+    double* velo(int pf, int k) { return vel.data() + ((size_t)pf * PLB_MAX_PRIM + k) * 8; }
+    int upload_poses(int pf0, int n) {
+        size_t off = (size_t)pf0 * PLB_MAX_PRIM * 8;
+        PLB_CUDA(cudaMemcpyAsync(d_traj + off, traj.data() + off, (size_t)n * PLB_MAX_PRIM * 8 * sizeof(double),
+                                 cudaMemcpyHostToDevice, stream));
+        return PLB_OK;
+    }
+    int set_prim_state(int pf, int k, const double* s) override {
+        if (int r = check_pf(pf)) return r;
+        PLB_REQUIRE(k >= 0 && k < cfg.n_primitives, "primitive index");
+        std::memcpy(pose(pf, k), s, 8 * sizeof(double));
+        return upload_poses(pf, 1);
+    }
+    int get_prim_state(int pf, int k, double* s) override {
+        if (int r = check_pf(pf)) return r;
+        PLB_REQUIRE(k >= 0 && k < cfg.n_primitives, "primitive index");
+        std::memcpy(s, pose(pf, k), 8 * sizeof(double));
+        return PLB_OK;
+    }
+    int copy_prim_frame(int src, int dst) override {
+        if (int r = check_pf(src)) return r;
+        if (int r = check_pf(dst)) return r;
+        std::memcpy(pose(dst, 0), pose(src, 0), PLB_MAX_PRIM * 8 * sizeof(double));
+        return upload_poses(dst, 1);
+    }
+    int set_softness(double s) override {
+        for (int k = 0; k < cfg.n_primitives; k++) prims.s[k].softness = (T)s;
+        return PLB_OK;
+    }
+    int set_action(int step, int S, const double* a, int n) override {
+        PLB_REQUIRE(n == action_total, "action length != sum of action dims");
+        PLB_REQUIRE(step >= 0 && step < max_steps_actions && S > 0, "bad step");
+        if (int r = check_pf((step + 1) * S - 1)) return r;
+        for (int i = 0; i < n; i++) actions[(size_t)step * action_total + i] = std::min(1.0, std::max(-1.0, a[i]));
+        for (int k = 0; k < cfg.n_primitives; k++) {
+            const kin::Desc& d = kdesc[k];
+            if (d.action_dim == 0) continue;
+            const double* ak = &actions[(size_t)step * action_total + action_off[k]];
+            for (int f = step * S; f < (step + 1) * S; f++) {
+                double* vv = velo(f, k);
+                for (int i = 0; i < 3; i++) vv[i] = ak[i] * d.action_scale[i] / S;
+                if (d.action_dim > 3) for (int i = 0; i < 3; i++) vv[3 + i] = ak[3 + i] * d.action_scale[3 + i] / S;
+                if (d.type == PRIM_CHOPSTICKS) vv[6] = ak[6] * d.action_scale[6] / S;
+            }
+        }
+        return PLB_OK;
+    }
+    int kinematics(int pf, int n) override {
+        if (int r = check_pf(pf, n)) return r;
+        for (int f = pf; f < pf + n; f++)
+            for (int k = 0; k < cfg.n_primitives; k++) {
+                const double* vv = velo(f, k);
+                kin::fk_forward(kdesc[k], pose(f, k), vv, vv + 3, vv[6], pose(f + 1, k));
+            }
+        return upload_poses(pf + 1, n);
+    }
+
+    // ---------------------------------------------------------------- substeps
+    int substep_fwd(int si, int so, int pf) override {
+        if (int r = check_slot(si)) return r;
+        if (int r = check_slot(so)) return r;
+        if (int r = check_pf(pf, 1)) return r;
+        PLB_REQUIRE(si != so, "in-place substep");
+        int nb = blocks(cfg.n_particles);
+        prof_begin(K_P2G);
+        k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in);
+        prof_end(); prof_begin(K_GRID_FWD);
+        k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
+        prof_end(); prof_begin(K_G2P);
+        k_g2p<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, grid_out);
+        prof_end();
+        launches += 3;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    int substep_bwd(int si, int pf) override {
+        if (int r = check_slot(si)) return r;
+        if (int r = check_pf(pf, 1)) return r;
+        int nb = blocks(cfg.n_particles), ng = blocks(n_nodes);
+        T* a_next = adj[cur];
+        T* a_cur = adj[cur ^ 1];
+        prof_begin(K_P2G_RECOMPUTE);
+        k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in);
+        prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
+        k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
+        prof_end(); prof_begin(K_G2P_BWD);
+        k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
+        prof_end(); prof_begin(K_GRID_BWD);
+        k_grid_bwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, n_nodes);
+        prof_end(); prof_begin(K_P2G_BWD);
+        k_p2g_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in);
+        prof_end();
+        launches += 5;
+        cur ^= 1;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+
+    // ---------------------------------------------------------------- adjoint bookkeeping
+    int zero_grads() override {
+        PLB_CUDA(cudaMemsetAsync(adj[0], 0, (size_t)24 * n_pad * sizeof(T), stream));
+        PLB_CUDA(cudaMemsetAsync(adj[1], 0, (size_t)24 * n_pad * sizeof(T), stream));
+        PLB_CUDA(cudaMemsetAsync(d_prim_grad, 0, traj.size() * sizeof(double), stream));
+        PLB_CUDA(cudaMemsetAsync(d_acc + kAccN, 0, sizeof(double), stream));
+        return PLB_OK;
+    }
+    int set_adjoint(const double* gx, const double* gv, const double* gF, const double* gC) override {
+        double *dx, *dv, *dF, *dC;
+        if (int r = upload_aos(gx, gv, gF, gC, &dx, &dv, &dF, &dC)) return r;
+        k_pack_frame<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, n_pad, adj[cur], dx, dv, dF, dC);
+        launches++;
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        return PLB_OK;
+    }
+    int get_adjoint(double* gx, double* gv, double* gF, double* gC) override { return download_aos(adj[cur], gx, gv, gF, gC); }
+    int get_prim_grads(int pf0, int n, double* out) override {
+        if (int r = check_pf(pf0, n - 1)) return r;
+        std::vector<double> tmp((size_t)n * PLB_MAX_PRIM * 8);
+        PLB_CUDA(cudaMemcpyAsync(tmp.data(), d_prim_grad + (size_t)pf0 * PLB_MAX_PRIM * 8, tmp.size() * sizeof(double),
+                                 cudaMemcpyDeviceToHost, stream));
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        for (int f = 0; f < n; f++)
+            for (int k = 0; k < cfg.n_primitives; k++)
+                std::memcpy(out + ((size_t)f * cfg.n_primitives + k) * 8, tmp.data() + ((size_t)f * PLB_MAX_PRIM + k) * 8, 8 * sizeof(double));
+        return PLB_OK;
+    }
+    int get_action_grad(int n_steps, int S, double* out) override {
+        int nf = n_steps * S;
+        if (int r = check_pf(nf)) return r;
+        std::vector<double> g((size_t)(nf + 1) * PLB_MAX_PRIM * 8);
+        PLB_CUDA(cudaMemcpyAsync(g.data(), d_prim_grad, g.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        std::fill(out, out + (size_t)n_steps * action_total, 0.0);
+        for (int f = nf - 1; f >= 0; f--) {
+            int step = f / S;
+            for (int k = cfg.n_primitives - 1; k >= 0; k--) {
+                const kin::Desc& d = kdesc[k];
+                const double* vv = velo(f, k);
+                double* gnext = &g[((size_t)(f + 1) * PLB_MAX_PRIM + k) * 8];
+                double* gcur = &g[((size_t)f * PLB_MAX_PRIM + k) * 8];
+                double gvel[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, ggv = 0;
+                kin::fk_backward(d, pose(f, k), vv, vv + 3, vv[6], gnext, gcur, gvel, gw, ggv);
+                if (d.action_dim == 0) continue;
+                double* o = out + (size_t)step * action_total + action_off[k];
+                for (int i = 0; i < 3; i++) o[i] += gvel[i] * d.action_scale[i] / S;
+                if (d.action_dim > 3) for (int i = 0; i < 3; i++) o[3 + i] += gw[i] * d.action_scale[3 + i] / S;
+                if (d.type == PRIM_CHOPSTICKS) o[6] += ggv * d.action_scale[6] / S;
+            }
+        }
+        return PLB_OK;
+    }
+
+    // ---------------------------------------------------------------- loss
+    int set_target(const double* density, const double* sdf) override {
+        PLB_REQUIRE(density != nullptr, "density is NULL");
+        double *d_den = nullptr, *d_sdf[2] = {nullptr, nullptr}, *d_near[2] = {nullptr, nullptr};
+        int* d_changed = nullptr;
+        int rc = PLB_OK;
+        auto cleanup = [&]() { cudaFree(d_den); cudaFree(d_sdf[0]); cudaFree(d_sdf[1]); cudaFree(d_near[0]); cudaFree(d_near[1]); cudaFree(d_changed); };
+        PLB_CUDA(cudaMalloc(&d_den, n_nodes * sizeof(double)));
+        PLB_CUDA(cudaMemcpy(d_den, density, n_nodes * sizeof(double), cudaMemcpyHostToDevice));
+        k_convert<T><<<blocks(n_nodes), kBlock, 0, stream>>>(n_nodes, d_den, target);
+        launches++;
+        target_max = 0; target_sum = 0;
+        for (long long i = 0; i < n_nodes; i++) { target_max = std::max(target_max, density[i]); target_sum += density[i]; }
+        if (cudaMalloc(&d_sdf[0], n_nodes * sizeof(double)) != cudaSuccess) { cleanup(); err = "cudaMalloc sdf"; return PLB_ERR_NOMEM; }
+        if (sdf) {
+            cudaMemcpy(d_sdf[0], sdf, n_nodes * sizeof(double), cudaMemcpyHostToDevice);
+            k_convert<T><<<blocks(n_nodes), kBlock, 0, stream>>>(n_nodes, d_sdf[0], target_sdf);
+            launches++;
+        } else {
+            if (cudaMalloc(&d_sdf[1], n_nodes * sizeof(double)) != cudaSuccess || cudaMalloc(&d_near[0], 3 * n_nodes * sizeof(double)) != cudaSuccess ||
+                cudaMalloc(&d_near[1], 3 * n_nodes * sizeof(double)) != cudaSuccess || cudaMalloc(&d_changed, sizeof(int)) != cudaSuccess) {
+                cleanup(); err = "cudaMalloc sdf sweep"; return PLB_ERR_NOMEM;
+            }
+            std::vector<double> inf((size_t)n_nodes, 1000.0);
+            cudaMemcpy(d_sdf[0], inf.data(), n_nodes * sizeof(double), cudaMemcpyHostToDevice);
+            cudaMemset(d_near[0], 0, 3 * n_nodes * sizeof(double));
+            int c = 0;
+            for (int it = 0; it < 2 * cfg.n_grid; it++) {
+                cudaMemsetAsync(d_changed, 0, sizeof(int), stream);
+                k_sdf_sweep<<<blocks(n_nodes, 128), 128, 0, stream>>>(cfg.n_grid, cfg.dx, d_den, d_sdf[c], d_near[c], d_sdf[c ^ 1], d_near[c ^ 1], d_changed);
+                launches++;
+                int changed = 1;
+                cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, stream);
+                cudaStreamSynchronize(stream);
+                c ^= 1;
+                if (!changed) break;     // fixed point: further sweeps are identities
+            }
+            k_convert<T><<<blocks(n_nodes), kBlock, 0, stream>>>(n_nodes, d_sdf[c], target_sdf);
+            launches++;
+        }
+        cudaError_t e = cudaStreamSynchronize(stream);
+        cleanup();
+        if (e != cudaSuccess) { err = cudaGetErrorString(e); return PLB_ERR_CUDA; }
+        has_target = true;
+        return rc;
+    }
+    int get_target_sdf(double* sdf) override {
+        std::vector<T> tmp((size_t)n_nodes);
+        PLB_CUDA(cudaMemcpy(tmp.data(), target_sdf, n_nodes * sizeof(T), cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < n_nodes; i++) sdf[i] = (double)tmp[i];
+        return PLB_OK;
+    }
+    int set_loss_weights(double sdf, double density, double contact, int soft, int all) override {
+        if (soft) { err = "soft contact loss is not implemented in the CUDA engine yet"; return PLB_ERR_UNSUPPORTED; }
+        lw.sdf = sdf; lw.density = density; lw.contact = contact; lw.soft = soft; contact_all = all;
+        return PLB_OK;
+    }
+    int loss_terms(int slot, int pf) {
+        int nb = blocks(cfg.n_particles);
+        k_loss_init<<<1, 32, 0, stream>>>(d_acc);
+        PLB_CUDA(cudaMemsetAsync(grid_mass, 0, n_nodes * sizeof(T), stream));
+        k_loss_mass<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
+        int rb = (int)std::min<long long>((n_nodes + 255) / 256, 148 * 8);
+        k_loss_reduce<T><<<rb, 256, 0, stream>>>(grid_mass, target, target_sdf, n_nodes, d_acc);
+        k_loss_contact<T><<<nb, kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, d_acc);
+        launches += 4;
+        return PLB_OK;
+    }
+    int loss_fwd(int slot, int pf, double* out8) override {
+        if (int r = check_slot(slot)) return r;
+        if (int r = check_pf(pf)) return r;
+        PLB_REQUIRE(has_target, "no target density set");
+        prof_begin(K_LOSS_FWD);
+        if (int r = loss_terms(slot, pf)) return r;
+        k_loss_finalize<T><<<1, 1, 0, stream>>>(prims, cfg.n_primitives, lw, d_acc, target_max, target_sum, d_acc + kAccN, d_acc + kAccN + 1);
+        prof_end();
+        launches++;
+        PLB_CUDA(cudaGetLastError());
+        if (out8) {
+            PLB_CUDA(cudaMemcpyAsync(out8, d_acc + kAccN + 1, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            PLB_CUDA(cudaStreamSynchronize(stream));
+        }
+        return PLB_OK;
+    }
+    int loss_bwd(int slot, int pf) override {
+        if (int r = check_slot(slot)) return r;
+        if (int r = check_pf(pf)) return r;
+        PLB_REQUIRE(has_target, "no target density set");
+        prof_begin(K_LOSS_BWD);
+        if (int r = loss_terms(slot, pf)) return r;
+        k_loss_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, adj[cur], grid_mass, target,
+                                                                      target_sdf, lw, d_acc, contact_all, d_prim_grad);
+        prof_end();
+        launches++;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    int get_loss(double* v) override {
+        PLB_CUDA(cudaMemcpyAsync(v, d_acc + kAccN, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        return PLB_OK;
+    }
+    int clear_loss() override { PLB_CUDA(cudaMemsetAsync(d_acc + kAccN, 0, sizeof(double), stream)); return PLB_OK; }
+
+    // ---------------------------------------------------------------- debug
+    int debug_get_grid(double* in4, double* out4) override {
+        double* tmp = nullptr;
+        PLB_CUDA(cudaMalloc(&tmp, n_nodes * 4 * sizeof(double)));
+        const Vec4<T>* src[2] = {grid_in, grid_out};
+        double* dst[2] = {in4, out4};
+        for (int i = 0; i < 2; i++) {
+            if (!dst[i]) continue;
+            k_grid_to_double<T><<<blocks(n_nodes), kBlock, 0, stream>>>(n_nodes, src[i], tmp);
+            launches++;
+            cudaMemcpyAsync(dst[i], tmp, n_nodes * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+            cudaStreamSynchronize(stream);
+        }
+        cudaFree(tmp);
+        return PLB_OK;
+    }
+    int count_active(int slot, long long* n) override {
+        if (int r = check_slot(slot)) return r;
+        // scatter this frame's particles (no F store), count, then clear grid_in again
+        k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, slot, 0, material(), grid_in);
+        PLB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
+        k_count_active<T><<<blocks(n_nodes), kBlock, 0, stream>>>(n_nodes, grid_in, d_count);
+        launches += 2;
+        unsigned long long c = 0;
+        PLB_CUDA(cudaMemcpyAsync(&c, d_count, sizeof(c), cudaMemcpyDeviceToHost, stream));
+        PLB_CUDA(cudaMemsetAsync(grid_in, 0, n_nodes * sizeof(Vec4<T>), stream));
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        *n = (long long)c;
+        return PLB_OK;
+    }
+};
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int plb_abi_version(void) { return 1; }
+
+int plb_create(const plb_config* cfg, const plb_primitive_desc* prims, plb_engine** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return PLB_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(ce) +
+                         " (this engine has no CPU fallback)";
+        return PLB_ERR_CUDA;
+    }
+    plb_engine* e = nullptr;
+    if (cfg->dtype == PLB_F32) e = new Engine<float>();
+    else if (cfg->dtype == PLB_F64) e = new Engine<double>();
+    else { g_create_error = "dtype must be PLB_F32 or PLB_F64"; return PLB_ERR_INVALID; }
+    int r = e->init(*cfg, prims);
+    if (r != PLB_OK) { g_create_error = e->err; delete e; return r; }
+    *out = e;
+    return PLB_OK;
+}
+int plb_destroy(plb_engine* e) { delete e; return PLB_OK; }
+const char* plb_last_error(const plb_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+int plb_set_stream(plb_engine* e, void* s) { return e->set_stream(s); }
+int plb_synchronize(plb_engine* e) { return e->synchronize(); }
+int plb_set_materials(plb_engine* e, const double* mu, const double* lam, const double* ys) { return e->set_materials(mu, lam, ys); }
+int plb_set_frame(plb_engine* e, int slot, const double* x, const double* v, const double* F, const double* C) { return e->set_frame(slot, x, v, F, C); }
+int plb_get_frame(plb_engine* e, int slot, double* x, double* v, double* F, double* C) { return e->get_frame(slot, x, v, F, C); }
+int plb_copy_frame(plb_engine* e, int s, int d) { return e->copy_frame(s, d); }
+int plb_frame_device_ptr(plb_engine* e, int slot, void** ptr, long long* n_pad, int* sb) { return e->frame_ptr(slot, ptr, n_pad, sb); }
+int plb_set_primitive_state(plb_engine* e, int pf, int k, const double* s) { return e->set_prim_state(pf, k, s); }
+int plb_get_primitive_state(plb_engine* e, int pf, int k, double* s) { return e->get_prim_state(pf, k, s); }
+int plb_copy_primitive_frame(plb_engine* e, int s, int d) { return e->copy_prim_frame(s, d); }
+int plb_set_softness(plb_engine* e, double s) { return e->set_softness(s); }
+int plb_set_action(plb_engine* e, int step, int S, const double* a, int n) { return e->set_action(step, S, a, n); }
+int plb_kinematics(plb_engine* e, int pf, int n) { return e->kinematics(pf, n); }
+int plb_substep_fwd(plb_engine* e, int si, int so, int pf) { return e->substep_fwd(si, so, pf); }
+int plb_step_fwd(plb_engine* e, int slot0, int pf0, int n) {
+    for (int i = 0; i < n; i++) { int r = e->substep_fwd(slot0 + i, slot0 + i + 1, pf0 + i); if (r) return r; }
+    return PLB_OK;
+}
+int plb_substep_bwd(plb_engine* e, int si, int pf) { return e->substep_bwd(si, pf); }
+int plb_step_bwd(plb_engine* e, int slot0, int pf0, int n) {
+    for (int i = n - 1; i >= 0; i--) { int r = e->substep_bwd(slot0 + i, pf0 + i); if (r) return r; }
+    return PLB_OK;
+}
+int plb_zero_grads(plb_engine* e) { return e->zero_grads(); }
+int plb_set_adjoint(plb_engine* e, const double* gx, const double* gv, const double* gF, const double* gC) { return e->set_adjoint(gx, gv, gF, gC); }
+int plb_get_adjoint(plb_engine* e, double* gx, double* gv, double* gF, double* gC) { return e->get_adjoint(gx, gv, gF, gC); }
+int plb_get_primitive_grads(plb_engine* e, int pf0, int n, double* out) { return e->get_prim_grads(pf0, n, out); }
+int plb_get_action_grad(plb_engine* e, int n_steps, int S, double* out) { return e->get_action_grad(n_steps, S, out); }
+int plb_set_target(plb_engine* e, const double* d, const double* s) { return e->set_target(d, s); }
+int plb_get_target_sdf(plb_engine* e, double* s) { return e->get_target_sdf(s); }
+int plb_set_loss_weights(plb_engine* e, double s, double d, double c, int soft, int all) { return e->set_loss_weights(s, d, c, soft, all); }
+int plb_loss_fwd(plb_engine* e, int slot, int pf, double* out8) { return e->loss_fwd(slot, pf, out8); }
+int plb_loss_bwd(plb_engine* e, int slot, int pf) { return e->loss_bwd(slot, pf); }
+int plb_get_loss(plb_engine* e, double* v) { return e->get_loss(v); }
+int plb_clear_loss(plb_engine* e) { return e->clear_loss(); }
+int plb_debug_get_grid(plb_engine* e, double* in4, double* out4) { return e->debug_get_grid(in4, out4); }
+long long plb_launch_count(const plb_engine* e) { return e->launches; }
+int plb_profile_enable(plb_engine* e, int on) {
+    e->prof_collect();
+    e->prof_on = on != 0;
+    if (on) for (int i = 0; i < K_COUNT; i++) { e->prof_ms[i] = 0; e->prof_cnt[i] = 0; }
+    return PLB_OK;
+}
+int plb_profile_read(plb_engine* e, int n, double* total_ms, long long* counts) {
+    e->prof_collect();
+    for (int i = 0; i < n && i < K_COUNT; i++) { total_ms[i] = e->prof_ms[i]; counts[i] = e->prof_cnt[i]; }
+    return K_COUNT;
+}
+const char* plb_kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : ""; }
+int plb_count_active(plb_engine* e, int slot, long long* n) { return e->count_active(slot, n); }
+
+}  // extern "C"
