@@ -8,7 +8,6 @@ import ctypes as C
 import numpy as np
 
 from .. import _capi
-from ..envs.scene import load_target, resample_target
 
 
 class _LossScalar:
@@ -45,6 +44,7 @@ class Loss:
 
     # ---- targets (loss.py:46-66)
     def load_target_density(self, path=None, grids=None, target_sdf=None):
+        from ..envs.scene import load_target, resample_target      # (late import: envs imports the engine)
         if path is not None and len(path) > 0:
             grids = load_target(path)
         if grids is None:

@@ -148,7 +148,7 @@ def test_copy_mode_matches_trajectory_mode():
     for i in range(2):
         env.step(a[i])
     x_traj = env.simulator.get_x(env.simulator.cur)
-    assert np.array_equal(x_copy, x_traj)
+    assert np.abs(x_copy - x_traj).max() < 1e-12        # float atomics: summation order differs run to run
     assert np.isfinite(info['reward']) and 0.0 <= info['incremental_iou'] <= 1.0
 
 
@@ -171,11 +171,12 @@ def test_move_v1_anchor_loss():
     solver = Solver(tenv, None, None, n_iters=1, softness=666., horizon=50)
     solver.total_steps = 0
     env.reset()
-    loss, grad = solver.forward(tenv.get_state()['state'], np.zeros((50, 6)))
+    state0 = tenv.get_state()['state']
+    loss, grad = solver.forward(state0, np.zeros((50, 6)))
     assert abs(loss - 663.857874990) < 2e-7, loss
     assert np.isfinite(grad).all() and np.abs(grad).max() > 0
     a = np.random.RandomState(123).random_sample((50, 6)) * 0.01
-    loss2, _ = solver.forward(tenv.get_state()['state'], a)
+    loss2, _ = solver.forward(state0, a)
     assert abs(loss2 - 663.3058) < 2e-3, loss2
 
 

@@ -1,0 +1,109 @@
+"""CPU tests of the host-side logic: config/scene loading, particle sampling, C-ABI surface, import hygiene."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('first', ['plasticinelab_b200.engine.taichi_env', 'plasticinelab_b200.envs',
+                                   'plasticinelab_b200.optimizer.solver', 'plasticinelab_b200.engine.losses'])
+def test_import_order(first):
+    code = f"import {first}; import plasticinelab_b200.envs, plasticinelab_b200.engine.taichi_env, plasticinelab_b200.optimizer.solver"
+    subprocess.check_call([sys.executable, '-c', code], cwd=ROOT)
+
+
+def test_scene_loading_matches_reference_semantics():
+    from plasticinelab_b200.envs.scene import load_variants, load_target
+    c = load_variants('move.yml', 3)
+    assert c.SIMULATOR.yield_stress == 200.0 and c.SIMULATOR.E == 5000.0 and c.SIMULATOR.ground_friction == 1.5
+    assert c.PRIMITIVES[0]['init_pos'] == (0.4953388885096601, 0.7803511669469463, 0.3652372561756634)
+    assert c.SHAPES[0]['radius'] == '0.21518886629207218/2'          # stays a string, eval'd by Shapes
+    assert c.ENV.loss.target_path == 'envs/assets/Move3D-v3.npy'
+    r = load_variants('rope.yml', 2)
+    assert r.PRIMITIVES[2]['shape'] == 'Cylinder' and r.PRIMITIVES[2]['init_pos'][0] == 0.4827737598605798
+    assert r.PRIMITIVES[0]['init_pos'] == (0.22, 0.015, 0.82)        # untouched by the `- ` (None) variant entries
+    t = load_target(c.ENV.loss.target_path)
+    assert t.shape == (64, 64, 64) and abs(t.sum() - 10000 * (1 / 128) ** 2) < 1e-12
+    ch = load_variants('chopsticks.yml', 1)
+    assert ch.SIMULATOR.gravity == (0, -5, 0) and ch.PRIMITIVES[0]['action']['dim'] == 7
+
+
+def test_all_bundled_scenes_load_and_sample():
+    from plasticinelab_b200.envs import ENVS
+    from plasticinelab_b200.envs.scene import load_variants, load_target
+    from plasticinelab_b200.engine.shapes import Shapes
+    from plasticinelab_b200 import _capi
+    assert len(ENVS) == 50
+    for name, kw in ENVS.items():
+        cfg = load_variants(**kw)
+        x, col = Shapes(cfg.SHAPES).get()
+        assert x.shape[1] == 3 and len(col) == len(x) and (x > 0).all() and (x < 1).all()
+        assert load_target(cfg.ENV.loss.target_path).shape == (64, 64, 64)
+        for p in cfg.PRIMITIVES:
+            d = _capi.primitive_desc(dict(p))
+            assert 0 <= d.type <= 6
+
+
+def test_shapes_rng_is_seed0_and_restored():
+    from plasticinelab_b200.envs.scene import load_variants
+    from plasticinelab_b200.engine.shapes import Shapes
+    np.random.seed(42)
+    before = np.random.get_state()[1].copy()
+    x, _ = Shapes(load_variants('move.yml', 1).SHAPES).get()
+    assert np.array_equal(before, np.random.get_state()[1])
+    # same draw order as shape_maker.py:60-72 (normal first, then random)
+    np.random.seed(0)
+    p = np.random.normal(size=(10000, 3)); p /= np.linalg.norm(p, axis=-1, keepdims=True)
+    u = np.random.random(size=(10000, 1)) ** (1. / 3)
+    ref = p * u * (0.2049069760770578 / 2) + np.array((0.6757143040494873, 0.5619162002773135, 0.7515980438048129))
+    assert np.array_equal(x, ref)
+
+
+def test_derived_constants():
+    from plasticinelab_b200 import _capi
+    for q, (n, S) in {1: (64, 19), 2: (128, 39), 4: (256, 79), 8: (512, 159)}.items():
+        k = _capi.sim_constants(dict(quality=q))
+        assert k['n_grid'] == n and k['substeps'] == S and k['p_vol'] == (0.5 / n) ** 2
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The library loads without a GPU and exports exactly what include/plb_b200.h declares."""
+    import __graft_entry__ as entry
+    entry.build_engine()
+    from plasticinelab_b200 import _capi
+    lib = _capi.load_library()
+    header = open(os.path.join(ROOT, 'include', 'plb_b200.h')).read()
+    declared = set(re.findall(r'\b(plb_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    assert declared == set(_capi.EXPORTED_SYMBOLS), declared ^ set(_capi.EXPORTED_SYMBOLS)
+    assert lib.plb_abi_version() == 1
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from plasticinelab_b200 import _capi
+    from plasticinelab_b200.envs import make
+    with pytest.raises(_capi.EngineError, match='no CPU fallback'):
+        make('Move-v1')
+
+
+def test_optimizers_match_reference_update_rule():
+    from plasticinelab_b200.optimizer.optim import Adam, Momentum
+    p = np.zeros((2, 3)); g = np.arange(6.0).reshape(2, 3) - 2
+    a = Adam(p.copy(), None, lr=0.1)
+    out = a.step(g)
+    assert np.allclose(out, -0.1 * np.sign(g) * (np.abs(g) / (np.abs(g) + 1e-8)))
+    m = Momentum(p.copy(), None, lr=0.1)
+    assert np.allclose(m.step(g), -0.1 * 0.1 * g)
+    big = Adam(np.full((1, 1), 0.95), None, lr=0.1)
+    assert big.step(np.array([[-1.0]]))[0, 0] == 1.0            # clipped to the bounds
