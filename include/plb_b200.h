@@ -92,6 +92,11 @@ int  plb_set_frame(plb_engine* e, int slot, const double* x, const double* v, co
 int  plb_get_frame(plb_engine* e, int slot, double* x, double* v, double* F, double* C);
 /* MPMSimulator.copyframe, mpm_simulator.py:303-312 (particles only; primitives: plb_copy_primitive_frame) */
 int  plb_copy_frame(plb_engine* e, int src_slot, int dst_slot);
+/* Re-orders the particles stored in `slot` spatially (by 4^3 grid block, then cell) so that consecutive particles
+   share stencil nodes; every other slot becomes stale.  Host-visible particle order is unchanged (the engine keeps the
+   permutation and applies it in plb_set_frame / plb_get_frame / plb_set_materials / plb_*_adjoint).  No reference
+   counterpart: the reference never reorders particles (plb/engine/mpm_simulator.py:157-184 scatters in sampling order). */
+int  plb_sort_particles(plb_engine* e, int slot);
 /* device-side access for torch interop: pointer to the frame's first scalar, padded particle count, scalar size */
 int  plb_frame_device_ptr(plb_engine* e, int slot, void** ptr, long long* n_pad, int* scalar_bytes);
 

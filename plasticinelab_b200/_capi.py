@@ -148,6 +148,7 @@ _SIGNATURES = {
     "plb_set_frame": ([C.c_void_p, C.c_int, _D, _D, _D, _D], C.c_int),
     "plb_get_frame": ([C.c_void_p, C.c_int, _D, _D, _D, _D], C.c_int),
     "plb_copy_frame": ([C.c_void_p, C.c_int, C.c_int], C.c_int),
+    "plb_sort_particles": ([C.c_void_p, C.c_int], C.c_int),
     "plb_frame_device_ptr": ([C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_int)], C.c_int),
     "plb_set_primitive_state": ([C.c_void_p, C.c_int, C.c_int, _D], C.c_int),
     "plb_get_primitive_state": ([C.c_void_p, C.c_int, C.c_int, _D], C.c_int),

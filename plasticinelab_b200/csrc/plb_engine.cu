@@ -7,6 +7,7 @@
 #include <vector>
 #include <algorithm>
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/plb_b200.h"
 #include "plb_kernels.cuh"
@@ -78,6 +79,7 @@ struct plb_engine {
     virtual int set_frame(int slot, const double* x, const double* v, const double* F, const double* C) = 0;
     virtual int get_frame(int slot, double* x, double* v, double* F, double* C) = 0;
     virtual int copy_frame(int src, int dst) = 0;
+    virtual int sort_particles(int slot) = 0;
     virtual int frame_ptr(int slot, void** ptr, long long* n_pad, int* sb) = 0;
     virtual int set_prim_state(int pf, int k, const double* s) = 0;
     virtual int get_prim_state(int pf, int k, double* s) = 0;
@@ -133,6 +135,12 @@ struct Engine : plb_engine {
     double* d_prim_grad = nullptr;  // same shape
     double* d_acc = nullptr;        // loss accumulators (kAccN) + [kAccN] running loss + [kAccN+1 ..] record(8)
     unsigned long long* d_count = nullptr;
+    // active 4^3 blocks of the current substep
+    unsigned char* d_flags = nullptr; int* d_list = nullptr; int* d_nactive = nullptr; int n_blocks = 0;
+    bool sparse = true;
+    // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
+    int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
+    int* d_vals = nullptr; int* d_vals2 = nullptr; void* d_cub = nullptr; size_t cub_bytes = 0; T* frame_tmp = nullptr;
     bool has_target = false;
     double target_max = 0, target_sum = 0;
     LossWeights lw{10.0, 10.0, 1.0, 0};
@@ -148,6 +156,8 @@ struct Engine : plb_engine {
         cudaFree(frames); cudaFree(adj[0]); cudaFree(adj[1]); cudaFree(grid_in); cudaFree(grid_out); cudaFree(g_out);
         cudaFree(g_in); cudaFree(mat_mu); cudaFree(mat_lam); cudaFree(mat_ys); cudaFree(grid_mass); cudaFree(target);
         cudaFree(target_sdf); cudaFree(d_stage); cudaFree(d_traj); cudaFree(d_prim_grad); cudaFree(d_acc); cudaFree(d_count);
+        cudaFree(d_flags); cudaFree(d_list); cudaFree(d_nactive); cudaFree(d_perm); cudaFree(d_perm2); cudaFree(d_keys);
+        cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_cub); cudaFree(frame_tmp);
     }
 
     int blocks(long long n, int b = kBlock) const { return (int)((n + b - 1) / b); }
@@ -202,6 +212,18 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMalloc(&d_acc, (kAccN + 1 + 8) * sizeof(double)));
         PLB_CUDA(cudaMemset(d_acc, 0, (kAccN + 1 + 8) * sizeof(double)));
         PLB_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
+        PLB_REQUIRE(c.n_grid % 4 == 0, "n_grid must be a multiple of 4");
+        sparse = c.kernel_variant != 1;
+        n_blocks = (c.n_grid / 4) * (c.n_grid / 4) * (c.n_grid / 4);
+        PLB_CUDA(cudaMalloc(&d_flags, n_blocks));
+        PLB_CUDA(cudaMemset(d_flags, 0, n_blocks));
+        PLB_CUDA(cudaMalloc(&d_list, n_blocks * sizeof(int)));
+        PLB_CUDA(cudaMalloc(&d_nactive, sizeof(int)));
+        PLB_CUDA(cudaMemset(d_nactive, 0, sizeof(int)));
+        PLB_CUDA(cudaMalloc(&d_perm, n_pad * sizeof(int)));
+        PLB_CUDA(cudaMalloc(&d_perm2, n_pad * sizeof(int)));
+        k_iota<<<blocks(n_pad), kBlock>>>((int)n_pad, d_perm);
+        PLB_CUDA(cudaDeviceSynchronize());
         return PLB_OK;
     }
 
@@ -218,7 +240,7 @@ struct Engine : plb_engine {
             if (!src[i]) continue;
             if (!*dst[i]) PLB_CUDA(cudaMalloc(dst[i], n_pad * sizeof(T)));
             PLB_CUDA(cudaMemcpyAsync(d_stage, src[i], cfg.n_particles * sizeof(double), cudaMemcpyHostToDevice, stream));
-            k_convert<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, d_stage, *dst[i]);
+            k_convert_perm<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, d_stage, *dst[i], d_perm);
             launches++;
             PLB_CUDA(cudaStreamSynchronize(stream));
         }
@@ -239,7 +261,7 @@ struct Engine : plb_engine {
         size_t n = cfg.n_particles;
         double *dx = x ? d_stage : nullptr, *dv = v ? d_stage + 3 * n : nullptr, *dF = F ? d_stage + 6 * n : nullptr,
                *dC = C ? d_stage + 15 * n : nullptr;
-        k_unpack_frame<T><<<blocks(n), kBlock, 0, stream>>>((int)n, n_pad, frame, dx, dv, dF, dC);
+        k_unpack_frame<T><<<blocks(n), kBlock, 0, stream>>>((int)n, n_pad, frame, d_perm, dx, dv, dF, dC);
         launches++;
         if (x) PLB_CUDA(cudaMemcpyAsync(x, dx, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
         if (v) PLB_CUDA(cudaMemcpyAsync(v, dv, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -253,7 +275,7 @@ struct Engine : plb_engine {
         if (int r = check_slot(slot)) return r;
         double *dx, *dv, *dF, *dC;
         if (int r = upload_aos(x, v, F, C, &dx, &dv, &dF, &dC)) return r;
-        k_pack_frame<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, n_pad, frame_base(slot), dx, dv, dF, dC);
+        k_pack_frame<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, n_pad, frame_base(slot), d_perm, dx, dv, dF, dC);
         launches++;
         PLB_CUDA(cudaStreamSynchronize(stream));      // the host arrays may be reused by the caller
         return PLB_OK;
@@ -267,6 +289,36 @@ struct Engine : plb_engine {
         if (int r = check_slot(dst)) return r;
         if (src == dst) return PLB_OK;
         PLB_CUDA(cudaMemcpyAsync(frame_base(dst), frame_base(src), (size_t)24 * n_pad * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        return PLB_OK;
+    }
+    // Re-order the particles of `slot` by (4^3 block, cell) of their base cell so that a warp's 32 particles share
+    // stencil nodes (coalesced gathers, few distinct scatter addresses).  All other slots become stale; the host-side
+    // order is kept through d_perm.  Called when a new state is installed (reset / set_state of frame 0).
+    int sort_particles(int slot) override {
+        if (int r = check_slot(slot)) return r;
+        const int n = cfg.n_particles;
+        if (!d_keys) {
+            PLB_CUDA(cudaMalloc(&d_keys, n_pad * sizeof(unsigned)));  PLB_CUDA(cudaMalloc(&d_keys2, n_pad * sizeof(unsigned)));
+            PLB_CUDA(cudaMalloc(&d_vals, n_pad * sizeof(int)));       PLB_CUDA(cudaMalloc(&d_vals2, n_pad * sizeof(int)));
+            PLB_CUDA(cudaMalloc(&frame_tmp, (size_t)24 * n_pad * sizeof(T)));
+            cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 32, stream);
+            PLB_CUDA(cudaMalloc(&d_cub, cub_bytes));
+        }
+        k_sort_keys<T><<<blocks(n), kBlock, 0, stream>>>(P, frame_base(slot), n_pad, d_keys, d_vals);
+        int bits = 6;
+        for (int nb = n_blocks; nb > 1; nb >>= 1) bits++;
+        PLB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, bits > 32 ? 32 : bits, stream));
+        k_permute_frame<T><<<blocks(n), kBlock, 0, stream>>>(n, n_pad, frame_base(slot), frame_tmp, d_vals2, d_perm, d_perm2);
+        PLB_CUDA(cudaMemcpyAsync(frame_base(slot), frame_tmp, (size_t)24 * n_pad * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        T* mats[3] = {mat_mu, mat_lam, mat_ys};
+        for (int i = 0; i < 3; i++) {
+            if (!mats[i]) continue;
+            k_permute_scalar<T><<<blocks(n), kBlock, 0, stream>>>(n, mats[i], frame_tmp, d_vals2);
+            PLB_CUDA(cudaMemcpyAsync(mats[i], frame_tmp, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        }
+        std::swap(d_perm, d_perm2);
+        launches += 3;
+        PLB_CUDA(cudaGetLastError());
         return PLB_OK;
     }
     int frame_ptr(int slot, void** ptr, long long* np, int* sb) override {
@@ -335,6 +387,12 @@ struct Engine : plb_engine {
     }
 
     // ---------------------------------------------------------------- substeps
+    int sparse_ctas() const { return std::min(std::max(n_blocks / 2, 1), 148 * 8); }
+    void compact_blocks() {
+        cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
+        k_compact<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags, d_list, d_nactive);
+        launches++;
+    }
     int substep_fwd(int si, int so, int pf) override {
         if (int r = check_slot(si)) return r;
         if (int r = check_slot(so)) return r;
@@ -342,9 +400,14 @@ struct Engine : plb_engine {
         PLB_REQUIRE(si != so, "in-place substep");
         int nb = blocks(cfg.n_particles);
         prof_begin(K_P2G);
-        k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in);
+        k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
         prof_end(); prof_begin(K_GRID_FWD);
-        k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
+        if (sparse) {
+            compact_blocks();
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive);
+        } else {
+            k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
+        }
         prof_end(); prof_begin(K_G2P);
         k_g2p<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, grid_out);
         prof_end();
@@ -359,13 +422,21 @@ struct Engine : plb_engine {
         T* a_next = adj[cur];
         T* a_cur = adj[cur ^ 1];
         prof_begin(K_P2G_RECOMPUTE);
-        k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in);
+        k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
-        k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
+        if (sparse) {
+            compact_blocks();
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, d_list, d_nactive);
+        } else {
+            k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
+        }
         prof_end(); prof_begin(K_G2P_BWD);
         k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
         prof_end(); prof_begin(K_GRID_BWD);
-        k_grid_bwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, n_nodes);
+        if (sparse)
+            k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive);
+        else
+            k_grid_bwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, n_nodes);
         prof_end(); prof_begin(K_P2G_BWD);
         k_p2g_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in);
         prof_end();
@@ -386,7 +457,7 @@ struct Engine : plb_engine {
     int set_adjoint(const double* gx, const double* gv, const double* gF, const double* gC) override {
         double *dx, *dv, *dF, *dC;
         if (int r = upload_aos(gx, gv, gF, gC, &dx, &dv, &dF, &dC)) return r;
-        k_pack_frame<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, n_pad, adj[cur], dx, dv, dF, dC);
+        k_pack_frame<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, n_pad, adj[cur], d_perm, dx, dv, dF, dC);
         launches++;
         PLB_CUDA(cudaStreamSynchronize(stream));
         return PLB_OK;
@@ -552,7 +623,7 @@ struct Engine : plb_engine {
     int count_active(int slot, long long* n) override {
         if (int r = check_slot(slot)) return r;
         // scatter this frame's particles (no F store), count, then clear grid_in again
-        k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, slot, 0, material(), grid_in);
+        k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, slot, 0, material(), grid_in, nullptr);
         PLB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
         k_count_active<T><<<blocks(n_nodes), kBlock, 0, stream>>>(n_nodes, grid_in, d_count);
         launches += 2;
@@ -596,6 +667,7 @@ int plb_set_materials(plb_engine* e, const double* mu, const double* lam, const 
 int plb_set_frame(plb_engine* e, int slot, const double* x, const double* v, const double* F, const double* C) { return e->set_frame(slot, x, v, F, C); }
 int plb_get_frame(plb_engine* e, int slot, double* x, double* v, double* F, double* C) { return e->get_frame(slot, x, v, F, C); }
 int plb_copy_frame(plb_engine* e, int s, int d) { return e->copy_frame(s, d); }
+int plb_sort_particles(plb_engine* e, int slot) { return e->sort_particles(slot); }
 int plb_frame_device_ptr(plb_engine* e, int slot, void** ptr, long long* n_pad, int* sb) { return e->frame_ptr(slot, ptr, n_pad, sb); }
 int plb_set_primitive_state(plb_engine* e, int pf, int k, const double* s) { return e->set_prim_state(pf, k, s); }
 int plb_get_primitive_state(plb_engine* e, int pf, int k, double* s) { return e->get_prim_state(pf, k, s); }

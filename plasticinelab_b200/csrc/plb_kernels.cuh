@@ -38,13 +38,99 @@ __device__ __forceinline__ void reduce_pose_grad(const PoseGrad<T>& g, double* d
     }
 }
 
+// ------------------------------------------------------------------------------------------------ active blocks
+// The grid stays dense in memory, but only 4x4x4-node blocks touched by a particle stencil in the current substep are
+// visited by the grid kernels.  P2G marks the (up to 8) blocks of each particle in `flags`; k_compact turns the flags
+// into a list (and clears them); the grid kernels walk the list.  Invariants: grid_in and g_out are zero outside the
+// listed blocks; grid_out / g_in outside the listed blocks are never read.
+constexpr int kBlkShift = 2;                 // 4 nodes per block edge
+constexpr int kBlkNodes = 64;
+
+__device__ __forceinline__ int block_id(int nbx, int i, int j, int k) {
+    return ((i >> kBlkShift) * nbx + (j >> kBlkShift)) * nbx + (k >> kBlkShift);
+}
+
+template <class T>
+__device__ __forceinline__ void mark_blocks(const SimConst<T>& P, V3<T> x, unsigned char* flags) {
+    const int nbx = P.n_grid >> kBlkShift;
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                int id = block_id(nbx, b[0] + 2 * a, b[1] + 2 * c, b[2] + 2 * e);
+                if (!flags[id]) flags[id] = 1;
+            }
+}
+
+__global__ void k_compact(int n_blocks, unsigned char* flags, int* list, int* count) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_blocks && flags[b]) {
+        flags[b] = 0;
+        list[atomicAdd(count, 1)] = b;
+    }
+}
+
+// node handled by thread `local` (0..63) of listed block `blk`
+__device__ __forceinline__ long long block_node(int n_grid, int blk, int local) {
+    const int nbx = n_grid >> kBlkShift;
+    int bk = blk % nbx, bj = (blk / nbx) % nbx, bi = blk / (nbx * nbx);
+    int i = (bi << kBlkShift) + (local >> 4), j = (bj << kBlkShift) + ((local >> 2) & 3), k = (bk << kBlkShift) + (local & 3);
+    return ((long long)i * n_grid + j) * n_grid + k;
+}
+
 // ------------------------------------------------------------------------------------------------ substep
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long long n_pad, int slot_in, int slot_out,
-                                                int store_F_out, Material<T> mat, Vec4<T>* grid_in) {
+                                                int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
-    p2g_body<T>(p, P, frame_at(frames, slot_in, n_pad), frame_at(frames, slot_out, n_pad), store_F_out != 0, mat, grid_in);
+    FramePtr<T> fin = frame_at(frames, slot_in, n_pad);
+    p2g_body<T>(p, P, fin, frame_at(frames, slot_out, n_pad), store_F_out != 0, mat, grid_in);
+    if (flags) mark_blocks<T>(P, load_x(fin, p), flags);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimSet<T> prims, const double* traj, int pf,
+                                                            Vec4<T>* grid_in, Vec4<T>* grid_out, int clear_in,
+                                                            const int* __restrict__ list, const int* __restrict__ count) {
+    __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
+    load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
+    const int per_cta = kBlock / kBlkNodes, n = *count;
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta)
+        grid_fwd_body<T>(block_node(P.n_grid, list[e], threadIdx.x & (kBlkNodes - 1)), P, prims, s0, s1, grid_in, grid_out, clear_in != 0);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse(SimConst<T> P, PrimSet<T> prims, const double* traj, int pf,
+                                                            Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, int clear,
+                                                            double* prim_grad, const int* __restrict__ list,
+                                                            const int* __restrict__ count) {
+    __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
+    load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
+    const int per_cta = kBlock / kBlkNodes, n = *count;
+    const int rounds = (n + gridDim.x * per_cta - 1) / (gridDim.x * per_cta);
+    for (int r = 0; r < rounds; r++) {              // uniform trip count: the pose-gradient reduction uses warp shuffles
+        int e = (r * gridDim.x + blockIdx.x) * per_cta + threadIdx.x / kBlkNodes;
+        PoseGrad<T> g0[PLB_MAX_PRIM], g1[PLB_MAX_PRIM];
+        unsigned touched = 0;
+        if (e < n) {
+            for (int k = 0; k < P.n_prim; k++) { g0[k].clear(); g1[k].clear(); }
+            grid_bwd_body<T>(block_node(P.n_grid, list[e], threadIdx.x & (kBlkNodes - 1)), P, prims, s0, s1, grid_in, g_out, g_in,
+                             clear != 0, g0, g1, touched);
+        }
+        for (int k = 0; k < P.n_prim; k++) {
+            unsigned any = __ballot_sync(0xffffffffu, (touched >> k) & 1u);
+            if (any == 0) continue;
+            if (!((touched >> k) & 1u)) { g0[k].clear(); g1[k].clear(); }
+            reduce_pose_grad<T>(g0[k], prim_grad + ((long long)pf * PLB_MAX_PRIM + k) * PLB_POSE_DIM);
+            reduce_pose_grad<T>(g1[k], prim_grad + ((long long)(pf + 1) * PLB_MAX_PRIM + k) * PLB_POSE_DIM);
+        }
+    }
 }
 
 template <class T>
@@ -241,39 +327,84 @@ __global__ void __launch_bounds__(128) k_sdf_sweep(int n, double dx, const doubl
 
 // ------------------------------------------------------------------------------------------------ host <-> frame
 // AoS float64 host layout (x[N][3], v[N][3], F[N][3][3], C[N][3][3], staged on the device) <-> packed planes
+// `perm[p]` = caller-side (reference order) index of the particle stored at position p (identity until the first sort)
 template <class T>
-__global__ void k_pack_frame(int n, long long n_pad, T* frame, const double* x, const double* v, const double* F, const double* C) {
+__global__ void k_pack_frame(int n, long long n_pad, T* frame, const int* __restrict__ perm, const double* x, const double* v,
+                             const double* F, const double* C) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
+    const long long q = perm[p];
     FramePtr<T> f = frame_at(frame, 0, n_pad);
     V3<T> xx, vv; M3<T> CC;
     load_xvC(f, p, xx, vv, CC);
     M3<T> FF = load_F(f, p);
-    if (x) xx = mk3<T>((T)x[p * 3], (T)x[p * 3 + 1], (T)x[p * 3 + 2]);
-    if (v) vv = mk3<T>((T)v[p * 3], (T)v[p * 3 + 1], (T)v[p * 3 + 2]);
-    if (C) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) CC.m[i][j] = (T)C[p * 9 + i * 3 + j];
-    if (F) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) FF.m[i][j] = (T)F[p * 9 + i * 3 + j];
+    if (x) xx = mk3<T>((T)x[q * 3], (T)x[q * 3 + 1], (T)x[q * 3 + 2]);
+    if (v) vv = mk3<T>((T)v[q * 3], (T)v[q * 3 + 1], (T)v[q * 3 + 2]);
+    if (C) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) CC.m[i][j] = (T)C[q * 9 + i * 3 + j];
+    if (F) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) FF.m[i][j] = (T)F[q * 9 + i * 3 + j];
     store_xvC(f, p, xx, vv, CC);
     store_F(f, p, FF);
 }
 
 template <class T>
-__global__ void k_unpack_frame(int n, long long n_pad, T* frame, double* x, double* v, double* F, double* C) {
+__global__ void k_unpack_frame(int n, long long n_pad, T* frame, const int* __restrict__ perm, double* x, double* v, double* F,
+                               double* C) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
+    const long long q = perm[p];
     FramePtr<T> f = frame_at(frame, 0, n_pad);
     V3<T> xx, vv; M3<T> CC;
     load_xvC(f, p, xx, vv, CC);
     M3<T> FF = load_F(f, p);
-    if (x) { x[p * 3] = xx.x; x[p * 3 + 1] = xx.y; x[p * 3 + 2] = xx.z; }
-    if (v) { v[p * 3] = vv.x; v[p * 3 + 1] = vv.y; v[p * 3 + 2] = vv.z; }
-    if (C) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C[p * 9 + i * 3 + j] = CC.m[i][j];
-    if (F) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[p * 9 + i * 3 + j] = FF.m[i][j];
+    if (x) { x[q * 3] = xx.x; x[q * 3 + 1] = xx.y; x[q * 3 + 2] = xx.z; }
+    if (v) { v[q * 3] = vv.x; v[q * 3 + 1] = vv.y; v[q * 3 + 2] = vv.z; }
+    if (C) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C[q * 9 + i * 3 + j] = CC.m[i][j];
+    if (F) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[q * 9 + i * 3 + j] = FF.m[i][j];
 }
+
+// ---- spatial sort support: key = (4^3-block id, cell within block) of the particle's base cell
+template <class T>
+__global__ void k_sort_keys(SimConst<T> P, T* frame, long long n_pad, unsigned* keys, int* vals) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_particles) return;
+    V3<T> x = load_x(frame_at(frame, 0, n_pad), p);
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    const int nbx = P.n_grid >> kBlkShift;
+    unsigned blk = (unsigned)block_id(nbx, b[0], b[1], b[2]);
+    unsigned cell = (unsigned)(((b[0] & 3) << 4) | ((b[1] & 3) << 2) | (b[2] & 3));
+    keys[p] = blk * 64u + cell;
+    vals[p] = p;
+}
+// dst[j] = src[order[j]] for a whole frame; perm_out[j] = perm_in[order[j]]
+template <class T>
+__global__ void k_permute_frame(int n, long long n_pad, const T* src, T* dst, const int* __restrict__ order,
+                                const int* __restrict__ perm_in, int* perm_out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int o = order[j];
+    FramePtr<T> fs = frame_at(const_cast<T*>(src), 0, n_pad), fd = frame_at(dst, 0, n_pad);
+    V3<T> x, v; M3<T> C;
+    load_xvC(fs, o, x, v, C);
+    M3<T> F = load_F(fs, o);
+    store_xvC(fd, j, x, v, C);
+    store_F(fd, j, F);
+    if (perm_out) perm_out[j] = perm_in[o];
+}
+template <class T> __global__ void k_permute_scalar(int n, const T* src, T* dst, const int* __restrict__ order) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[j] = src[order[j]];
+}
+__global__ void k_iota(int n, int* a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
 
 template <class T> __global__ void k_convert(long long n, const double* src, T* dst) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (T)src[i];
+}
+template <class T> __global__ void k_convert_perm(int n, const double* src, T* dst, const int* __restrict__ perm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (T)src[perm[i]];
 }
 template <class T> __global__ void k_grid_to_double(long long n, const Vec4<T>* src, double* dst) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -58,6 +58,8 @@ class MPMSimulator:
         self.engine.call("plb_set_frame", int(f), _capi.dptr(x), _capi.dptr(v), _capi.dptr(F), _capi.dptr(C))
         for s, p in zip(state[4:], self.primitives):
             p.set_state(f, s)
+        if f == 0:
+            self.engine.call("plb_sort_particles", 0)     # new episode state: restore spatial order
 
     def reset(self, x):
         n = self.n_particles
@@ -65,6 +67,7 @@ class MPMSimulator:
         F = np.ascontiguousarray(np.broadcast_to(np.eye(3), (n, 3, 3)))
         self.engine.call("plb_set_frame", 0, _capi.dptr(x), _capi.dptr(np.zeros((n, 3))), _capi.dptr(F),
                          _capi.dptr(np.zeros((n, 3, 3))))
+        self.engine.call("plb_sort_particles", 0)
         self.cur = 0
 
     def get_x(self, f):

@@ -218,3 +218,53 @@ def test_full_size_properties_config2():
         eng.call("plb_loss_fwd", 0, 0, D(out))
         assert abs(out[2] - n * k['p_mass']) < tol * n * k['p_mass']        # density loss vs zero target = total mass
         eng.close()
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+def test_sorted_sparse_path_equals_dense_unsorted(dtype):
+    """The spatial sort (+ permutation kept for host I/O) and the active-block grid kernels change nothing but the
+    floating-point summation order: same state, same adjoint, same pose gradients as the dense, unsorted variant."""
+    n = 5000
+    cfg = H.small_cfg(PRIM_SETS['spheres'], n_particles=n, ground_friction=1.5, yield_stress=30.0)
+    osim = O.OracleSim(dict(cfg.SIMULATOR), [dict(p) for p in cfg.PRIMITIVES])
+    state = H.random_state(n, 3, 0.3, 0.7)
+    pose0, pose1 = _poses(osim, 0)
+    adj = H.random_adjoint(n, 3)
+    res = []
+    for variant, do_sort in ((1, False), (0, True)):
+        descs = [_capi.primitive_desc(dict(p)) for p in cfg.PRIMITIVES]
+        conf = _capi.make_config(dict(cfg.SIMULATOR), n, len(descs), dtype=dtype, max_frames=4, max_prim_frames=4, kernel_variant=variant)
+        eng = _capi.Engine(conf, descs)
+        x, v, Cm, F = state
+        eng.call("plb_set_frame", 0, D(x), D(v), D(F), D(Cm))
+        if do_sort:
+            eng.call("plb_sort_particles", 0)
+            xb, vb, Fb, Cb = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3, 3)), np.zeros((n, 3, 3))
+            eng.call("plb_get_frame", 0, D(xb), D(vb), D(Fb), D(Cb))
+            if dtype == 'float64':
+                assert np.array_equal(xb, x) and np.array_equal(Fb, F) and np.array_equal(Cb, Cm) and np.array_equal(vb, v)
+        res.append(_substep_gpu_noset(eng, n, 2, (pose0, pose1), 666.0, adj))
+        eng.close()
+    tol = 1e-11 if dtype == 'float64' else 2e-4
+    for a, b in zip(res[0][0] + res[0][1], res[1][0] + res[1][1]):
+        assert H.relerr(a, b) < tol
+    assert np.abs(res[0][2] - res[1][2]).max() < tol * max(np.abs(res[0][2]).max(), 1e-30) * 100
+
+
+def _substep_gpu_noset(eng, n, P, poses, softness, adj):
+    eng.call("plb_set_softness", C.c_double(softness))
+    for k in range(P):
+        eng.call("plb_set_primitive_state", 0, k, D(np.ascontiguousarray(poses[0][k])))
+        eng.call("plb_set_primitive_state", 1, k, D(np.ascontiguousarray(poses[1][k])))
+    eng.call("plb_substep_fwd", 0, 1, 0)
+    xo, vo, Fo, Co = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3, 3)), np.zeros((n, 3, 3))
+    eng.call("plb_get_frame", 1, D(xo), D(vo), D(Fo), D(Co))
+    gxn, gvn, gCn, gFn = adj
+    eng.call("plb_zero_grads")
+    eng.call("plb_set_adjoint", D(gxn), D(gvn), D(gFn), D(gCn))
+    eng.call("plb_substep_bwd", 0, 0)
+    gx, gv, gF, gC = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3, 3)), np.zeros((n, 3, 3))
+    eng.call("plb_get_adjoint", D(gx), D(gv), D(gF), D(gC))
+    gp = np.zeros((2, max(P, 1), 8))
+    eng.call("plb_get_primitive_grads", 0, 2, D(gp))
+    return (xo, vo, Co, Fo), (gx, gv, gC, gF), gp
