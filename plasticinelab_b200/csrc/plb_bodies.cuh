@@ -84,21 +84,29 @@ template <class T> inline void scatter_add4(Vec4<T>* addr, Vec4<T> v) { addr->x 
 template <class T> inline void scatter_add1(T* addr, T v) { *addr += v; }
 #endif
 
+PLB_HD long long node_index(int n, int i, int j, int k) { return ((long long)i * n + j) * n + k; }
+
+// Scatter policy used by the two scattering bodies.  Direct: one (vector) atomic per node and particle.
+// The CUDA kernels can substitute WarpTileScatter (plb_kernels.cuh), which pre-reduces a warp's contributions.
+template <class T> struct DirectScatter {
+    Vec4<T>* grid;
+    int n;
+    PLB_HD void add(int slot, int i, int j, int k, Vec4<T> v) const { (void)slot; scatter_add4(grid + node_index(n, i, j, k), v); }
+};
+
 template <class T> PLB_HD void load_material(const SimConst<T>& P, const Material<T>& mat, int p, T& mu, T& lam, T& ys) {
     mu = mat.mu ? mat.mu[p] : P.mu;
     lam = mat.lam ? mat.lam[p] : P.lam;
     ys = mat.ys ? mat.ys[p] : P.yield_stress;
 }
 
-PLB_HD long long node_index(int n, int i, int j, int k) { return ((long long)i * n + j) * n + k; }
-
 // ================================================================================================
 // forward substep
 // ================================================================================================
 // P2G: F_tmp, SVD, return mapping, stress, 27-node scatter.  `out` may alias nothing (F[f+1] store skipped if !store_F_out).
-template <class T>
+template <class T, class Sc>
 PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,
-                     const Material<T>& mat, Vec4<T>* grid_in) {
+                     const Material<T>& mat, const Sc& sc) {
     V3<T> x, v; M3<T> C;
     load_xvC(in, p, x, v, C);
     M3<T> F = load_F(in, p);
@@ -118,9 +126,14 @@ PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const F
                 T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
                 V3<T> dpos = mk3<T>((T(i) - st.fx.x) * P.dx, (T(j) - st.fx.y) * P.dx, (T(k) - st.fx.z) * P.dx);
                 V3<T> mom = w * (mvel + mv(affine, dpos));
-                scatter_add4(grid_in + node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k),
-                             mk4<T>(mom.x, mom.y, mom.z, w * P.p_mass));
+                sc.add((i * 3 + j) * 3 + k, st.b[0] + i, st.b[1] + j, st.b[2] + k, mk4<T>(mom.x, mom.y, mom.z, w * P.p_mass));
             }
+}
+template <class T>
+PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,
+                     const Material<T>& mat, Vec4<T>* grid_in) {
+    DirectScatter<T> sc{grid_in, P.n_grid};
+    p2g_body<T, DirectScatter<T>>(p, P, in, out, store_F_out, mat, sc);
 }
 
 // grid operator: grid_in -> grid_out; optionally zeroes grid_in for the next scatter
@@ -165,9 +178,9 @@ PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const F
 // ================================================================================================
 // g2p.grad: reads adjoint of (x,v,C)[f+1], scatters the adjoint of grid_out, writes the partial x-adjoint of frame f
 // into adj_cur.A0 (xyz lanes; the w lane is finished by p2g_bwd_body).
-template <class T>
+template <class T, class Sc>
 PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
-                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, const Sc& sc) {
     V3<T> x = load_x(in, p);
     V3<T> gxn, gvn; M3<T> gCn;
     load_xvC(adj_next, p, gxn, gvn, gCn);
@@ -207,7 +220,7 @@ PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
                 V3<T> dpos = mk3<T>(T(i) - st.fx.x, T(j) - st.fx.y, T(k) - st.fx.z);
                 V3<T> Cd = mv(gCn, dpos);                     // gC' dpos
                 V3<T> gg = w * (gv + c4 * Cd);                // adjoint of grid_out[node]
-                scatter_add4(g_out + node, mk4<T>(gg.x, gg.y, gg.z, T(0)));
+                sc.add((i * 3 + j) * 3 + k, st.b[0] + i, st.b[1] + j, st.b[2] + k, mk4<T>(gg.x, gg.y, gg.z, T(0)));
                 T gwt = dot(gv, gvn_) + c4 * dot(gvn_, Cd);   // adjoint of the 3-D weight
                 V3<T> gd = (c4 * w) * mTv(gCn, gvn_);         // adjoint of dpos
                 gfx -= gd;
@@ -217,6 +230,12 @@ PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
             }
     gx += stencil_backward(st, gw, gfx, P.inv_dx);
     adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
+}
+template <class T>
+PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
+                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+    DirectScatter<T> sc{g_out, P.n_grid};
+    g2p_bwd_body<T, DirectScatter<T>>(p, P, in, adj_next, adj_cur, grid_out, sc);
 }
 
 // grid_op.grad for one node.  Reads grid_in (forward values) and g_out (adjoint of grid_out); writes g_in (adjoint of

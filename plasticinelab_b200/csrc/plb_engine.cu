@@ -138,6 +138,8 @@ struct Engine : plb_engine {
     // active 4^3 blocks of the current substep
     unsigned char* d_flags = nullptr; int* d_list = nullptr; int* d_nactive = nullptr; int n_blocks = 0;
     bool sparse = true;
+    bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
+    size_t tile_smem = 0;
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
     int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
     int* d_vals = nullptr; int* d_vals2 = nullptr; void* d_cub = nullptr; size_t cub_bytes = 0; T* frame_tmp = nullptr;
@@ -214,6 +216,12 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
         PLB_REQUIRE(c.n_grid % 4 == 0, "n_grid must be a multiple of 4");
         sparse = c.kernel_variant != 1;
+        tile_scatter = c.kernel_variant == 0;
+        tile_smem = (size_t)(kBlock / 32) * kTileVec4 * sizeof(Vec4<T>);
+        if (tile_scatter) {
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+        }
         n_blocks = (c.n_grid / 4) * (c.n_grid / 4) * (c.n_grid / 4);
         PLB_CUDA(cudaMalloc(&d_flags, n_blocks));
         PLB_CUDA(cudaMemset(d_flags, 0, n_blocks));
@@ -400,7 +408,10 @@ struct Engine : plb_engine {
         PLB_REQUIRE(si != so, "in-place substep");
         int nb = blocks(cfg.n_particles);
         prof_begin(K_P2G);
-        k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
+        if (tile_scatter)
+            k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
+        else
+            k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
         prof_end(); prof_begin(K_GRID_FWD);
         if (sparse) {
             compact_blocks();
@@ -422,7 +433,10 @@ struct Engine : plb_engine {
         T* a_next = adj[cur];
         T* a_cur = adj[cur ^ 1];
         prof_begin(K_P2G_RECOMPUTE);
-        k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
+        if (tile_scatter)
+            k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
+        else
+            k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
         if (sparse) {
             compact_blocks();
@@ -431,7 +445,10 @@ struct Engine : plb_engine {
             k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
         }
         prof_end(); prof_begin(K_G2P_BWD);
-        k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
+        if (tile_scatter)
+            k_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
+        else
+            k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
         prof_end(); prof_begin(K_GRID_BWD);
         if (sparse)
             k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive);

@@ -83,6 +83,54 @@ __device__ __forceinline__ long long block_node(int n_grid, int blk, int local) 
     return ((long long)i * n_grid + j) * n_grid + k;
 }
 
+// ------------------------------------------------------------------------------------------------ warp scatter
+// Warp-level pre-reduction of the 27-node scatters (P2G and the G2P adjoint).
+// After the spatial sort the 32 particles of a warp sit in a handful of cells, so their 27-node stencils coincide and
+// per-particle atomics serialise at the L2 atomic unit (measured: 1M particles, p2g 230 us unsorted -> 439 us sorted).
+// Here every lane parks its 27 Vec4 contributions in a per-warp shared tile [27 nodes][33 lanes] (row padded by one
+// Vec4: the transposed read then walks 4-bank groups conflict-free).  Lanes are grouped by base cell; for each group
+// (uniform loop over distinct cells) lane q < 27 sums node q over the group's lanes and issues ONE vector RED.
+// Cost per warp: 27 STS.128 + 32 LDS.128 per lane, independent of the number of groups; atomics drop from
+// 27 x 32 to 27 x (#cells in the warp).
+constexpr int kTileStride = 33;
+constexpr int kTileVec4 = 27 * kTileStride;
+
+template <class T> struct WarpTileScatter {
+    Vec4<T>* tile;     // this warp's tile
+    int lane;
+    __device__ __forceinline__ void add(int slot, int, int, int, Vec4<T> v) const { tile[slot * kTileStride + lane] = v; }
+};
+
+// valid: lane holds a particle; b: its base cell.  All 32 lanes must call.
+template <class T>
+__device__ __forceinline__ void warp_tile_flush(const Vec4<T>* tile, int lane, bool valid, const int b[3], int n_grid, Vec4<T>* grid) {
+    __syncwarp();
+    const unsigned full = 0xffffffffu;
+    int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
+    unsigned remaining = __ballot_sync(full, valid);
+    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;       // node offset owned by this lane (lane < 27)
+    while (remaining) {
+        int leader = __ffs(remaining) - 1;
+        int lkey = __shfl_sync(full, key, leader);
+        unsigned group = __ballot_sync(full, key == lkey);
+        remaining &= ~group;
+        if (lane < 27) {
+            Vec4<T> acc = mk4<T>(T(0), T(0), T(0), T(0));
+            const Vec4<T>* row = tile + lane * kTileStride;
+            unsigned g = group;
+            while (g) {
+                int j = __ffs(g) - 1;
+                g &= g - 1;
+                Vec4<T> v = row[j];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            int bk = lkey % n_grid, bj = (lkey / n_grid) % n_grid, bi = lkey / (n_grid * n_grid);
+            scatter_add4(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ substep
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long long n_pad, int slot_in, int slot_out,
@@ -92,6 +140,28 @@ __global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long l
     FramePtr<T> fin = frame_at(frames, slot_in, n_pad);
     p2g_body<T>(p, P, fin, frame_at(frames, slot_out, n_pad), store_F_out != 0, mat, grid_in);
     if (flags) mark_blocks<T>(P, load_x(fin, p), flags);
+}
+
+// same, with the warp-tile scatter (dynamic shared memory: kBlock/32 tiles)
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, long long n_pad, int slot_in, int slot_out,
+                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    int b[3] = {0, 0, 0};
+    if (valid) {
+        FramePtr<T> fin = frame_at(frames, slot_in, n_pad);
+        WarpTileScatter<T> sc{tile, lane};
+        p2g_body<T, WarpTileScatter<T>>(p, P, fin, frame_at(frames, slot_out, n_pad), store_F_out != 0, mat, sc);
+        V3<T> x = load_x(fin, p);
+#pragma unroll
+        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+        if (flags) mark_blocks<T>(P, x, flags);
+    }
+    warp_tile_flush<T>(tile, lane, valid, b, P.n_grid, grid_in);
 }
 
 template <class T>
@@ -158,6 +228,26 @@ __global__ void __launch_bounds__(kBlock) k_g2p_bwd(SimConst<T> P, T* frames, lo
     if (p >= P.n_particles) return;
     g2p_bwd_body<T>(p, P, frame_at(frames, slot_in, n_pad), frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad),
                     grid_out, g_out);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, int slot_in, T* adj_next,
+                                                         T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    int b[3] = {0, 0, 0};
+    if (valid) {
+        FramePtr<T> fin = frame_at(frames, slot_in, n_pad);
+        WarpTileScatter<T> sc{tile, lane};
+        g2p_bwd_body<T, WarpTileScatter<T>>(p, P, fin, frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad), grid_out, sc);
+        V3<T> x = load_x(fin, p);
+#pragma unroll
+        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    }
+    warp_tile_flush<T>(tile, lane, valid, b, P.n_grid, g_out);
 }
 
 template <class T>
