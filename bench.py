@@ -268,14 +268,17 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = eng.lib.plb_launch_count(eng.h)
-    eng.call("plb_profile_enable", 1)
     ms_dev = timed(episode_device, args.steps)
     launches = eng.lib.plb_launch_count(eng.h) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel device times: one more episode of the same workload with a CUDA-event pair around every launch
+    # (the engine then launches kernel by kernel instead of replaying its per-env-step CUDA graphs)
+    eng.call("plb_profile_enable", 1)
+    episode_device()
     kms = np.zeros(16)
     kcnt = (C.c_longlong * 16)()
     nk = eng.lib.plb_profile_read(eng.h, 16, _capi.dptr(kms), kcnt)
     eng.call("plb_profile_enable", 0)
-    clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the public API
     episode_e2e()
@@ -310,6 +313,8 @@ def main():
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_us": sub[dom]["avg_us"], "share_of_kernel_time": sub[dom]["total_ms"] / max(kernel_ms_total, 1e-9),
                 "n_active_nodes": n_active,
+                "timing": "CUDA events around every launch of one extra episode run inside bench.py right after the timed "
+                          "region (graphs off for that episode); `value` itself is timed with graphs on",
                 "fused_substep": {"algorithmic_bytes": fused_bytes, "achieved": fused_gbs, "frac": fused_gbs / peak,
                                   "formula": "(504 N + 168 N_active) B per fwd+bwd substep (SURVEY.md 8d)"},
                 "kernels": per_kernel}

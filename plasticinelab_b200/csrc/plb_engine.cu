@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <map>
+#include <tuple>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -89,6 +91,8 @@ struct plb_engine {
     virtual int kinematics(int pf, int n) = 0;
     virtual int substep_fwd(int si, int so, int pf) = 0;
     virtual int substep_bwd(int si, int pf) = 0;
+    virtual int step_fwd(int slot0, int pf0, int n) = 0;
+    virtual int step_bwd(int slot0, int pf0, int n) = 0;
     virtual int zero_grads() = 0;
     virtual int set_adjoint(const double* gx, const double* gv, const double* gF, const double* gC) = 0;
     virtual int get_adjoint(double* gx, double* gv, double* gF, double* gC) = 0;
@@ -138,6 +142,15 @@ struct Engine : plb_engine {
     // active 4^3 blocks of the current substep
     unsigned char* d_flags = nullptr; int* d_list = nullptr; int* d_nactive = nullptr; int n_blocks = 0;
     bool sparse = true;
+    // forward-grid store + CUDA graphs
+    GridStore<T> store{nullptr, nullptr, nullptr, nullptr, 0};
+    std::vector<char> stored;       // host view: slot s holds the grid of the substep that started at s
+    int* d_cursor = nullptr;
+    bool use_graphs = true;
+    cudaStream_t own_stream = nullptr;
+    struct GraphKey { int dir, n, parity, stored; bool operator<(const GraphKey& o) const {
+        return std::tie(dir, n, parity, stored) < std::tie(o.dir, o.n, o.parity, o.stored); } };
+    std::map<GraphKey, cudaGraphExec_t> graphs;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     size_t tile_smem = 0;
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
@@ -160,6 +173,9 @@ struct Engine : plb_engine {
         cudaFree(target_sdf); cudaFree(d_stage); cudaFree(d_traj); cudaFree(d_prim_grad); cudaFree(d_acc); cudaFree(d_count);
         cudaFree(d_flags); cudaFree(d_list); cudaFree(d_nactive); cudaFree(d_perm); cudaFree(d_perm2); cudaFree(d_keys);
         cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_cub); cudaFree(frame_tmp);
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt); cudaFree(store.overflow); cudaFree(d_cursor);
+        if (own_stream) cudaStreamDestroy(own_stream);
     }
 
     int blocks(long long n, int b = kBlock) const { return (int)((n + b - 1) / b); }
@@ -228,6 +244,16 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMalloc(&d_list, n_blocks * sizeof(int)));
         PLB_CUDA(cudaMalloc(&d_nactive, sizeof(int)));
         PLB_CUDA(cudaMemset(d_nactive, 0, sizeof(int)));
+        // a blocking (non-legacy) stream: graph capture is not allowed on the legacy default stream, and a blocking
+        // stream still orders with work the caller issues on the default stream (torch events, copies)
+        PLB_CUDA(cudaStreamCreate(&own_stream));
+        stream = own_stream; prof_stream = own_stream;
+        use_graphs = c.kernel_variant == 0 && !getenv("PLB_NO_GRAPHS");
+        PLB_CUDA(cudaMalloc(&d_cursor, 4 * sizeof(int)));
+        PLB_CUDA(cudaMemset(d_cursor, 0, 4 * sizeof(int)));
+        stored.assign(c.max_frames, 0);
+        PLB_CUDA(cudaMalloc(&store.overflow, sizeof(int)));
+        PLB_CUDA(cudaMemset(store.overflow, 0, sizeof(int)));
         PLB_CUDA(cudaMalloc(&d_perm, n_pad * sizeof(int)));
         PLB_CUDA(cudaMalloc(&d_perm2, n_pad * sizeof(int)));
         k_iota<<<blocks(n_pad), kBlock>>>((int)n_pad, d_perm);
@@ -235,7 +261,15 @@ struct Engine : plb_engine {
         return PLB_OK;
     }
 
-    int set_stream(void* s) override { stream = (cudaStream_t)s; prof_stream = stream; return PLB_OK; }
+    int set_stream(void* s) override {
+        // NULL / legacy stream requests keep the engine's own blocking stream (needed for graph capture)
+        if (s == nullptr || (cudaStream_t)s == cudaStreamLegacy) { stream = own_stream; }
+        else { stream = (cudaStream_t)s; }
+        prof_stream = stream;
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+        return PLB_OK;
+    }
     int synchronize() override { PLB_CUDA(cudaStreamSynchronize(stream)); return PLB_OK; }
 
     int check_slot(int s) { PLB_REQUIRE(s >= 0 && s < cfg.max_frames, "frame slot out of range"); return PLB_OK; }
@@ -281,6 +315,7 @@ struct Engine : plb_engine {
 
     int set_frame(int slot, const double* x, const double* v, const double* F, const double* C) override {
         if (int r = check_slot(slot)) return r;
+        stored[slot] = 0;
         double *dx, *dv, *dF, *dC;
         if (int r = upload_aos(x, v, F, C, &dx, &dv, &dF, &dC)) return r;
         k_pack_frame<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, n_pad, frame_base(slot), d_perm, dx, dv, dF, dC);
@@ -296,6 +331,7 @@ struct Engine : plb_engine {
         if (int r = check_slot(src)) return r;
         if (int r = check_slot(dst)) return r;
         if (src == dst) return PLB_OK;
+        stored[dst] = 0;
         PLB_CUDA(cudaMemcpyAsync(frame_base(dst), frame_base(src), (size_t)24 * n_pad * sizeof(T), cudaMemcpyDeviceToDevice, stream));
         return PLB_OK;
     }
@@ -327,6 +363,33 @@ struct Engine : plb_engine {
         std::swap(d_perm, d_perm2);
         launches += 3;
         PLB_CUDA(cudaGetLastError());
+        std::fill(stored.begin(), stored.end(), 0);
+        // size the forward-grid store from the active-block count of this frame (2x margin + 256 blocks)
+        if (sparse && cfg.kernel_variant == 0) {
+            k_mark_only<T><<<blocks(n), kBlock, 0, stream>>>(P, frame_base(slot), n_pad, d_flags);
+            compact_blocks();
+            int cnt = 0;
+            PLB_CUDA(cudaMemcpyAsync(&cnt, d_nactive, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            PLB_CUDA(cudaStreamSynchronize(stream));
+            int want = std::min(n_blocks, 2 * cnt + 256);
+            if (want > store.cap) {
+                cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt);
+                store.vals = nullptr; store.ids = nullptr; store.cnt = nullptr; store.cap = 0;
+                size_t vb = (size_t)cfg.max_frames * want * kBlkNodes * sizeof(Vec4<T>);
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                if (vb + ((size_t)2 << 30) < free_b && cudaMalloc(&store.vals, vb) == cudaSuccess) {
+                    PLB_CUDA(cudaMalloc(&store.ids, (size_t)cfg.max_frames * want * sizeof(int)));
+                    PLB_CUDA(cudaMalloc(&store.cnt, (size_t)cfg.max_frames * sizeof(int)));
+                    store.cap = want;
+                } else {
+                    cudaGetLastError();      // not enough memory: keep recomputing P2G in the backward pass
+                    store.vals = nullptr;
+                }
+                for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+                graphs.clear();
+            }
+        }
         return PLB_OK;
     }
     int frame_ptr(int slot, void** ptr, long long* np, int* sb) override {
@@ -401,12 +464,10 @@ struct Engine : plb_engine {
         k_compact<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags, d_list, d_nactive);
         launches++;
     }
-    int substep_fwd(int si, int so, int pf) override {
-        if (int r = check_slot(si)) return r;
-        if (int r = check_slot(so)) return r;
-        if (int r = check_pf(pf, 1)) return r;
-        PLB_REQUIRE(si != so, "in-place substep");
-        int nb = blocks(cfg.n_particles);
+    // Enqueue one forward substep.  Slots/poses are given as SlotRef so the same code serves direct launches
+    // (absolute indices) and graph capture (cursor-relative indices).
+    void enqueue_fwd(SlotRef si, SlotRef so, SlotRef pf) {
+        const int nb = blocks(cfg.n_particles);
         prof_begin(K_P2G);
         if (tile_scatter)
             k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
@@ -415,7 +476,7 @@ struct Engine : plb_engine {
         prof_end(); prof_begin(K_GRID_FWD);
         if (sparse) {
             compact_blocks();
-            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive);
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si);
         } else {
             k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
         }
@@ -423,27 +484,26 @@ struct Engine : plb_engine {
         k_g2p<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, grid_out);
         prof_end();
         launches += 3;
-        PLB_CUDA(cudaGetLastError());
-        return PLB_OK;
     }
-    int substep_bwd(int si, int pf) override {
-        if (int r = check_slot(si)) return r;
-        if (int r = check_pf(pf, 1)) return r;
-        int nb = blocks(cfg.n_particles), ng = blocks(n_nodes);
-        T* a_next = adj[cur];
-        T* a_cur = adj[cur ^ 1];
+    // One backward substep; `restore` = the forward grid of this slot is in the store.
+    void enqueue_bwd(SlotRef si, SlotRef pf, bool restore, T* a_next, T* a_cur) {
+        const int nb = blocks(cfg.n_particles), ng = blocks(n_nodes);
+        GridStore<T> nostore{nullptr, nullptr, nullptr, nullptr, 0};
         prof_begin(K_P2G_RECOMPUTE);
-        if (tile_scatter)
-            k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
-        else
-            k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
-        prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
-        if (sparse) {
-            compact_blocks();
-            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, d_list, d_nactive);
+        if (restore) {
+            k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid_in, d_list, d_nactive, store, si);
         } else {
-            k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
+            if (tile_scatter)
+                k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
+            else
+                k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
+            if (sparse) compact_blocks();
         }
+        prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
+        if (sparse)
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, d_list, d_nactive, nostore, si);
+        else
+            k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
         prof_end(); prof_begin(K_G2P_BWD);
         if (tile_scatter)
             k_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
@@ -458,8 +518,85 @@ struct Engine : plb_engine {
         k_p2g_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in);
         prof_end();
         launches += 5;
+    }
+    static SlotRef abs_ref(int v) { SlotRef r; r.cur = nullptr; r.idx = 0; r.rel = v; return r; }
+    SlotRef cur_ref(int idx, int rel) const { SlotRef r; r.cur = d_cursor; r.idx = idx; r.rel = rel; return r; }
+
+    int substep_fwd(int si, int so, int pf) override {
+        if (int r = check_slot(si)) return r;
+        if (int r = check_slot(so)) return r;
+        if (int r = check_pf(pf, 1)) return r;
+        PLB_REQUIRE(si != so, "in-place substep");
+        enqueue_fwd(abs_ref(si), abs_ref(so), abs_ref(pf));
+        stored[si] = store.vals != nullptr;
+        stored[so] = 0;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    int substep_bwd(int si, int pf) override {
+        if (int r = check_slot(si)) return r;
+        if (int r = check_pf(pf, 1)) return r;
+        enqueue_bwd(abs_ref(si), abs_ref(pf), stored[si] && store.vals, adj[cur], adj[cur ^ 1]);
         cur ^= 1;
         PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+
+    // ---- whole env steps: one captured CUDA graph per (direction, n, adjoint parity, stored), replayed with a new cursor
+    int launch_graph(const GraphKey& key, int slot0, int pf0) {
+        auto it = graphs.find(key);
+        if (it == graphs.end()) {
+            cudaGraph_t g = nullptr;
+            long long l0 = launches;
+            PLB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            if (key.dir == 0) {
+                for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
+            } else {
+                int c = key.parity;
+                for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), key.stored != 0, adj[c], adj[c ^ 1]); c ^= 1; }
+            }
+            cudaError_t ce = cudaStreamEndCapture(stream, &g);
+            launches = l0;
+            if (ce != cudaSuccess) { err = std::string("graph capture: ") + cudaGetErrorString(ce); return PLB_ERR_CUDA; }
+            cudaGraphExec_t ge = nullptr;
+            PLB_CUDA(cudaGraphInstantiate(&ge, g, 0));
+            cudaGraphDestroy(g);
+            it = graphs.emplace(key, ge).first;
+        }
+        k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
+        PLB_CUDA(cudaGraphLaunch(it->second, stream));
+        launches += (key.dir == 0 ? 4 : (key.stored ? 6 : 7)) * (long long)key.n + 1;
+        return PLB_OK;
+    }
+    int step_fwd(int slot0, int pf0, int n) override {
+        if (n <= 0) return PLB_OK;
+        if (int r = check_slot(slot0)) return r;
+        if (int r = check_slot(slot0 + n)) return r;
+        if (int r = check_pf(pf0, n)) return r;
+        if (!use_graphs || prof_on || !sparse) {
+            for (int i = 0; i < n; i++) if (int r = substep_fwd(slot0 + i, slot0 + i + 1, pf0 + i)) return r;
+            return PLB_OK;
+        }
+        GraphKey key{0, n, 0, store.vals != nullptr};
+        if (int r = launch_graph(key, slot0, pf0)) return r;
+        for (int i = 0; i < n; i++) stored[slot0 + i] = store.vals != nullptr;
+        stored[slot0 + n] = 0;
+        return PLB_OK;
+    }
+    int step_bwd(int slot0, int pf0, int n) override {
+        if (n <= 0) return PLB_OK;
+        if (int r = check_slot(slot0 + n - 1)) return r;
+        if (int r = check_pf(pf0, n)) return r;
+        int n_stored = 0;
+        for (int i = 0; i < n; i++) n_stored += stored[slot0 + i] ? 1 : 0;
+        bool uniform = (n_stored == 0 || n_stored == n);
+        if (!use_graphs || prof_on || !sparse || !uniform) {
+            for (int i = n - 1; i >= 0; i--) if (int r = substep_bwd(slot0 + i, pf0 + i)) return r;
+            return PLB_OK;
+        }
+        GraphKey key{1, n, cur, (n_stored == n && store.vals) ? 1 : 0};
+        if (int r = launch_graph(key, slot0, pf0)) return r;
+        cur ^= (n & 1);
         return PLB_OK;
     }
 
@@ -479,7 +616,10 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaStreamSynchronize(stream));
         return PLB_OK;
     }
-    int get_adjoint(double* gx, double* gv, double* gF, double* gC) override { return download_aos(adj[cur], gx, gv, gF, gC); }
+    int get_adjoint(double* gx, double* gv, double* gF, double* gC) override {
+        if (int r = check_overflow()) return r;
+        return download_aos(adj[cur], gx, gv, gF, gC);
+    }
     int get_prim_grads(int pf0, int n, double* out) override {
         if (int r = check_pf(pf0, n - 1)) return r;
         std::vector<double> tmp((size_t)n * PLB_MAX_PRIM * 8);
@@ -491,9 +631,22 @@ struct Engine : plb_engine {
                 std::memcpy(out + ((size_t)f * cfg.n_primitives + k) * 8, tmp.data() + ((size_t)f * PLB_MAX_PRIM + k) * 8, 8 * sizeof(double));
         return PLB_OK;
     }
+    int check_overflow() {
+        int ov = 0;
+        PLB_CUDA(cudaMemcpyAsync(&ov, store.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        if (ov) {
+            PLB_CUDA(cudaMemsetAsync(store.overflow, 0, sizeof(int), stream));
+            err = "forward-grid store overflow: the material spread over more 4^3 blocks than reserved at the last "
+                  "plb_sort_particles; gradients of this episode are invalid (re-sort the state or create the engine with kernel_variant=2)";
+            return PLB_ERR_NOMEM;
+        }
+        return PLB_OK;
+    }
     int get_action_grad(int n_steps, int S, double* out) override {
         int nf = n_steps * S;
         if (int r = check_pf(nf)) return r;
+        if (int r = check_overflow()) return r;
         std::vector<double> g((size_t)(nf + 1) * PLB_MAX_PRIM * 8);
         PLB_CUDA(cudaMemcpyAsync(g.data(), d_prim_grad, g.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         PLB_CUDA(cudaStreamSynchronize(stream));
@@ -640,7 +793,7 @@ struct Engine : plb_engine {
     int count_active(int slot, long long* n) override {
         if (int r = check_slot(slot)) return r;
         // scatter this frame's particles (no F store), count, then clear grid_in again
-        k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, slot, 0, material(), grid_in, nullptr);
+        k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(slot), abs_ref(slot), 0, material(), grid_in, nullptr);
         PLB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
         k_count_active<T><<<blocks(n_nodes), kBlock, 0, stream>>>(n_nodes, grid_in, d_count);
         launches += 2;
@@ -693,15 +846,9 @@ int plb_set_softness(plb_engine* e, double s) { return e->set_softness(s); }
 int plb_set_action(plb_engine* e, int step, int S, const double* a, int n) { return e->set_action(step, S, a, n); }
 int plb_kinematics(plb_engine* e, int pf, int n) { return e->kinematics(pf, n); }
 int plb_substep_fwd(plb_engine* e, int si, int so, int pf) { return e->substep_fwd(si, so, pf); }
-int plb_step_fwd(plb_engine* e, int slot0, int pf0, int n) {
-    for (int i = 0; i < n; i++) { int r = e->substep_fwd(slot0 + i, slot0 + i + 1, pf0 + i); if (r) return r; }
-    return PLB_OK;
-}
+int plb_step_fwd(plb_engine* e, int slot0, int pf0, int n) { return e->step_fwd(slot0, pf0, n); }
 int plb_substep_bwd(plb_engine* e, int si, int pf) { return e->substep_bwd(si, pf); }
-int plb_step_bwd(plb_engine* e, int slot0, int pf0, int n) {
-    for (int i = n - 1; i >= 0; i--) { int r = e->substep_bwd(slot0 + i, pf0 + i); if (r) return r; }
-    return PLB_OK;
-}
+int plb_step_bwd(plb_engine* e, int slot0, int pf0, int n) { return e->step_bwd(slot0, pf0, n); }
 int plb_zero_grads(plb_engine* e) { return e->zero_grads(); }
 int plb_set_adjoint(plb_engine* e, const double* gx, const double* gv, const double* gF, const double* gC) { return e->set_adjoint(gx, gv, gF, gC); }
 int plb_get_adjoint(plb_engine* e, double* gx, double* gv, double* gF, double* gC) { return e->get_adjoint(gx, gv, gF, gC); }

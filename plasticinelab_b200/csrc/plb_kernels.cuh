@@ -8,6 +8,22 @@ namespace plb {
 
 constexpr int kBlock = 128;
 
+// A frame index given either absolutely (cur == nullptr) or relative to a device-resident cursor.  The cursor form
+// lets one captured CUDA graph of an env step (S substeps) be replayed for every env step: only the 3-int cursor
+// (slot_in base, slot_out base, primitive-frame base) changes between launches.
+struct SlotRef {
+    const int* cur; int idx; int rel;
+    __device__ __forceinline__ int get() const { return (cur ? cur[idx] : 0) + rel; }
+};
+__global__ void k_set_cursor(int* cur, int a, int b, int c) { cur[0] = a; cur[1] = b; cur[2] = c; }
+
+// Per-slot compact copy of the forward grid (momentum, mass) of the substep that STARTED at that slot: the list of
+// active 4^3 blocks and their 64 Vec4 each.  Written by the forward grid kernel, read by the backward pass instead
+// of re-running P2G (SVD + 27-node scatter per particle).
+template <class T> struct GridStore {
+    Vec4<T>* vals; int* ids; int* cnt; int* overflow; int cap;     // cap blocks per slot; vals == nullptr: disabled
+};
+
 // poses of frame pf and pf+1 converted to T in shared memory (2 * n_prim * 8 doubles are read per block)
 template <class T>
 __device__ __forceinline__ void load_poses_smem(const double* __restrict__ traj, int pf, int n_prim, Pose<T>* s0, Pose<T>* s1) {
@@ -65,6 +81,12 @@ __device__ __forceinline__ void mark_blocks(const SimConst<T>& P, V3<T> x, unsig
                 int id = block_id(nbx, b[0] + 2 * a, b[1] + 2 * c, b[2] + 2 * e);
                 if (!flags[id]) flags[id] = 1;
             }
+}
+
+template <class T>
+__global__ void k_mark_only(SimConst<T> P, T* frame, long long n_pad, unsigned char* flags) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P.n_particles) mark_blocks<T>(P, load_x(frame_at(frame, 0, n_pad), p), flags);
 }
 
 __global__ void k_compact(int n_blocks, unsigned char* flags, int* list, int* count) {
@@ -133,18 +155,18 @@ __device__ __forceinline__ void warp_tile_flush(const Vec4<T>* tile, int lane, b
 
 // ------------------------------------------------------------------------------------------------ substep
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long long n_pad, int slot_in, int slot_out,
+__global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
                                                 int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
-    FramePtr<T> fin = frame_at(frames, slot_in, n_pad);
-    p2g_body<T>(p, P, fin, frame_at(frames, slot_out, n_pad), store_F_out != 0, mat, grid_in);
+    FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
+    p2g_body<T>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in);
     if (flags) mark_blocks<T>(P, load_x(fin, p), flags);
 }
 
 // same, with the warp-tile scatter (dynamic shared memory: kBlock/32 tiles)
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, long long n_pad, int slot_in, int slot_out,
+__global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
                                                      int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -153,9 +175,9 @@ __global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, l
     const bool valid = p < P.n_particles;
     int b[3] = {0, 0, 0};
     if (valid) {
-        FramePtr<T> fin = frame_at(frames, slot_in, n_pad);
+        FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
         WarpTileScatter<T> sc{tile, lane};
-        p2g_body<T, WarpTileScatter<T>>(p, P, fin, frame_at(frames, slot_out, n_pad), store_F_out != 0, mat, sc);
+        p2g_body<T, WarpTileScatter<T>>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, sc);
         V3<T> x = load_x(fin, p);
 #pragma unroll
         for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
@@ -165,22 +187,58 @@ __global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, l
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimSet<T> prims, const double* traj, int pf,
+__global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pf,
                                                             Vec4<T>* grid_in, Vec4<T>* grid_out, int clear_in,
-                                                            const int* __restrict__ list, const int* __restrict__ count) {
+                                                            const int* __restrict__ list, const int* __restrict__ count,
+                                                            GridStore<T> store, SlotRef slot) {
     __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
-    load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
+    load_poses_smem<T>(traj, pf.get(), P.n_prim, s0, s1);
     const int per_cta = kBlock / kBlkNodes, n = *count;
-    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta)
-        grid_fwd_body<T>(block_node(P.n_grid, list[e], threadIdx.x & (kBlkNodes - 1)), P, prims, s0, s1, grid_in, grid_out, clear_in != 0);
+    const int local = threadIdx.x & (kBlkNodes - 1);
+    Vec4<T>* svals = nullptr; int* sids = nullptr;
+    if (store.vals) {
+        const long long sl = slot.get();
+        svals = store.vals + sl * store.cap * kBlkNodes;
+        sids = store.ids + sl * store.cap;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            store.cnt[sl] = n <= store.cap ? n : -1;
+            if (n > store.cap) *store.overflow = 1;
+        }
+    }
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
+        const int blk = list[e];
+        const long long node = block_node(P.n_grid, blk, local);
+        if (svals && e < store.cap) {
+            svals[(long long)e * kBlkNodes + local] = grid_in[node];
+            if (local == 0) sids[e] = blk;
+        }
+        grid_fwd_body<T>(node, P, prims, s0, s1, grid_in, grid_out, clear_in != 0);
+    }
+}
+
+// backward: re-install the stored forward grid of `slot` (values + active list) instead of recomputing P2G
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_restore_blocks(int n_grid, Vec4<T>* grid_in, int* list, int* count, GridStore<T> store, SlotRef slot) {
+    const long long sl = slot.get();
+    const int n = store.cnt[sl];
+    const Vec4<T>* svals = store.vals + sl * store.cap * kBlkNodes;
+    const int* sids = store.ids + sl * store.cap;
+    const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count = n;
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
+        const int blk = sids[e];
+        grid_in[block_node(n_grid, blk, local)] = svals[(long long)e * kBlkNodes + local];
+        if (local == 0) list[e] = blk;
+    }
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse(SimConst<T> P, PrimSet<T> prims, const double* traj, int pf,
+__global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pfr,
                                                             Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, int clear,
                                                             double* prim_grad, const int* __restrict__ list,
                                                             const int* __restrict__ count) {
     __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
+    const int pf = pfr.get();
     load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
     const int per_cta = kBlock / kBlkNodes, n = *count;
     const int rounds = (n + gridDim.x * per_cta - 1) / (gridDim.x * per_cta);
@@ -204,34 +262,34 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse(SimConst<T> P, PrimS
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_grid_fwd(SimConst<T> P, PrimSet<T> prims, const double* traj, int pf,
+__global__ void __launch_bounds__(kBlock) k_grid_fwd(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pf,
                                                      Vec4<T>* grid_in, Vec4<T>* grid_out, int clear_in, long long n_nodes) {
     __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
-    load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
+    load_poses_smem<T>(traj, pf.get(), P.n_prim, s0, s1);
     long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= n_nodes) return;
     grid_fwd_body<T>(node, P, prims, s0, s1, grid_in, grid_out, clear_in != 0);
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_g2p(SimConst<T> P, T* frames, long long n_pad, int slot_in, int slot_out,
+__global__ void __launch_bounds__(kBlock) k_g2p(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
                                                 const Vec4<T>* grid_out) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
-    g2p_body<T>(p, P, frame_at(frames, slot_in, n_pad), frame_at(frames, slot_out, n_pad), grid_out);
+    g2p_body<T>(p, P, frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_out.get(), n_pad), grid_out);
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_g2p_bwd(SimConst<T> P, T* frames, long long n_pad, int slot_in, T* adj_next,
+__global__ void __launch_bounds__(kBlock) k_g2p_bwd(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
                                                     T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
-    g2p_bwd_body<T>(p, P, frame_at(frames, slot_in, n_pad), frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad),
+    g2p_bwd_body<T>(p, P, frame_at(frames, slot_in.get(), n_pad), frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad),
                     grid_out, g_out);
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, int slot_in, T* adj_next,
+__global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
                                                          T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -240,7 +298,7 @@ __global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frame
     const bool valid = p < P.n_particles;
     int b[3] = {0, 0, 0};
     if (valid) {
-        FramePtr<T> fin = frame_at(frames, slot_in, n_pad);
+        FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
         WarpTileScatter<T> sc{tile, lane};
         g2p_bwd_body<T, WarpTileScatter<T>>(p, P, fin, frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad), grid_out, sc);
         V3<T> x = load_x(fin, p);
@@ -251,10 +309,11 @@ __global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frame
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_grid_bwd(SimConst<T> P, PrimSet<T> prims, const double* traj, int pf,
+__global__ void __launch_bounds__(kBlock) k_grid_bwd(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pfr,
                                                      Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, int clear,
                                                      double* prim_grad, long long n_nodes) {
     __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
+    const int pf = pfr.get();
     load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
     long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     PoseGrad<T> g0[PLB_MAX_PRIM], g1[PLB_MAX_PRIM];
@@ -273,11 +332,11 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd(SimConst<T> P, PrimSet<T> p
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_p2g_bwd(SimConst<T> P, T* frames, long long n_pad, int slot_in, T* adj_next,
+__global__ void __launch_bounds__(kBlock) k_p2g_bwd(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
                                                     T* adj_cur, Material<T> mat, const Vec4<T>* g_in) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
-    p2g_bwd_body<T>(p, P, frame_at(frames, slot_in, n_pad), frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad), mat, g_in);
+    p2g_bwd_body<T>(p, P, frame_at(frames, slot_in.get(), n_pad), frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad), mat, g_in);
 }
 
 // ------------------------------------------------------------------------------------------------ loss
