@@ -268,3 +268,39 @@ def _substep_gpu_noset(eng, n, P, poses, softness, adj):
     gp = np.zeros((2, max(P, 1), 8))
     eng.call("plb_get_primitive_grads", 0, 2, D(gp))
     return (xo, vo, Co, Fo), (gx, gv, gC, gF), gp
+
+
+def test_engine_matches_committed_golden_vectors():
+    """tests/golden/*.npz (made by tests/golden/make_golden.py from the oracle): episode loss / action gradient / final state
+    of the two-sphere squeeze, and the first env step of stock Move-v1.  float64 engine, 1e-7 relative on gradients."""
+    import os
+    from plasticinelab_b200.config import load_dict
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.optimizer.solver import Solver
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    g = np.load(os.path.join(gold, 'episode_two_spheres_q0.5.npz'))
+    cfg = _episode_cfg()
+    for mode, key in ((True, 'grad_taichi'), (False, 'grad_argmin')):
+        env = TaichiEnv(cfg, dtype='float64')
+        env.initialize()
+        env.loss.contact_grad_all = mode
+        env.loss.load_target_density(grids=g['target32'])
+        env.loss.set_weights(10, 10, 1, False)
+        solver = Solver(env, None, None, n_iters=1, softness=666., horizon=3)
+        solver.total_steps = 0
+        loss, grad = solver.forward(env.get_state()['state'], g['actions'])
+        assert abs(loss - float(g['loss'])) < 1e-9 * abs(float(g['loss']))
+        assert H.relerr(grad, g[key]) < 1e-7
+        assert np.abs(env.simulator.get_x(env.simulator.cur) - g['final_x']).max() < 1e-11
+    from plasticinelab_b200.envs import make
+    m = np.load(os.path.join(gold, 'move_v1_first_step.npz'))
+    env = make('Move-v1', dtype='float64')
+    tenv = env.unwrapped.taichi_env
+    env.reset()
+    tenv.set_state(tenv.get_state()['state'], 666.0, False)
+    tenv.step(m['action'][0])
+    info = tenv.compute_loss()
+    st = tenv.simulator.get_state(tenv.simulator.cur)
+    assert abs(info['loss'] - float(m['step_loss'])) < 1e-9 * float(m['step_loss'])
+    assert np.abs(st[0][m['sel']] - m['x']).max() < 1e-12 and np.abs(st[1][m['sel']] - m['v']).max() < 1e-9
+    assert np.abs(st[2][m['sel']] - m['F']).max() < 1e-11
