@@ -116,18 +116,27 @@ PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const F
     p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine);
     if (store_F_out) store_F(out, p, new_F);
     Stencil<T> st = make_stencil(x, P.inv_dx);
-    V3<T> mvel = P.p_mass * v;
+    // momentum_o = w_o (p_mass v + affine ((o - fx) dx)) = w_o (m0 + i c0 + j c1 + k c2): the affine part is evaluated
+    // incrementally along the three stencil axes (81 + 27 + 9 FMAs instead of 27 mat-vecs)
+    V3<T> c0 = mk3<T>(affine.m[0][0] * P.dx, affine.m[1][0] * P.dx, affine.m[2][0] * P.dx);
+    V3<T> c1 = mk3<T>(affine.m[0][1] * P.dx, affine.m[1][1] * P.dx, affine.m[2][1] * P.dx);
+    V3<T> c2 = mk3<T>(affine.m[0][2] * P.dx, affine.m[1][2] * P.dx, affine.m[2][2] * P.dx);
+    V3<T> m0 = P.p_mass * v - (st.fx.x * c0 + st.fx.y * c1 + st.fx.z * c2);
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+        V3<T> mi = m0 + T(i) * c0;
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+        for (int j = 0; j < 3; j++) {
+            V3<T> mij = mi + T(j) * c1;
+            T wij = st.w[i][0] * st.w[j][1];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
-                V3<T> dpos = mk3<T>((T(i) - st.fx.x) * P.dx, (T(j) - st.fx.y) * P.dx, (T(k) - st.fx.z) * P.dx);
-                V3<T> mom = w * (mvel + mv(affine, dpos));
+                T w = wij * st.w[k][2];
+                V3<T> mom = w * (mij + T(k) * c2);
                 sc.add((i * 3 + j) * 3 + k, st.b[0] + i, st.b[1] + j, st.b[2] + k, mk4<T>(mom.x, mom.y, mom.z, w * P.p_mass));
             }
+        }
+    }
 }
 template <class T>
 PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,

@@ -731,7 +731,8 @@ struct Engine : plb_engine {
         int nb = blocks(cfg.n_particles);
         k_loss_init<<<1, 32, 0, stream>>>(d_acc);
         PLB_CUDA(cudaMemsetAsync(grid_mass, 0, n_nodes * sizeof(T), stream));
-        k_loss_mass<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
+        if (tile_scatter) k_loss_mass_tile<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
+        else k_loss_mass<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
         int rb = (int)std::min<long long>((n_nodes + 255) / 256, 148 * 8);
         k_loss_reduce<T><<<rb, 256, 0, stream>>>(grid_mass, target, target_sdf, n_nodes, d_acc);
         k_loss_contact<T><<<nb, kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, d_acc);

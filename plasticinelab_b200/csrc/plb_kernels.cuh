@@ -122,32 +122,45 @@ template <class T> struct WarpTileScatter {
     int lane;
     __device__ __forceinline__ void add(int slot, int, int, int, Vec4<T> v) const { tile[slot * kTileStride + lane] = v; }
 };
+// payload helpers: the tile carries Vec4 (momentum+mass, velocity adjoint) or a scalar (loss mass)
+template <class T> __device__ __forceinline__ void pay_zero(Vec4<T>& a) { a = mk4<T>(T(0), T(0), T(0), T(0)); }
+template <class T> __device__ __forceinline__ void pay_acc(Vec4<T>& a, const Vec4<T>& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+template <class T> __device__ __forceinline__ void pay_red(Vec4<T>* dst, const Vec4<T>& a) { scatter_add4(dst, a); }
+__device__ __forceinline__ void pay_zero(float& a) { a = 0.f; }
+__device__ __forceinline__ void pay_zero(double& a) { a = 0.0; }
+__device__ __forceinline__ void pay_acc(float& a, const float& v) { a += v; }
+__device__ __forceinline__ void pay_acc(double& a, const double& v) { a += v; }
+__device__ __forceinline__ void pay_red(float* dst, const float& a) { atomicAdd(dst, a); }
+__device__ __forceinline__ void pay_red(double* dst, const double& a) { atomicAdd(dst, a); }
 
 // valid: lane holds a particle; b: its base cell.  All 32 lanes must call.
-template <class T>
-__device__ __forceinline__ void warp_tile_flush(const Vec4<T>* tile, int lane, bool valid, const int b[3], int n_grid, Vec4<T>* grid) {
+// Groups are maximal RUNS of consecutive lanes with the same base cell (after the spatial sort a warp is a few runs;
+// for arbitrary order the result is still correct, the runs just get short).  One pass over the 32 tile columns:
+// lane q < 27 accumulates node q and, at the end of each run, adds the run's sum to the grid with one vector RED.
+template <class T, class Pay>
+__device__ __forceinline__ void warp_tile_flush(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid) {
     __syncwarp();
     const unsigned full = 0xffffffffu;
-    int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
-    unsigned remaining = __ballot_sync(full, valid);
+    const int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
+    const int next = __shfl_down_sync(full, key, 1);
+    const unsigned run_end = __ballot_sync(full, lane == 31 || next != key);
+    const unsigned vmask = __ballot_sync(full, valid);
     const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;       // node offset owned by this lane (lane < 27)
-    while (remaining) {
-        int leader = __ffs(remaining) - 1;
-        int lkey = __shfl_sync(full, key, leader);
-        unsigned group = __ballot_sync(full, key == lkey);
-        remaining &= ~group;
-        if (lane < 27) {
-            Vec4<T> acc = mk4<T>(T(0), T(0), T(0), T(0));
-            const Vec4<T>* row = tile + lane * kTileStride;
-            unsigned g = group;
-            while (g) {
-                int j = __ffs(g) - 1;
-                g &= g - 1;
-                Vec4<T> v = row[j];
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
+    Pay acc;
+    pay_zero(acc);
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if ((vmask >> j) & 1u) {                                       // warp-uniform
+            pay_acc(acc, row[j]);
+            if ((run_end >> j) & 1u) {                                 // warp-uniform
+                const int rkey = __shfl_sync(full, key, j);
+                if (lane < 27) {
+                    int bk = rkey % n_grid, bj = (rkey / n_grid) % n_grid, bi = rkey / (n_grid * n_grid);
+                    pay_red(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
+                }
+                pay_zero(acc);
             }
-            int bk = lkey % n_grid, bj = (lkey / n_grid) % n_grid, bi = lkey / (n_grid * n_grid);
-            scatter_add4(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
         }
     }
     __syncwarp();
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, l
         for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
         if (flags) mark_blocks<T>(P, x, flags);
     }
-    warp_tile_flush<T>(tile, lane, valid, b, P.n_grid, grid_in);
+    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, grid_in);
 }
 
 template <class T>
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frame
 #pragma unroll
         for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
     }
-    warp_tile_flush<T>(tile, lane, valid, b, P.n_grid, g_out);
+    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, g_out);
 }
 
 template <class T>
@@ -348,6 +361,30 @@ __global__ void __launch_bounds__(kBlock) k_loss_mass(SimConst<T> P, T* frames, 
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
     loss_mass_body<T>(p, P, frame_at(frames, slot, n_pad), grid_mass);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_loss_mass_tile(SimConst<T> P, T* frames, long long n_pad, int slot, T* grid_mass) {
+    __shared__ T tiles[(kBlock / 32) * kTileVec4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* tile = tiles + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    int b[3] = {0, 0, 0};
+    if (valid) {
+        V3<T> x = load_x(frame_at(frames, slot, n_pad), p);
+        Stencil<T> st = make_stencil(x, P.inv_dx);
+#pragma unroll
+        for (int d = 0; d < 3; d++) b[d] = st.b[d];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    tile[((i * 3 + j) * 3 + k) * kTileStride + lane] = st.w[i][0] * st.w[j][1] * st.w[k][2] * P.p_mass;
+    }
+    warp_tile_flush<T, T>(tile, lane, valid, b, P.n_grid, grid_mass);
 }
 
 __global__ void k_loss_init(double* acc) {

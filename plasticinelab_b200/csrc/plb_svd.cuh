@@ -34,9 +34,12 @@ PLB_HD void svd3(const M3<T>& F, M3<T>& U, V3<T>& sig, M3<T>& V) {
             T alpha = dot(a[p], a[p]), beta = dot(a[q], a[q]), gamma = dot(a[p], a[q]);
             if (gamma * gamma > SvdTol<T>::tol2 * alpha * beta) {
                 rotated = true;
-                T zeta = (beta - alpha) / (T(2) * gamma);
-                T t = (zeta >= T(0) ? T(1) : T(-1)) / (plb_abs(zeta) + plb_sqrt(T(1) + zeta * zeta));
-                T c = T(1) / plb_sqrt(T(1) + t * t);
+                T zeta = (beta - alpha) * plb_rcp(T(2) * gamma);
+                T az = plb_abs(zeta);
+                T rt = T(1) + zeta * zeta;
+                T t = plb_rcp(az + rt * plb_rsqrt(rt));          // 1 / (|zeta| + sqrt(1 + zeta^2))
+                t = (zeta >= T(0)) ? t : -t;
+                T c = plb_rsqrt(T(1) + t * t);
                 T s = c * t;
                 V3<T> ap = c * a[p] - s * a[q], aq = s * a[p] + c * a[q];
                 a[p] = ap; a[q] = aq;

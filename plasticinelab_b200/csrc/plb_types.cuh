@@ -169,6 +169,18 @@ PLB_HD double plb_sin(double x) { return sin(x); }
 PLB_HD float  plb_cos(float x) { return cosf(x); }
 PLB_HD double plb_cos(double x) { return cos(x); }
 
+// Reciprocal and reciprocal square root used inside the Jacobi SVD.  double / host: exact IEEE forms.  float on the
+// device: MUFU approximation + one Newton step (<= 1 ulp), a third of the instructions of the IEEE div/sqrt sequences.
+PLB_HD double plb_rcp(double x) { return 1.0 / x; }
+PLB_HD double plb_rsqrt(double x) { return 1.0 / sqrt(x); }
+#if defined(__CUDA_ARCH__)
+PLB_HD float plb_rcp(float x) { float r = __frcp_rn(x); return r; }
+PLB_HD float plb_rsqrt(float x) { float r = rsqrtf(x); return r * (1.5f - 0.5f * x * r * r); }
+#else
+PLB_HD float plb_rcp(float x) { return 1.0f / x; }
+PLB_HD float plb_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
+
 // ti.max / ti.min value semantics and the gradient routing of Taichi's autodiff:
 //   max(a,b): d/da = [b < a], d/db = 1 - [b < a];   min(a,b): d/da = [a < b], d/db = 1 - [a < b].
 template <class T> PLB_HD T tmax(T a, T b) { return (b < a) ? a : b; }
