@@ -70,8 +70,7 @@ template <class T> PLB_HD V3<T> load_x(const FramePtr<T>& f, int p) {
 // ---- scatter primitives: red.global on the device, plain adds in the sequential host emulation
 #if defined(__CUDA_ARCH__)
 PLB_D void scatter_add4(Vec4<float>* addr, Vec4<float> v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 PLB_D void scatter_add4(Vec4<double>* addr, Vec4<double> v) {
     double* a = reinterpret_cast<double*>(addr);

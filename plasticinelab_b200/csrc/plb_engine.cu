@@ -153,6 +153,7 @@ struct Engine : plb_engine {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     size_t tile_smem = 0;
+    int flush_variant = 1;
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
     int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
     int* d_vals = nullptr; int* d_vals2 = nullptr; void* d_cub = nullptr; size_t cub_bytes = 0; T* frame_tmp = nullptr;
@@ -233,6 +234,7 @@ struct Engine : plb_engine {
         PLB_REQUIRE(c.n_grid % 4 == 0, "n_grid must be a multiple of 4");
         sparse = c.kernel_variant != 1;
         tile_scatter = c.kernel_variant == 0;
+        if (const char* fv = getenv("PLB_FLUSH")) flush_variant = atoi(fv);
         tile_smem = (size_t)(kBlock / 32) * kTileVec4 * sizeof(Vec4<T>);
         if (tile_scatter) {
             PLB_CUDA(cudaFuncSetAttribute(k_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
@@ -470,7 +472,7 @@ struct Engine : plb_engine {
         const int nb = blocks(cfg.n_particles);
         prof_begin(K_P2G);
         if (tile_scatter)
-            k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
+            k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr, flush_variant);
         else
             k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
         prof_end(); prof_begin(K_GRID_FWD);
@@ -494,7 +496,7 @@ struct Engine : plb_engine {
             k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid_in, d_list, d_nactive, store, si);
         } else {
             if (tile_scatter)
-                k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
+                k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr, flush_variant);
             else
                 k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
             if (sparse) compact_blocks();
@@ -506,7 +508,7 @@ struct Engine : plb_engine {
             k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
         prof_end(); prof_begin(K_G2P_BWD);
         if (tile_scatter)
-            k_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
+            k_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out, flush_variant);
         else
             k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
         prof_end(); prof_begin(K_GRID_BWD);
@@ -731,7 +733,7 @@ struct Engine : plb_engine {
         int nb = blocks(cfg.n_particles);
         k_loss_init<<<1, 32, 0, stream>>>(d_acc);
         PLB_CUDA(cudaMemsetAsync(grid_mass, 0, n_nodes * sizeof(T), stream));
-        if (tile_scatter) k_loss_mass_tile<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
+        if (tile_scatter) k_loss_mass_tile<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass, flush_variant);
         else k_loss_mass<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
         int rb = (int)std::min<long long>((n_nodes + 255) / 256, 148 * 8);
         k_loss_reduce<T><<<rb, 256, 0, stream>>>(grid_mass, target, target_sdf, n_nodes, d_acc);

@@ -137,25 +137,62 @@ __device__ __forceinline__ void pay_red(double* dst, const double& a) { atomicAd
 // Groups are maximal RUNS of consecutive lanes with the same base cell (after the spatial sort a warp is a few runs;
 // for arbitrary order the result is still correct, the runs just get short).  One pass over the 32 tile columns:
 // lane q < 27 accumulates node q and, at the end of each run, adds the run's sum to the grid with one vector RED.
+// Variant A ("groups"): loop over the distinct cells of the warp, gather the lanes of each cell.
 template <class T, class Pay>
-__device__ __forceinline__ void warp_tile_flush(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid) {
+__device__ __forceinline__ void warp_tile_flush_groups(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid) {
+    __syncwarp();
+    const unsigned full = 0xffffffffu;
+    int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
+    unsigned remaining = __ballot_sync(full, valid);
+    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
+    while (remaining) {
+        int leader = __ffs(remaining) - 1;
+        int lkey = __shfl_sync(full, key, leader);
+        unsigned group = __ballot_sync(full, key == lkey);
+        remaining &= ~group;
+        if (lane < 27) {
+            Pay acc;
+            pay_zero(acc);
+            const Pay* row = tile + lane * kTileStride;
+            unsigned g = group;
+            while (g) {
+                int j = __ffs(g) - 1;
+                g &= g - 1;
+                pay_acc(acc, row[j]);
+            }
+            int bk = lkey % n_grid, bj = (lkey / n_grid) % n_grid, bi = lkey / (n_grid * n_grid);
+            pay_red(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
+        }
+    }
+    __syncwarp();
+}
+
+// Variant B ("runs"): groups are maximal RUNS of consecutive lanes with the same base cell (after the spatial sort a warp
+// is a few runs; for arbitrary order the result is still correct, the runs just get short).  One pass over the 32 tile
+// columns in chunks of 8 (8 independent LDS in flight), lane q < 27 accumulates node q and adds the sum of each run to
+// the grid with one vector RED at the run's last column.  Invalid lanes must have zero-filled their column.
+template <class T, class Pay>
+__device__ __forceinline__ void warp_tile_flush_runs(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid) {
     __syncwarp();
     const unsigned full = 0xffffffffu;
     const int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
     const int next = __shfl_down_sync(full, key, 1);
     const unsigned run_end = __ballot_sync(full, lane == 31 || next != key);
-    const unsigned vmask = __ballot_sync(full, valid);
     const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;       // node offset owned by this lane (lane < 27)
     const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
     Pay acc;
     pay_zero(acc);
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-        if ((vmask >> j) & 1u) {                                       // warp-uniform
-            pay_acc(acc, row[j]);
-            if ((run_end >> j) & 1u) {                                 // warp-uniform
-                const int rkey = __shfl_sync(full, key, j);
-                if (lane < 27) {
+    for (int c = 0; c < 4; c++) {
+        Pay v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = row[c * 8 + j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            pay_acc(acc, v[j]);
+            if ((run_end >> (c * 8 + j)) & 1u) {                       // warp-uniform
+                const int rkey = __shfl_sync(full, key, c * 8 + j);
+                if (lane < 27 && rkey >= 0) {
                     int bk = rkey % n_grid, bj = (rkey / n_grid) % n_grid, bi = rkey / (n_grid * n_grid);
                     pay_red(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
                 }
@@ -164,6 +201,20 @@ __device__ __forceinline__ void warp_tile_flush(const Pay* tile, int lane, bool 
         }
     }
     __syncwarp();
+}
+
+template <class T, class Pay>
+__device__ __forceinline__ void warp_tile_flush(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid, int variant) {
+    if (variant == 0) warp_tile_flush_groups<T, Pay>(tile, lane, valid, b, n_grid, grid);
+    else warp_tile_flush_runs<T, Pay>(tile, lane, valid, b, n_grid, grid);
+}
+
+// zero this lane's tile column (lanes without a particle, so that the run-based flush can read every column)
+template <class Pay> __device__ __forceinline__ void tile_zero_column(Pay* tile, int lane) {
+    Pay z;
+    pay_zero(z);
+#pragma unroll
+    for (int q = 0; q < 27; q++) tile[q * kTileStride + lane] = z;
 }
 
 // ------------------------------------------------------------------------------------------------ substep
@@ -180,7 +231,8 @@ __global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long l
 // same, with the warp-tile scatter (dynamic shared memory: kBlock/32 tiles)
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
-                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
+                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags,
+                                                     int flush_variant) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
@@ -195,8 +247,10 @@ __global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, l
 #pragma unroll
         for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
         if (flags) mark_blocks<T>(P, x, flags);
+    } else {
+        tile_zero_column(tile, lane);
     }
-    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, grid_in);
+    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, grid_in, flush_variant);
 }
 
 template <class T>
@@ -303,7 +357,7 @@ __global__ void __launch_bounds__(kBlock) k_g2p_bwd(SimConst<T> P, T* frames, lo
 
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
-                                                         T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+                                                         T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_variant) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
@@ -317,8 +371,10 @@ __global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frame
         V3<T> x = load_x(fin, p);
 #pragma unroll
         for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    } else {
+        tile_zero_column(tile, lane);
     }
-    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, g_out);
+    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, g_out, flush_variant);
 }
 
 template <class T>
@@ -364,7 +420,7 @@ __global__ void __launch_bounds__(kBlock) k_loss_mass(SimConst<T> P, T* frames, 
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_loss_mass_tile(SimConst<T> P, T* frames, long long n_pad, int slot, T* grid_mass) {
+__global__ void __launch_bounds__(kBlock) k_loss_mass_tile(SimConst<T> P, T* frames, long long n_pad, int slot, T* grid_mass, int flush_variant) {
     __shared__ T tiles[(kBlock / 32) * kTileVec4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* tile = tiles + warp * kTileVec4;
@@ -383,8 +439,10 @@ __global__ void __launch_bounds__(kBlock) k_loss_mass_tile(SimConst<T> P, T* fra
 #pragma unroll
                 for (int k = 0; k < 3; k++)
                     tile[((i * 3 + j) * 3 + k) * kTileStride + lane] = st.w[i][0] * st.w[j][1] * st.w[k][2] * P.p_mass;
+    } else {
+        tile_zero_column(tile, lane);
     }
-    warp_tile_flush<T, T>(tile, lane, valid, b, P.n_grid, grid_mass);
+    warp_tile_flush<T, T>(tile, lane, valid, b, P.n_grid, grid_mass, flush_variant);
 }
 
 __global__ void k_loss_init(double* acc) {
