@@ -150,6 +150,28 @@ int  plb_loss_bwd(plb_engine* e, int slot, int pf);
 int  plb_get_loss(plb_engine* e, double* accumulated);     /* loss.loss[None] */
 int  plb_clear_loss(plb_engine* e);                        /* Loss.clear_loss (loss.py:181-183) */
 
+/* ---- multi-GPU slab decomposition (no reference counterpart: the reference is single-device) -------
+ * One engine per GPU holds the particles whose base cell lies in its slab of grid planes [own_lo, own_hi) along axis 0
+ * (planes are contiguous in memory).  Stencils reach into the neighbours' slabs, so the planes [b-w, b+w) around each
+ * boundary b are computed by both neighbours as partial sums and exchanged by the host (NCCL send/recv of the buffers
+ * returned by plb_slab_buffer) between the two halves of a substep:
+ *   forward : plb_slab_fwd_p2g   -> exchange which=0 (grid_in zones)   -> plb_slab_fwd_finish
+ *   backward: plb_slab_bwd_begin -> exchange which=1 (g_out zones)     -> plb_slab_bwd_finish
+ *   loss    : plb_slab_loss_begin-> exchange which=2 (grid_mass zones) -> plb_slab_loss_reduce
+ *             -> all-reduce of buffer 0 (sum [0..3], max [4], min [8..15]) -> plb_slab_loss_finish
+ * The grid operator runs redundantly inside the zones; a plane's nodes contribute their pose gradients on the rank that
+ * owns the plane; buffer 1 (pose gradients) is sum-all-reduced before plb_get_action_grad. */
+int  plb_slab_configure(plb_engine* e, int own_lo, int own_hi, int halo_w, int has_left, int has_right);
+int  plb_slab_buffer(plb_engine* e, int which, int side, int dir, void** ptr, long long* bytes);
+int  plb_slab_fwd_p2g(plb_engine* e, int slot_in, int slot_out);
+int  plb_slab_fwd_finish(plb_engine* e, int slot_in, int slot_out, int pf);
+int  plb_slab_bwd_begin(plb_engine* e, int slot_in, int pf);
+int  plb_slab_bwd_finish(plb_engine* e, int slot_in, int pf);
+int  plb_slab_loss_begin(plb_engine* e, int slot);
+int  plb_slab_loss_reduce(plb_engine* e, int slot, int pf);
+int  plb_slab_loss_finish(plb_engine* e, int slot, int pf, int backward, double* out8);
+int  plb_device_buffer(plb_engine* e, int which, void** ptr, long long* bytes);
+
 /* ---- introspection for tests / profiling ------------------------------------------------------------------ */
 /* copies the dense grids of the last substep: any of in4/out4 may be NULL; [n_grid^3][4] float64 */
 int  plb_debug_get_grid(plb_engine* e, double* in4, double* out4);

@@ -174,6 +174,16 @@ _SIGNATURES = {
     "plb_clear_loss": ([C.c_void_p], C.c_int),
     "plb_debug_get_grid": ([C.c_void_p, _D, _D], C.c_int),
     "plb_launch_count": ([C.c_void_p], C.c_longlong),
+    "plb_slab_configure": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
+    "plb_slab_buffer": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)], C.c_int),
+    "plb_slab_fwd_p2g": ([C.c_void_p, C.c_int, C.c_int], C.c_int),
+    "plb_slab_fwd_finish": ([C.c_void_p, C.c_int, C.c_int, C.c_int], C.c_int),
+    "plb_slab_bwd_begin": ([C.c_void_p, C.c_int, C.c_int], C.c_int),
+    "plb_slab_bwd_finish": ([C.c_void_p, C.c_int, C.c_int], C.c_int),
+    "plb_slab_loss_begin": ([C.c_void_p, C.c_int], C.c_int),
+    "plb_slab_loss_reduce": ([C.c_void_p, C.c_int, C.c_int], C.c_int),
+    "plb_slab_loss_finish": ([C.c_void_p, C.c_int, C.c_int, C.c_int, _D], C.c_int),
+    "plb_device_buffer": ([C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)], C.c_int),
     "plb_profile_enable": ([C.c_void_p, C.c_int], C.c_int),
     "plb_profile_read": ([C.c_void_p, C.c_int, _D, C.POINTER(C.c_longlong)], C.c_int),
     "plb_kernel_name": ([C.c_int], C.c_char_p),

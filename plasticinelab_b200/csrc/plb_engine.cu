@@ -107,6 +107,16 @@ struct plb_engine {
     virtual int clear_loss() = 0;
     virtual int debug_get_grid(double* in4, double* out4) = 0;
     virtual int count_active(int slot, long long* n) = 0;
+    virtual int slab_configure(int own_lo, int own_hi, int halo_w, int has_left, int has_right) = 0;
+    virtual int slab_buffer(int which, int side, int dir, void** ptr, long long* bytes) = 0;
+    virtual int slab_fwd_p2g(int si, int so) = 0;
+    virtual int slab_fwd_finish(int si, int so, int pf) = 0;
+    virtual int slab_bwd_begin(int si, int pf) = 0;
+    virtual int slab_bwd_finish(int si, int pf) = 0;
+    virtual int slab_loss_begin(int slot) = 0;
+    virtual int slab_loss_reduce(int slot, int pf) = 0;
+    virtual int slab_loss_finish(int slot, int pf, int backward, double* out8) = 0;
+    virtual int device_buffer(int which, void** ptr, long long* bytes) = 0;
     virtual int set_stream(void* s) = 0;
     virtual int synchronize() = 0;
     long long launches = 0;
@@ -151,9 +161,12 @@ struct Engine : plb_engine {
     struct GraphKey { int dir, n, parity, stored; bool operator<(const GraphKey& o) const {
         return std::tie(dir, n, parity, stored) < std::tie(o.dir, o.n, o.parity, o.stored); } };
     std::map<GraphKey, cudaGraphExec_t> graphs;
+    // slab decomposition (multi-GPU): owned planes [own_lo, own_hi), zones of +-halo_w planes around the boundaries
+    struct Slab { bool on = false; int own_lo = 0, own_hi = 0, w = 0; bool has[2] = {false, false}; int zlo[2] = {0, 0}, zhi[2] = {0, 0};
+                  void* recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}}; } slab;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     size_t tile_smem = 0;
-    int flush_variant = 1;
+    int flush_variant = 0;      // 0 = per-cell groups (measured faster), 1 = chunked runs (PLB_FLUSH overrides)
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
     int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
     int* d_vals = nullptr; int* d_vals2 = nullptr; void* d_cub = nullptr; size_t cub_bytes = 0; T* frame_tmp = nullptr;
@@ -513,7 +526,7 @@ struct Engine : plb_engine {
             k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
         prof_end(); prof_begin(K_GRID_BWD);
         if (sparse)
-            k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive);
+            k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive, own_lo(), own_hi());
         else
             k_grid_bwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, n_nodes);
         prof_end(); prof_begin(K_P2G_BWD);
@@ -521,6 +534,8 @@ struct Engine : plb_engine {
         prof_end();
         launches += 5;
     }
+    int own_lo() const { return slab.on ? slab.own_lo : 0; }
+    int own_hi() const { return slab.on ? slab.own_hi : cfg.n_grid; }
     static SlotRef abs_ref(int v) { SlotRef r; r.cur = nullptr; r.idx = 0; r.rel = v; return r; }
     SlotRef cur_ref(int idx, int rel) const { SlotRef r; r.cur = d_cursor; r.idx = idx; r.rel = rel; return r; }
 
@@ -600,6 +615,160 @@ struct Engine : plb_engine {
         if (int r = launch_graph(key, slot0, pf0)) return r;
         cur ^= (n & 1);
         return PLB_OK;
+    }
+
+    // ---------------------------------------------------------------- slab decomposition (multi-GPU)
+    // The host (Python + torch.distributed over NCCL) moves zone planes between neighbours between the phases:
+    //   fwd:  slab_fwd_p2g -> exchange grid_in zones -> slab_fwd_finish
+    //   bwd:  slab_bwd_begin -> exchange g_out zones -> slab_bwd_finish
+    //   loss: slab_loss_begin -> exchange grid_mass zones -> slab_loss_reduce -> all-reduce acc -> slab_loss_finish
+    int slab_configure(int lo, int hi, int w, int has_left, int has_right) override {
+        PLB_REQUIRE(sparse && tile_scatter, "slab mode needs kernel_variant 0");
+        PLB_REQUIRE(lo % 4 == 0 && hi % 4 == 0 && w % 4 == 0 && w >= 4 && lo >= 0 && hi <= cfg.n_grid && lo < hi, "slab planes must be multiples of 4");
+        PLB_REQUIRE((!has_left || lo - w >= 0) && (!has_right || hi + w <= cfg.n_grid), "halo outside the grid");
+        PLB_REQUIRE(hi - lo >= 2 * w || !(has_left && has_right), "slab thinner than two halos");
+        slab.on = true; slab.own_lo = lo; slab.own_hi = hi; slab.w = w;
+        slab.has[0] = has_left != 0; slab.has[1] = has_right != 0;
+        slab.zlo[0] = lo - w; slab.zhi[0] = lo + w; slab.zlo[1] = hi - w; slab.zhi[1] = hi + w;
+        size_t plane = (size_t)cfg.n_grid * cfg.n_grid;
+        for (int side = 0; side < 2; side++) {
+            if (!slab.has[side]) continue;
+            for (int which = 0; which < 3; which++) {
+                if (slab.recv[which][side]) continue;
+                size_t bytes = 2 * (size_t)w * plane * (which == 2 ? sizeof(T) : sizeof(Vec4<T>));
+                PLB_CUDA(cudaMalloc(&slab.recv[which][side], bytes));
+            }
+        }
+        use_graphs = false;                    // phases are host-driven
+        return PLB_OK;
+    }
+    // which: 0 grid_in, 1 g_out, 2 grid_mass; side: 0 left, 1 right; dir: 0 send (inside the grid), 1 recv (staging)
+    int slab_buffer(int which, int side, int dir, void** ptr, long long* bytes) override {
+        PLB_REQUIRE(slab.on && which >= 0 && which < 3 && side >= 0 && side < 2 && slab.has[side], "no such slab buffer");
+        size_t plane = (size_t)cfg.n_grid * cfg.n_grid;
+        size_t esz = which == 2 ? sizeof(T) : sizeof(Vec4<T>);
+        *bytes = (long long)(2 * (size_t)slab.w * plane * esz);
+        if (dir == 1) { *ptr = slab.recv[which][side]; return PLB_OK; }
+        char* base = which == 0 ? (char*)grid_in : (which == 1 ? (char*)g_out : (char*)grid_mass);
+        *ptr = base + (size_t)slab.zlo[side] * plane * esz;
+        return PLB_OK;
+    }
+    int slab_fwd_p2g(int si, int so) override {
+        if (int r = check_slot(si)) return r;
+        if (int r = check_slot(so)) return r;
+        PLB_REQUIRE(slab.on && si != so, "slab mode not configured");
+        prof_begin(K_P2G);
+        k_p2g_tile<T><<<blocks(cfg.n_particles), kBlock, tile_smem, stream>>>(P, frames, n_pad, abs_ref(si), abs_ref(so), 1, material(), grid_in, d_flags, flush_variant);
+        prof_end();
+        launches++;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    void halo_add(Vec4<T>* grid, int which) {
+        for (int side = 0; side < 2; side++)
+            if (slab.has[side]) {
+                k_halo_add_listed<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid, (const Vec4<T>*)slab.recv[which][side], slab.zlo[side], slab.zhi[side], d_list, d_nactive);
+                launches++;
+            }
+    }
+    int slab_fwd_finish(int si, int so, int pf) override {
+        if (int r = check_pf(pf, 1)) return r;
+        PLB_REQUIRE(slab.on && store.vals, "slab mode needs the forward-grid store (call plb_sort_particles first)");
+        prof_begin(K_GRID_FWD);
+        for (int side = 0; side < 2; side++)
+            if (slab.has[side]) {
+                k_halo_mark<T><<<148, 256, 0, stream>>>(cfg.n_grid, (const Vec4<T>*)slab.recv[0][side], slab.zlo[side], slab.zhi[side], slab.own_lo, slab.own_hi, d_flags);
+                launches++;
+            }
+        compact_blocks();
+        halo_add(grid_in, 0);
+        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 1, d_list, d_nactive, store, abs_ref(si));
+        prof_end(); prof_begin(K_G2P);
+        k_g2p<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(si), abs_ref(so), grid_out);
+        prof_end();
+        launches += 2;
+        stored[si] = 1; stored[so] = 0;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    int slab_bwd_begin(int si, int pf) override {
+        if (int r = check_slot(si)) return r;
+        if (int r = check_pf(pf, 1)) return r;
+        PLB_REQUIRE(slab.on && stored[si] && store.vals, "slab backward needs the stored forward grid of this slot");
+        GridStore<T> nostore{nullptr, nullptr, nullptr, nullptr, 0};
+        prof_begin(K_P2G_RECOMPUTE);
+        k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid_in, d_list, d_nactive, store, abs_ref(si));
+        prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
+        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 0, d_list, d_nactive, nostore, abs_ref(si));
+        prof_end(); prof_begin(K_G2P_BWD);
+        k_g2p_bwd_tile<T><<<blocks(cfg.n_particles), kBlock, tile_smem, stream>>>(P, frames, n_pad, abs_ref(si), adj[cur], adj[cur ^ 1], grid_out, g_out, flush_variant);
+        prof_end();
+        launches += 3;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    int slab_bwd_finish(int si, int pf) override {
+        PLB_REQUIRE(slab.on, "slab mode not configured");
+        prof_begin(K_GRID_BWD);
+        halo_add(g_out, 1);
+        k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive, own_lo(), own_hi());
+        prof_end(); prof_begin(K_P2G_BWD);
+        k_p2g_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(si), adj[cur], adj[cur ^ 1], material(), g_in);
+        prof_end();
+        launches += 2;
+        cur ^= 1;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    int slab_loss_begin(int slot) override {
+        if (int r = check_slot(slot)) return r;
+        PLB_REQUIRE(slab.on && has_target, "slab loss needs slab mode and a target");
+        k_loss_init<<<1, 32, 0, stream>>>(d_acc);
+        PLB_CUDA(cudaMemsetAsync(grid_mass, 0, n_nodes * sizeof(T), stream));
+        k_loss_mass_tile<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass, flush_variant);
+        launches += 2;
+        return PLB_OK;
+    }
+    int slab_loss_reduce(int slot, int pf) override {
+        if (int r = check_pf(pf)) return r;
+        size_t plane = (size_t)cfg.n_grid * cfg.n_grid;
+        for (int side = 0; side < 2; side++)
+            if (slab.has[side]) {
+                long long cnt = 2LL * slab.w * plane;
+                k_add_scalar<T><<<blocks(cnt), kBlock, 0, stream>>>(cnt, grid_mass + (size_t)slab.zlo[side] * plane, (const T*)slab.recv[2][side]);
+                launches++;
+            }
+        long long own_nodes = (long long)(slab.own_hi - slab.own_lo) * plane;
+        size_t off = (size_t)slab.own_lo * plane;
+        int rb = (int)std::min<long long>((own_nodes + 255) / 256, 148 * 8);
+        k_loss_reduce<T><<<rb, 256, 0, stream>>>(grid_mass + off, target + off, target_sdf + off, own_nodes, d_acc);
+        k_loss_contact<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, d_acc);
+        launches += 2;
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    // after the host all-reduced d_acc (sum [0..3], max [4], min [8..]) across ranks
+    int slab_loss_finish(int slot, int pf, int backward, double* out8) override {
+        if (!backward) {
+            k_loss_finalize<T><<<1, 1, 0, stream>>>(prims, cfg.n_primitives, lw, d_acc, target_max, target_sum, d_acc + kAccN, d_acc + kAccN + 1);
+            launches++;
+            if (out8) {
+                PLB_CUDA(cudaMemcpyAsync(out8, d_acc + kAccN + 1, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                PLB_CUDA(cudaStreamSynchronize(stream));
+            }
+        } else {
+            k_loss_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, adj[cur], grid_mass, target,
+                                                                          target_sdf, lw, d_acc, contact_all, d_prim_grad);
+            launches++;
+        }
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    // which: 0 loss accumulators (kAccN doubles), 1 primitive pose gradients (max_prim_frames*8*8 doubles)
+    int device_buffer(int which, void** ptr, long long* bytes) override {
+        if (which == 0) { *ptr = d_acc; *bytes = kAccN * (long long)sizeof(double); return PLB_OK; }
+        if (which == 1) { *ptr = d_prim_grad; *bytes = (long long)(traj.size() * sizeof(double)); return PLB_OK; }
+        err = "unknown device buffer"; return PLB_ERR_INVALID;
     }
 
     // ---------------------------------------------------------------- adjoint bookkeeping
@@ -864,6 +1033,16 @@ int plb_loss_fwd(plb_engine* e, int slot, int pf, double* out8) { return e->loss
 int plb_loss_bwd(plb_engine* e, int slot, int pf) { return e->loss_bwd(slot, pf); }
 int plb_get_loss(plb_engine* e, double* v) { return e->get_loss(v); }
 int plb_clear_loss(plb_engine* e) { return e->clear_loss(); }
+int plb_slab_configure(plb_engine* e, int lo, int hi, int w, int l, int r) { return e->slab_configure(lo, hi, w, l, r); }
+int plb_slab_buffer(plb_engine* e, int which, int side, int dir, void** ptr, long long* bytes) { return e->slab_buffer(which, side, dir, ptr, bytes); }
+int plb_slab_fwd_p2g(plb_engine* e, int si, int so) { return e->slab_fwd_p2g(si, so); }
+int plb_slab_fwd_finish(plb_engine* e, int si, int so, int pf) { return e->slab_fwd_finish(si, so, pf); }
+int plb_slab_bwd_begin(plb_engine* e, int si, int pf) { return e->slab_bwd_begin(si, pf); }
+int plb_slab_bwd_finish(plb_engine* e, int si, int pf) { return e->slab_bwd_finish(si, pf); }
+int plb_slab_loss_begin(plb_engine* e, int slot) { return e->slab_loss_begin(slot); }
+int plb_slab_loss_reduce(plb_engine* e, int slot, int pf) { return e->slab_loss_reduce(slot, pf); }
+int plb_slab_loss_finish(plb_engine* e, int slot, int pf, int backward, double* out8) { return e->slab_loss_finish(slot, pf, backward, out8); }
+int plb_device_buffer(plb_engine* e, int which, void** ptr, long long* bytes) { return e->device_buffer(which, ptr, bytes); }
 int plb_debug_get_grid(plb_engine* e, double* in4, double* out4) { return e->debug_get_grid(in4, out4); }
 long long plb_launch_count(const plb_engine* e) { return e->launches; }
 int plb_profile_enable(plb_engine* e, int on) {

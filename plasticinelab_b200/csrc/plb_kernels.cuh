@@ -217,6 +217,50 @@ template <class Pay> __device__ __forceinline__ void tile_zero_column(Pay* tile,
     for (int q = 0; q < 27; q++) tile[q * kTileStride + lane] = z;
 }
 
+// ------------------------------------------------------------------------------------------------ slab halo
+// Multi-GPU slab decomposition along grid axis 0 (planes are contiguous: zero-copy sends).  A zone is the plane range
+// [lo, hi) around a slab boundary; `recv` holds the neighbour's partial sums for exactly those planes.
+//  k_halo_mark: blocks of the zone that lie in MY owned planes and carry mass from the neighbour become active here too
+//  (the owner of a plane is responsible for its nodes' pose gradients).
+//  k_halo_add_listed: add the neighbour's values into my listed blocks that lie inside the zone.
+template <class T>
+__global__ void k_halo_mark(int n_grid, const Vec4<T>* __restrict__ recv, int zone_lo, int zone_hi, int own_lo, int own_hi,
+                            unsigned char* flags) {
+    const int nbx = n_grid >> kBlkShift;
+    const int lo = max(zone_lo, own_lo), hi = min(zone_hi, own_hi);
+    const int nb_planes = (hi - lo) >> kBlkShift;
+    const int per_cta = blockDim.x / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1);
+    const int total = nb_planes * nbx * nbx;
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < total; e += gridDim.x * per_cta) {
+        int bi = (lo >> kBlkShift) + e / (nbx * nbx), bj = (e / nbx) % nbx, bk = e % nbx;
+        int i = (bi << kBlkShift) + (local >> 4), j = (bj << kBlkShift) + ((local >> 2) & 3), k = (bk << kBlkShift) + (local & 3);
+        Vec4<T> v = recv[((long long)(i - zone_lo) * n_grid + j) * n_grid + k];
+        if (v.w > T(0)) flags[(bi * nbx + bj) * nbx + bk] = 1;
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_halo_add_listed(int n_grid, Vec4<T>* grid, const Vec4<T>* __restrict__ recv, int zone_lo,
+                                                            int zone_hi, const int* __restrict__ list, const int* __restrict__ count) {
+    const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1), n = *count;
+    const int nbx = n_grid >> kBlkShift;
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
+        const int blk = list[e];
+        const int i0 = (blk / (nbx * nbx)) << kBlkShift;
+        if (i0 < zone_lo || i0 + 4 > zone_hi) continue;
+        const long long node = block_node(n_grid, blk, local);
+        const long long plane_sz = (long long)n_grid * n_grid;
+        Vec4<T> r = recv[node - (long long)zone_lo * plane_sz];
+        Vec4<T> g = grid[node];
+        grid[node] = mk4<T>(g.x + r.x, g.y + r.y, g.z + r.z, g.w + r.w);
+    }
+}
+
+template <class T> __global__ void k_add_scalar(long long n, T* dst, const T* __restrict__ src) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
 // ------------------------------------------------------------------------------------------------ substep
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
@@ -303,7 +347,7 @@ template <class T>
 __global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pfr,
                                                             Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, int clear,
                                                             double* prim_grad, const int* __restrict__ list,
-                                                            const int* __restrict__ count) {
+                                                            const int* __restrict__ count, int own_lo, int own_hi) {
     __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
     const int pf = pfr.get();
     load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
@@ -315,8 +359,11 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse(SimConst<T> P, PrimS
         unsigned touched = 0;
         if (e < n) {
             for (int k = 0; k < P.n_prim; k++) { g0[k].clear(); g1[k].clear(); }
-            grid_bwd_body<T>(block_node(P.n_grid, list[e], threadIdx.x & (kBlkNodes - 1)), P, prims, s0, s1, grid_in, g_out, g_in,
-                             clear != 0, g0, g1, touched);
+            const long long node = block_node(P.n_grid, list[e], threadIdx.x & (kBlkNodes - 1));
+            grid_bwd_body<T>(node, P, prims, s0, s1, grid_in, g_out, g_in, clear != 0, g0, g1, touched);
+            // slab decomposition: a node's pose gradient is accumulated by the rank that owns its plane
+            const int plane = (int)(node / ((long long)P.n_grid * P.n_grid));
+            if (plane < own_lo || plane >= own_hi) touched = 0;
         }
         for (int k = 0; k < P.n_prim; k++) {
             unsigned any = __ballot_sync(0xffffffffu, (touched >> k) & 1u);

@@ -19,13 +19,16 @@ from .tape import Tape, active_tape
 
 
 class TaichiEnv:
-    def __init__(self, cfg, nn=False, loss=True, dtype=None, device=0, max_prim_frames=None):
+    def __init__(self, cfg, nn=False, loss=True, dtype=None, device=0, max_prim_frames=None, particle_index=None):
         if nn:
             raise NotImplementedError("the Taichi MLP policy (plb/engine/nn/mlp.py) is out of scope (SURVEY.md 8f #3)")
         self.cfg = cfg.ENV
         self.primitives = Primitives(cfg.PRIMITIVES, max_timesteps=cfg.SIMULATOR.max_steps)
         self.shapes = Shapes(cfg.SHAPES)
         self.init_particles, self.particle_colors = self.shapes.get()
+        if particle_index is not None:      # one rank's share of the particles (slab decomposition, engine/sharded.py)
+            self.init_particles = np.ascontiguousarray(self.init_particles[particle_index])
+            self.particle_colors = self.particle_colors[particle_index]
         self.n_particles = cfg.SIMULATOR.n_particles = len(self.init_particles)
         dtype = dtype or os.environ.get("PLB_DTYPE") or cfg.SIMULATOR.get("dtype", "float64")
         conf = _capi.make_config(dict(cfg.SIMULATOR), self.n_particles, len(self.primitives), dtype=dtype,
