@@ -43,24 +43,43 @@ WORKLOADS = {
     # BASELINE.json configs[0] (the reference's own CPU-runnable case), here as fwd+bwd
     "move10k": dict(scene="move.yml", n=10_000, quality=1, horizon=50,
                     desc="Move-v1 stock, 10k particles, 64^3 grid, 50 env steps x 19 substeps, fwd+bwd"),
+    # multi-GPU weak scaling (north_star / BASELINE configs[4]-style): an elastic-plastic bar along the slab axis,
+    # 1M particles and 0.1 of the domain (25.6 planes of 256) per GPU; --gpus N decomposes it into N slabs
+    "slab1m": dict(scene="slab", n=1_000_000, quality=4, horizon=2,
+                   desc="bar 0.1*N x 0.1 x 0.1 on the ground, 1M particles per GPU, 256^3 grid, 2 env steps x 79 substeps, fwd+bwd"),
     "rope1m": dict(scene="rope.yml", n=1_000_000, quality=4, horizon=2,
                    desc="Rope-v1 geometry, 1M particles, 256^3 grid, 2 env steps x 79 substeps, fwd+bwd"),
 }
 
 
-def build_cfg(w):
+def build_cfg(w, world=1):
     from plasticinelab_b200.envs.scene import load_variants
     from plasticinelab_b200 import _capi
-    cfg = load_variants(w["scene"], 1)
-    cfg.SIMULATOR.quality = w["quality"]
-    cfg.SHAPES[0]["n_particles"] = w["n"]
+    if w["scene"] == "slab":
+        from plasticinelab_b200.config import load_dict
+        L = 0.1 * world
+        tree = dict(SIMULATOR=dict(quality=w["quality"], yield_stress=50.0, ground_friction=0.3),
+                    SHAPES=[dict(shape="box", width=(L, 0.1, 0.1), init_pos=(0.5, 0.06, 0.5), n_particles=w["n"] * world)],
+                    PRIMITIVES=[dict(shape="Sphere", radius=0.03, init_pos=(0.5 - 0.3 * L, 0.145, 0.5), friction=0.9,
+                                     action=dict(dim=3, scale=(0.01, 0.01, 0.01))),
+                                dict(shape="Sphere", radius=0.03, init_pos=(0.5 + 0.3 * L, 0.145, 0.5), friction=0.9,
+                                     action=dict(dim=3, scale=(0.01, 0.01, 0.01)))])
+        cfg = load_dict(tree)
+        cfg.ENV.loss.target_path = "envs/assets/Rope3D-v1.npy"
+    else:
+        cfg = load_variants(w["scene"], 1)
+        cfg.SIMULATOR.quality = w["quality"]
+        cfg.SHAPES[0]["n_particles"] = w["n"]
     S = _capi.sim_constants(dict(cfg.SIMULATOR))["substeps"]
     cfg.SIMULATOR.max_steps = w["horizon"] * S + 2
     return cfg, S
 
 
 def actions_for(w, A):
-    return np.random.RandomState(0).uniform(-0.01, 0.01, (w["horizon"], A))
+    a = np.random.RandomState(0).uniform(-0.01, 0.01, (w["horizon"], A))
+    if w["scene"] == "slab":
+        a[:, 1::3] = -0.5          # press the spheres into the bar
+    return a
 
 
 class ClockSampler:
@@ -179,13 +198,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="move100k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:      # one GPU: BASELINE configs[1]; several GPUs: the slab-decomposed weak-scaling bar
+        args.workload = "move100k" if world == 1 else "slab1m"
+    w = WORKLOADS[args.workload]
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, w, rank)
@@ -205,14 +226,22 @@ def main():
     from plasticinelab_b200.engine.taichi_env import TaichiEnv
     from plasticinelab_b200.optimizer.solver import Solver
 
-    cfg, S = build_cfg(w)
+    slab = world > 1 and w["scene"] == "slab"
+    cfg, S = build_cfg(w, world if slab else 1)
     torch.cuda.set_device(local_rank)
-    env = TaichiEnv(cfg, dtype=args.dtype, device=local_rank)
-    env.initialize()
+    senv = None
+    if slab:
+        from plasticinelab_b200.engine.sharded import ShardedEnv
+        senv = ShardedEnv(cfg, dtype=args.dtype, device=local_rank, halo_w=8)
+        env = senv.env
+    else:
+        env = TaichiEnv(cfg, dtype=args.dtype, device=local_rank)
+        env.initialize()
     env.loss.set_weights(10, 10, 1, False)
     eng = env.engine
     eng.call("plb_set_stream", C.c_void_p(torch.cuda.current_stream().cuda_stream))
     N, H = env.n_particles, w["horizon"]
+    N_global = senv.n_global if slab else N * world
     A = env.primitives.action_dim
     actions = actions_for(w, A)
     pinned_actions = torch.from_numpy(actions).pin_memory()
@@ -221,8 +250,20 @@ def main():
     solver.total_steps = 0
     grad_out = np.zeros((H, max(A, 1)))
 
+    def episode_slab(load_state=False):
+        if load_state:
+            env.simulator.set_state(0, host_state)
+        senv.begin_episode(666.0)
+        a = pinned_actions.numpy()
+        for i in range(H):
+            senv.step(a[i])
+            senv.compute_loss(sync=load_state)
+        grad_out[:, :A] = senv.backward()
+
     def episode_device():
         """state resident in HBM (frame 0), no host read-back except the final action gradient"""
+        if slab:
+            return episode_slab(False)
         env.simulator.cur = 0
         env._is_copy = False
         for p in env.primitives:
@@ -240,6 +281,8 @@ def main():
         eng.call("plb_get_action_grad", H, S, _capi.dptr(grad_out))
 
     def episode_e2e():
+        if slab:
+            return episode_slab(True)
         return solver.forward(host_state, pinned_actions.numpy())
 
     def timed(fn, k):
@@ -284,9 +327,10 @@ def main():
     episode_e2e()
     ms_e2e = timed(episode_e2e, args.steps)
 
-    units_per_step = N * H * S
-    value = world * units_per_step * args.steps / (ms_dev * 1e-3)
-    e2e_value = world * units_per_step * args.steps / (ms_e2e * 1e-3)
+    units_per_step = N_global * H * S if slab else N * H * S
+    mult = 1 if slab else world
+    value = mult * units_per_step * args.steps / (ms_dev * 1e-3)
+    e2e_value = mult * units_per_step * args.steps / (ms_e2e * 1e-3)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -306,8 +350,10 @@ def main():
     sc = 2 if args.dtype == "float64" else 1
     alg_bytes = sc * (bpp * N + bpn * n_active)
     achieved = alg_bytes / (sub[dom]["avg_us"] * 1e-6) / 1e9
-    fused_bytes = sc * (504 * N + 168 * n_active)
+    # whole job: all ranks' particles and (approximately) all ranks' active nodes against world x the per-GPU peak
+    fused_bytes = sc * (504 * (N_global if slab else N * world) + 168 * n_active * world)
     fused_gbs = fused_bytes * (H * S * args.steps) / (ms_dev * 1e-3) / 1e9
+    peak_job = peak * world
     kernel_ms_total = sum(v["total_ms"] for v in per_kernel.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
@@ -315,12 +361,12 @@ def main():
                 "n_active_nodes": n_active,
                 "timing": "CUDA events around every launch of one extra episode run inside bench.py right after the timed "
                           "region (graphs off for that episode); `value` itself is timed with graphs on",
-                "fused_substep": {"algorithmic_bytes": fused_bytes, "achieved": fused_gbs, "frac": fused_gbs / peak,
+                "fused_substep": {"algorithmic_bytes": fused_bytes, "achieved": fused_gbs, "frac": fused_gbs / peak_job, "peak": peak_job,
                                   "formula": "(504 N + 168 N_active) B per fwd+bwd substep (SURVEY.md 8d)"},
                 "kernels": per_kernel}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         n_sub = 2 if N >= 1_000_000 else 4
         v, dt = oracle_sample(cfg, w, S, n_sub, threads)
@@ -335,7 +381,11 @@ def main():
             "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": w["desc"], "n_particles": N, "n_grid": env.simulator.n_grid,
                        "substeps_per_env_step": S, "env_steps": H, "particle_substeps_per_step": units_per_step,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one env per GPU)",
+                       "parallelism": "single GPU" if world == 1 else (
+                           f"{world} slabs along grid axis 0, {senv.halo_w}-plane halo zones summed over NCCL send/recv once per "
+                           f"substep (fwd) and once per substep (bwd); bounds {senv.bounds}" if slab
+                           else f"{world} independent replicas (one env per GPU)"),
+                       "n_particles_global": N_global,
                        "l2": "inputs larger than L2: every substep reads a different trajectory frame "
                              f"({(H * S + 1) * 96 * N / 1e9:.1f} GB trajectory per episode)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
