@@ -99,3 +99,41 @@ def test_golden_episode_regression():
     assert abs(r['loss'] - float(g['loss'])) < 1e-10 * abs(float(g['loss']))
     assert np.allclose(r['grad'], g['grad_taichi'], rtol=1e-8, atol=1e-14)
     assert np.abs(r['final_state'][0].numpy() - g['final_x']).max() < 1e-12
+
+
+@pytest.mark.parametrize('softness,gf,fscale', [(666.0, 1.5, 0.1), (0.0, 0.0, 0.004), (666.0, 100.0, 0.0)])
+def test_c_port_matches_torch_oracle(softness, gf, fscale):
+    """oracle/mpm_oracle.c (the CPU baseline bench.py times) against the torch oracle: one substep forward + adjoint."""
+    import plb_test_helpers as H
+    from oracle.c_port import CPort
+    n = 400
+    prims = [dict(shape='Sphere', radius=0.08, init_pos=(0.45, 0.5, 0.5), friction=0.9, action=dict(dim=3, scale=(0.01,) * 3)),
+             dict(shape='Sphere', radius=0.06, init_pos=(0.6, 0.45, 0.55), friction=0.5, action=dict(dim=3, scale=(0.01,) * 3))]
+    cfg = H.small_cfg(prims, n_particles=n, ground_friction=gf, yield_stress=30.0)
+    osim = O.OracleSim(dict(cfg.SIMULATOR), [dict(p) for p in cfg.PRIMITIVES])
+    osim.set_materials(n)
+    osim.set_softness(softness)
+    x, v, Cm, F = H.random_state(n, 2, 0.02 if gf else 0.3, 0.3 if gf else 0.7)
+    if fscale != 0.1:
+        F = np.eye(3)[None] + fscale * np.random.RandomState(5).randn(n, 3, 3)
+    rng = np.random.RandomState(9)
+    p0 = [np.concatenate([p.init_state().numpy()[:3], [0.9, 0.1, -0.2, 0.3]]) for p in osim.prims]
+    p0 = [np.concatenate([s[:3], s[3:] / np.linalg.norm(s[3:])]) for s in p0]
+    p1 = [np.concatenate([s[:3] + 2e-4 * rng.randn(3), (s[3:] + 2e-3 * rng.randn(4))]) for s in p0]
+    p1 = [np.concatenate([s[:3], s[3:] / np.linalg.norm(s[3:])]) for s in p1]
+    port = CPort(osim, n, softness)
+    st = tuple(torch.as_tensor(a) for a in (x, v, Cm, F))
+    pf, pf1 = [torch.as_tensor(s) for s in p0], [torch.as_tensor(s) for s in p1]
+    ref = osim.substep(st, pf, pf1)
+    out = port.substep_fwd((x, v, Cm, F), port.poses(p0), port.poses(p1))
+    for a, b in zip(out, ref):
+        assert H.relerr(a, b.numpy()) < 1e-9
+    adj = H.random_adjoint(n, 2)
+    o_adj, g0, g1 = osim.substep_vjp(st, pf, pf1, tuple(torch.as_tensor(a) for a in adj))
+    c_adj, c0, c1 = port.substep_bwd((x, v, Cm, F), port.poses(p0), port.poses(p1), adj)
+    for a, b in zip(c_adj, o_adj):
+        assert H.relerr(a, b.numpy()) < 1e-7
+    for k in range(2):
+        scale = max(np.abs(g0[k].numpy()).max(), np.abs(g1[k].numpy()).max(), 1e-12)
+        assert np.abs(c0[k, :7] - g0[k].numpy()).max() < 1e-7 * scale + 1e-12
+        assert np.abs(c1[k, :7] - g1[k].numpy()).max() < 1e-7 * scale + 1e-12
