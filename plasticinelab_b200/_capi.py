@@ -16,7 +16,7 @@ MAX_PRIMITIVES = 8
 MAX_ACTION_DIM = 7
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplb_b200.so")
+LIB_PATH = os.environ.get("PLB_LIB") or os.path.join(_HERE, "libplb_b200.so")
 
 
 class PrimitiveDesc(C.Structure):

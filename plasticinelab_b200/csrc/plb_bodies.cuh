@@ -162,21 +162,36 @@ template <class T>
 PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, const Vec4<T>* grid_out) {
     V3<T> x = load_x(in, p);
     Stencil<T> st = make_stencil(x, P.inv_dx);
-    V3<T> nv = zero3<T>();
-    M3<T> nC = zeroM<T>();
+    // v' = sum w g;  C' = 4 inv_dx sum w g (x) (o - fx) = 4 inv_dx (sum w g (x) o - v' (x) fx): accumulate sum w g and the
+    // three offset-weighted sums (offsets are 0/1/2, so these are adds), one rank-1 correction at the end
+    V3<T> nv = zero3<T>(), si = zero3<T>(), sj = zero3<T>(), sk = zero3<T>();
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+        for (int j = 0; j < 3; j++) {
+            T wij = st.w[i][0] * st.w[j][1];
+            V3<T> t0 = zero3<T>(), tk = zero3<T>();
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
                 Vec4<T> g4 = grid_out[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
-                V3<T> gv = mk3<T>(g4.x, g4.y, g4.z);
-                V3<T> dpos = mk3<T>(T(i) - st.fx.x, T(j) - st.fx.y, T(k) - st.fx.z);
-                nv += w * gv;
-                nC += (T(4) * P.inv_dx * w) * outer(gv, dpos);
+                V3<T> wg = st.w[k][2] * mk3<T>(g4.x, g4.y, g4.z);
+                t0 += wg;
+                if (k > 0) tk += T(k) * wg;
             }
+            V3<T> u = wij * t0;
+            nv += u;
+            sk += wij * tk;
+            if (i > 0) si += T(i) * u;
+            if (j > 0) sj += T(j) * u;
+        }
+    M3<T> nC;
+    const T c4 = T(4) * P.inv_dx;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        nC.m[r][0] = c4 * (si[r] - nv[r] * st.fx.x);
+        nC.m[r][1] = c4 * (sj[r] - nv[r] * st.fx.y);
+        nC.m[r][2] = c4 * (sk[r] - nv[r] * st.fx.z);
+    }
     V3<T> nx = advect(P, x, nv);
     store_xvC(out, p, nx, nv, nC);
 }
@@ -193,18 +208,20 @@ PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
     V3<T> gxn, gvn; M3<T> gCn;
     load_xvC(adj_next, p, gxn, gvn, gCn);
     Stencil<T> st = make_stencil(x, P.inv_dx);
-    // recompute new_v for the clamp masks of the advection
+    // recompute new_v = sum w g (clamp masks of the advection; it is also the sum the dpos adjoint needs)
     V3<T> nv = zero3<T>();
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+        for (int j = 0; j < 3; j++) {
+            V3<T> t0 = zero3<T>();
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
                 Vec4<T> g4 = grid_out[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
-                nv += w * mk3<T>(g4.x, g4.y, g4.z);
+                t0 += st.w[k][2] * mk3<T>(g4.x, g4.y, g4.z);
             }
+            nv += (st.w[i][0] * st.w[j][1]) * t0;
+        }
     V3<T> gy = advect_backward(P, x, nv, gxn);
     V3<T> gx = gy;
     V3<T> gv = gvn + P.dt * gy;
@@ -215,27 +232,35 @@ PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
         for (int d = 0; d < 3; d++) gw[a][d] = T(0);
     V3<T> gfx = zero3<T>();
     const T c4 = T(4) * P.inv_dx;
+    // adjoint of grid_out[o] = w_o h_o with h_o = gv + c4 gC' (o - fx): h is evaluated incrementally along the axes;
+    // the adjoint of the 3-D weight is g_v[o] . h_o and the adjoint of dpos sums to c4 gC'^T (sum_o w_o g_v[o])
+    V3<T> hc0 = mk3<T>(c4 * gCn.m[0][0], c4 * gCn.m[1][0], c4 * gCn.m[2][0]);
+    V3<T> hc1 = mk3<T>(c4 * gCn.m[0][1], c4 * gCn.m[1][1], c4 * gCn.m[2][1]);
+    V3<T> hc2 = mk3<T>(c4 * gCn.m[0][2], c4 * gCn.m[1][2], c4 * gCn.m[2][2]);
+    V3<T> h0 = gv - (st.fx.x * hc0 + st.fx.y * hc1 + st.fx.z * hc2);
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+        V3<T> hi = h0 + T(i) * hc0;
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+        for (int j = 0; j < 3; j++) {
+            V3<T> hij = hi + T(j) * hc1;
+            T wij = st.w[i][0] * st.w[j][1];
+            T tij = T(0);                                   // sum_k g(weight_ijk) w_k
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
-                long long node = node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k);
-                Vec4<T> g4 = grid_out[node];
-                V3<T> gvn_ = mk3<T>(g4.x, g4.y, g4.z);
-                V3<T> dpos = mk3<T>(T(i) - st.fx.x, T(j) - st.fx.y, T(k) - st.fx.z);
-                V3<T> Cd = mv(gCn, dpos);                     // gC' dpos
-                V3<T> gg = w * (gv + c4 * Cd);                // adjoint of grid_out[node]
-                sc.add((i * 3 + j) * 3 + k, st.b[0] + i, st.b[1] + j, st.b[2] + k, mk4<T>(gg.x, gg.y, gg.z, T(0)));
-                T gwt = dot(gv, gvn_) + c4 * dot(gvn_, Cd);   // adjoint of the 3-D weight
-                V3<T> gd = (c4 * w) * mTv(gCn, gvn_);         // adjoint of dpos
-                gfx -= gd;
-                gw[i][0] += gwt * st.w[j][1] * st.w[k][2];
-                gw[j][1] += gwt * st.w[i][0] * st.w[k][2];
-                gw[k][2] += gwt * st.w[i][0] * st.w[j][1];
+                T w = wij * st.w[k][2];
+                V3<T> h = hij + T(k) * hc2;
+                Vec4<T> g4 = grid_out[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
+                sc.add((i * 3 + j) * 3 + k, st.b[0] + i, st.b[1] + j, st.b[2] + k, mk4<T>(w * h.x, w * h.y, w * h.z, T(0)));
+                T gwt = g4.x * h.x + g4.y * h.y + g4.z * h.z;
+                tij += gwt * st.w[k][2];
+                gw[k][2] += gwt * wij;
             }
+            gw[i][0] += tij * st.w[j][1];
+            gw[j][1] += tij * st.w[i][0];
+        }
+    }
+    gfx = (-c4) * mTv(gCn, nv);
     gx += stencil_backward(st, gw, gfx, P.inv_dx);
     adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
 }
@@ -277,34 +302,54 @@ PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
     P2GState<T> keep;
     p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine, &keep);
     Stencil<T> st = make_stencil(x, P.inv_dx);
-    V3<T> mvel = P.p_mass * v;
-    V3<T> gv = zero3<T>();
-    M3<T> g_aff = zeroM<T>();
+    // forward node value: w_o (m_o, p_mass) with m_o = p_mass v + affine (o - fx) dx, evaluated incrementally.
+    // With a_o = adjoint of the node momentum: g(weight_o) = a_o . m_o + b_o p_mass;  g(v) = p_mass sum w a;
+    // g(affine) = (sum w a (x) o - (sum w a) (x) fx) dx;  g(fx) -= dx affine^T (sum w a)  -- the last two leave the loop.
+    V3<T> c0 = mk3<T>(affine.m[0][0] * P.dx, affine.m[1][0] * P.dx, affine.m[2][0] * P.dx);
+    V3<T> c1 = mk3<T>(affine.m[0][1] * P.dx, affine.m[1][1] * P.dx, affine.m[2][1] * P.dx);
+    V3<T> c2 = mk3<T>(affine.m[0][2] * P.dx, affine.m[1][2] * P.dx, affine.m[2][2] * P.dx);
+    V3<T> m0 = P.p_mass * v - (st.fx.x * c0 + st.fx.y * c1 + st.fx.z * c2);
+    V3<T> gv = zero3<T>();                 // sum w a
+    V3<T> si = zero3<T>(), sj = zero3<T>(), sk = zero3<T>();     // sum w a * {i, j, k}
     T gw[3][3];
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
         for (int d = 0; d < 3; d++) gw[a][d] = T(0);
-    V3<T> gfx = zero3<T>();
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+        V3<T> mi = m0 + T(i) * c0;
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+        for (int j = 0; j < 3; j++) {
+            V3<T> mij = mi + T(j) * c1;
+            T wij = st.w[i][0] * st.w[j][1];
+            T tij = T(0);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                T w = st.w[i][0] * st.w[j][1] * st.w[k][2];
+                T w = wij * st.w[k][2];
                 Vec4<T> g4 = g_in[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
                 V3<T> a = mk3<T>(g4.x, g4.y, g4.z);
-                V3<T> dpos = mk3<T>((T(i) - st.fx.x) * P.dx, (T(j) - st.fx.y) * P.dx, (T(k) - st.fx.z) * P.dx);
-                T gwt = dot(a, mvel + mv(affine, dpos)) + g4.w * P.p_mass;
-                gv += w * a;
-                g_aff += w * outer(a, dpos);
-                V3<T> gd = w * mTv(affine, a);
-                gfx -= P.dx * gd;
-                gw[i][0] += gwt * st.w[j][1] * st.w[k][2];
-                gw[j][1] += gwt * st.w[i][0] * st.w[k][2];
-                gw[k][2] += gwt * st.w[i][0] * st.w[j][1];
+                T gwt = dot(a, mij + T(k) * c2) + g4.w * P.p_mass;
+                V3<T> wa = w * a;
+                gv += wa;
+                if (i > 0) si += T(i) * wa;
+                if (j > 0) sj += T(j) * wa;
+                if (k > 0) sk += T(k) * wa;
+                tij += gwt * st.w[k][2];
+                gw[k][2] += gwt * wij;
             }
+            gw[i][0] += tij * st.w[j][1];
+            gw[j][1] += tij * st.w[i][0];
+        }
+    }
+    M3<T> g_aff;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        g_aff.m[r][0] = (si[r] - gv[r] * st.fx.x) * P.dx;
+        g_aff.m[r][1] = (sj[r] - gv[r] * st.fx.y) * P.dx;
+        g_aff.m[r][2] = (sk[r] - gv[r] * st.fx.z) * P.dx;
+    }
+    V3<T> gfx = (-P.dx) * mTv(affine, gv);
     gv = P.p_mass * gv;
     V3<T> gx = stencil_backward(st, gw, gfx, P.inv_dx);
     Vec4<T> part = adj_cur.A0[p];                           // partial x-adjoint from g2p_bwd_body

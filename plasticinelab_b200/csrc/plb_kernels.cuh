@@ -7,6 +7,9 @@
 namespace plb {
 
 constexpr int kBlock = 128;
+// minimum resident blocks per SM requested from ptxas for the register-heavy adjoint kernels (float only)
+template <class T> struct Occ { static constexpr int p2g_bwd = 1, g2p_bwd = 1; };
+template <> struct Occ<float> { static constexpr int p2g_bwd = 3, g2p_bwd = 3; };   // measured best of {1,3,4} x {1,3,4}
 
 // A frame index given either absolutely (cur == nullptr) or relative to a device-resident cursor.  The cursor form
 // lets one captured CUDA graph of an env step (S substeps) be replayed for every env step: only the 3-int cursor
@@ -203,10 +206,39 @@ __device__ __forceinline__ void warp_tile_flush_runs(const Pay* tile, int lane, 
     __syncwarp();
 }
 
+// Variant C ("run loops"): runs of consecutive equal cells like B, but with runtime loops: per run a plain counted loop
+// over its columns (LDS + adds + 3 loop instructions per column instead of the find-first-set walk of variant A).
+template <class T, class Pay>
+__device__ __forceinline__ void warp_tile_flush_runloops(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid) {
+    __syncwarp();
+    const unsigned full = 0xffffffffu;
+    const int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
+    const int next = __shfl_down_sync(full, key, 1);
+    unsigned run_end = __ballot_sync(full, lane == 31 || next != key);
+    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
+    const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
+    int start = 0;
+    while (run_end) {
+        const int end = __ffs(run_end);                 // one past the last column of this run
+        run_end &= run_end - 1;
+        const int rkey = __shfl_sync(full, key, end - 1);
+        if (rkey >= 0 && lane < 27) {
+            Pay acc;
+            pay_zero(acc);
+            for (int j = start; j < end; j++) pay_acc(acc, row[j]);
+            int bk = rkey % n_grid, bj = (rkey / n_grid) % n_grid, bi = rkey / (n_grid * n_grid);
+            pay_red(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
+        }
+        start = end;
+    }
+    __syncwarp();
+}
+
 template <class T, class Pay>
 __device__ __forceinline__ void warp_tile_flush(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid, int variant) {
     if (variant == 0) warp_tile_flush_groups<T, Pay>(tile, lane, valid, b, n_grid, grid);
-    else warp_tile_flush_runs<T, Pay>(tile, lane, valid, b, n_grid, grid);
+    else if (variant == 1) warp_tile_flush_runs<T, Pay>(tile, lane, valid, b, n_grid, grid);
+    else warp_tile_flush_runloops<T, Pay>(tile, lane, valid, b, n_grid, grid);
 }
 
 // zero this lane's tile column (lanes without a particle, so that the run-based flush can read every column)
@@ -403,7 +435,7 @@ __global__ void __launch_bounds__(kBlock) k_g2p_bwd(SimConst<T> P, T* frames, lo
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
+__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
                                                          T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_variant) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -448,7 +480,7 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd(SimConst<T> P, PrimSet<T> p
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_p2g_bwd(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
+__global__ void __launch_bounds__(kBlock, Occ<T>::p2g_bwd) k_p2g_bwd(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
                                                     T* adj_cur, Material<T> mat, const Vec4<T>* g_in) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
