@@ -171,6 +171,14 @@ int  plb_slab_loss_begin(plb_engine* e, int slot);
 int  plb_slab_loss_reduce(plb_engine* e, int slot, int pf);
 int  plb_slab_loss_finish(plb_engine* e, int slot, int pf, int backward, double* out8);
 int  plb_device_buffer(plb_engine* e, int which, void** ptr, long long* bytes);
+/* Peer-memory halo (preferred): every rank exports a CUDA-IPC handle of its per-side inbox, the host hands it to the
+ * neighbour on that side (torch.distributed all_gather_object), the neighbour imports it.  Once all neighbours are
+ * imported, plb_substep_fwd/bwd and plb_step_fwd/bwd do the halo themselves: after the scatter each rank stores ONLY its
+ * active 4^3 blocks inside the zone into the neighbour's inbox (P2P stores over NVLink), stamps them with a sequence
+ * number, publishes the number in a flag, spins on its own flag, adds what arrived -- all in-stream, so whole env steps
+ * are CUDA graphs again.  handle64: 64 bytes (cudaIpcMemHandle_t). */
+int  plb_slab_ipc_export(plb_engine* e, int side, void* handle64);
+int  plb_slab_ipc_import(plb_engine* e, int side, const void* handle64);
 
 /* ---- introspection for tests / profiling ------------------------------------------------------------------ */
 /* copies the dense grids of the last substep: any of in4/out4 may be NULL; [n_grid^3][4] float64 */

@@ -117,6 +117,8 @@ struct plb_engine {
     virtual int slab_loss_reduce(int slot, int pf) = 0;
     virtual int slab_loss_finish(int slot, int pf, int backward, double* out8) = 0;
     virtual int device_buffer(int which, void** ptr, long long* bytes) = 0;
+    virtual int slab_ipc_export(int side, void* handle64) = 0;
+    virtual int slab_ipc_import(int side, const void* handle64) = 0;
     virtual int set_stream(void* s) = 0;
     virtual int synchronize() = 0;
     long long launches = 0;
@@ -163,7 +165,10 @@ struct Engine : plb_engine {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     // slab decomposition (multi-GPU): owned planes [own_lo, own_hi), zones of +-halo_w planes around the boundaries
     struct Slab { bool on = false; int own_lo = 0, own_hi = 0, w = 0; bool has[2] = {false, false}; int zlo[2] = {0, 0}, zhi[2] = {0, 0};
-                  void* recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}}; } slab;
+                  void* recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+                  // peer-memory halo: my inboxes (neighbours write here), the neighbours' inboxes mapped through CUDA IPC
+                  char* inbox[2] = {nullptr, nullptr}; char* peer[2] = {nullptr, nullptr}; HaloGeom geom[2]; size_t inbox_bytes = 0;
+                  int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; bool peer_ready = false; } slab;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     size_t tile_smem = 0;
     int flush_variant = 0;      // 0 = per-cell groups (measured faster), 1 = chunked runs (PLB_FLUSH overrides)
@@ -490,7 +495,20 @@ struct Engine : plb_engine {
             k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
         prof_end(); prof_begin(K_GRID_FWD);
         if (sparse) {
-            compact_blocks();
+            if (slab.peer_ready) {
+                k_halo_next_seq<<<1, 1, 0, stream>>>(slab.seq);
+                cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
+                k_compact_stamped<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags, d_list, d_nactive, slab.listed_stamp, slab.seq);
+                halo_exchange(grid_in);
+                for (int side = 0; side < 2; side++)
+                    if (slab.has[side])
+                        k_halo_append<<<32, 256, 0, stream>>>(cfg.n_grid, slab.inbox[side], slab.geom[side], slab.own_lo, slab.own_hi, slab.seq,
+                                                              slab.listed_stamp, d_list, d_nactive);
+                halo_add_inbox(grid_in);
+                launches += 8;
+            } else {
+                compact_blocks();
+            }
             k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si);
         } else {
             k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
@@ -525,6 +543,12 @@ struct Engine : plb_engine {
         else
             k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
         prof_end(); prof_begin(K_GRID_BWD);
+        if (slab.peer_ready) {
+            k_halo_next_seq<<<1, 1, 0, stream>>>(slab.seq);
+            halo_exchange(g_out);
+            halo_add_inbox(g_out);
+            launches += 6;
+        }
         if (sparse)
             k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive, own_lo(), own_hi());
         else
@@ -533,6 +557,19 @@ struct Engine : plb_engine {
         k_p2g_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in);
         prof_end();
         launches += 5;
+    }
+    // push my listed zone blocks of `grid` into the neighbours' inboxes, publish, wait for theirs
+    void halo_exchange(const Vec4<T>* grid) {
+        for (int side = 0; side < 2; side++)
+            if (slab.has[side])
+                k_halo_push<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid, d_list, d_nactive, slab.peer[side], slab.geom[side], slab.seq);
+        k_halo_signal<<<1, 1, 0, stream>>>(slab.has[0] ? slab.peer[0] : nullptr, slab.has[1] ? slab.peer[1] : nullptr, slab.seq);
+        k_halo_wait<<<1, 1, 0, stream>>>(slab.has[0] ? slab.inbox[0] : nullptr, slab.has[1] ? slab.inbox[1] : nullptr, slab.seq, slab.err);
+    }
+    void halo_add_inbox(Vec4<T>* grid) {
+        for (int side = 0; side < 2; side++)
+            if (slab.has[side])
+                k_halo_add_inbox<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid, slab.inbox[side], slab.geom[side], d_list, d_nactive, slab.seq);
     }
     int own_lo() const { return slab.on ? slab.own_lo : 0; }
     int own_hi() const { return slab.on ? slab.own_hi : cfg.n_grid; }
@@ -764,6 +801,58 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
     }
+    // ---- peer-memory halo set-up: inbox allocation + CUDA IPC handles (exchanged by the host through torch.distributed)
+    int alloc_inboxes() {
+        if (slab.seq) return PLB_OK;
+        const int nbx = cfg.n_grid / 4;
+        for (int side = 0; side < 2; side++) {
+            HaloGeom& g = slab.geom[side];
+            g.zone_lo = slab.zlo[side]; g.zone_hi = slab.zhi[side];
+            g.nzb = (2 * slab.w / 4) * nbx * nbx;
+            g.stamps_off = 256;
+            g.data_off = (256 + 2LL * g.nzb * (long long)sizeof(int) + 255) / 256 * 256;
+            slab.inbox_bytes = (size_t)g.data_off + 2ULL * g.nzb * kBlkNodes * sizeof(Vec4<T>);
+            if (!slab.has[side]) continue;
+            PLB_CUDA(cudaMalloc(&slab.inbox[side], slab.inbox_bytes));
+            PLB_CUDA(cudaMemset(slab.inbox[side], 0, 256));
+            PLB_CUDA(cudaMemset(slab.inbox[side] + g.stamps_off, 0xFF, 2ULL * g.nzb * sizeof(int)));
+        }
+        PLB_CUDA(cudaMalloc(&slab.seq, sizeof(int)));
+        PLB_CUDA(cudaMemset(slab.seq, 0, sizeof(int)));
+        PLB_CUDA(cudaMalloc(&slab.err, sizeof(int)));
+        PLB_CUDA(cudaMemset(slab.err, 0, sizeof(int)));
+        PLB_CUDA(cudaMalloc(&slab.listed_stamp, n_blocks * sizeof(int)));
+        PLB_CUDA(cudaMemset(slab.listed_stamp, 0xFF, n_blocks * sizeof(int)));
+        return PLB_OK;
+    }
+    int slab_ipc_export(int side, void* handle64) override {
+        PLB_REQUIRE(slab.on && side >= 0 && side < 2 && slab.has[side], "no neighbour on that side");
+        if (int r = alloc_inboxes()) return r;
+        cudaIpcMemHandle_t h;
+        PLB_CUDA(cudaIpcGetMemHandle(&h, slab.inbox[side]));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(handle64, &h, 64);
+        return PLB_OK;
+    }
+    // side: the neighbour this handle came from (0 = my left neighbour's RIGHT inbox, 1 = my right neighbour's LEFT inbox)
+    int slab_ipc_import(int side, const void* handle64) override {
+        PLB_REQUIRE(slab.on && side >= 0 && side < 2 && slab.has[side], "no neighbour on that side");
+        if (int r = alloc_inboxes()) return r;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, 64);
+        void* ptr = nullptr;
+        PLB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        slab.peer[side] = (char*)ptr;
+        bool ready = true;
+        for (int s2 = 0; s2 < 2; s2++) if (slab.has[s2] && !slab.peer[s2]) ready = false;
+        if (ready) {
+            slab.peer_ready = true;
+            use_graphs = cfg.kernel_variant == 0 && !getenv("PLB_NO_GRAPHS");
+            for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+            graphs.clear();
+        }
+        return PLB_OK;
+    }
     // which: 0 loss accumulators (kAccN doubles), 1 primitive pose gradients (max_prim_frames*8*8 doubles)
     int device_buffer(int which, void** ptr, long long* bytes) override {
         if (which == 0) { *ptr = d_acc; *bytes = kAccN * (long long)sizeof(double); return PLB_OK; }
@@ -806,6 +895,11 @@ struct Engine : plb_engine {
         int ov = 0;
         PLB_CUDA(cudaMemcpyAsync(&ov, store.overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
         PLB_CUDA(cudaStreamSynchronize(stream));
+        if (slab.err) {
+            int he = 0;
+            PLB_CUDA(cudaMemcpy(&he, slab.err, sizeof(int), cudaMemcpyDeviceToHost));
+            if (he) { cudaMemset(slab.err, 0, sizeof(int)); err = "slab halo: timed out waiting for a neighbour's push"; return PLB_ERR_CUDA; }
+        }
         if (ov) {
             PLB_CUDA(cudaMemsetAsync(store.overflow, 0, sizeof(int), stream));
             err = "forward-grid store overflow: the material spread over more 4^3 blocks than reserved at the last "
@@ -1043,6 +1137,8 @@ int plb_slab_loss_begin(plb_engine* e, int slot) { return e->slab_loss_begin(slo
 int plb_slab_loss_reduce(plb_engine* e, int slot, int pf) { return e->slab_loss_reduce(slot, pf); }
 int plb_slab_loss_finish(plb_engine* e, int slot, int pf, int backward, double* out8) { return e->slab_loss_finish(slot, pf, backward, out8); }
 int plb_device_buffer(plb_engine* e, int which, void** ptr, long long* bytes) { return e->device_buffer(which, ptr, bytes); }
+int plb_slab_ipc_export(plb_engine* e, int side, void* handle64) { return e->slab_ipc_export(side, handle64); }
+int plb_slab_ipc_import(plb_engine* e, int side, const void* handle64) { return e->slab_ipc_import(side, handle64); }
 int plb_debug_get_grid(plb_engine* e, double* in4, double* out4) { return e->debug_get_grid(in4, out4); }
 long long plb_launch_count(const plb_engine* e) { return e->launches; }
 int plb_profile_enable(plb_engine* e, int on) {

@@ -288,6 +288,112 @@ __global__ void __launch_bounds__(kBlock) k_halo_add_listed(int n_grid, Vec4<T>*
     }
 }
 
+// ---- peer-memory halo (NVLink P2P stores into the neighbour's inbox, no host round trip) -------------------------------
+// Inbox of one side (lives in the RECEIVER's memory, mapped into the sender through CUDA IPC):
+//   int flag[64]                      flag[0] = sequence number of the newest complete push
+//   int stamps[2][zone_blocks]        per parity: sequence number at which the block's data were pushed
+//   Vec4 data[2][zone_blocks][64]     per parity: the block's 64 node values (block-major, same order as the store)
+// A push writes only the sender's ACTIVE blocks inside the zone; the receiver trusts a block iff its stamp == seq.
+struct HaloGeom { int zone_lo, zone_hi, nzb; long long stamps_off, data_off; };   // offsets in bytes from the inbox base
+
+__device__ __forceinline__ int zone_block_index(int n_grid, int blk, int zone_lo) {
+    const int nbx = n_grid >> kBlkShift;
+    const int bi = blk / (nbx * nbx);
+    return (bi - (zone_lo >> kBlkShift)) * nbx * nbx + blk % (nbx * nbx);
+}
+
+// sender: copy my listed blocks that lie in the zone into the peer's inbox (parity = seq & 1) and stamp them
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_halo_push(int n_grid, const Vec4<T>* __restrict__ grid, const int* __restrict__ list,
+                                                      const int* __restrict__ count, char* peer_inbox, HaloGeom g, const int* seq_ptr) {
+    const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1), n = *count, seq = *seq_ptr, par = seq & 1;
+    const int nbx = n_grid >> kBlkShift;
+    int* stamps = reinterpret_cast<int*>(peer_inbox + g.stamps_off) + (long long)par * g.nzb;
+    Vec4<T>* data = reinterpret_cast<Vec4<T>*>(peer_inbox + g.data_off) + (long long)par * g.nzb * kBlkNodes;
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
+        const int blk = list[e];
+        const int i0 = (blk / (nbx * nbx)) << kBlkShift;
+        if (i0 < g.zone_lo || i0 + 4 > g.zone_hi) continue;
+        const int zb = zone_block_index(n_grid, blk, g.zone_lo);
+        data[(long long)zb * kBlkNodes + local] = grid[block_node(n_grid, blk, local)];
+        if (local == 0) stamps[zb] = seq;
+    }
+}
+// one thread: make the pushes visible system-wide, then publish the sequence number in the peers' flags
+__global__ void k_halo_signal(char* peer0, char* peer1, const int* seq_ptr) {
+    __threadfence_system();
+    const int seq = *seq_ptr;
+    if (peer0) { volatile int* f = reinterpret_cast<volatile int*>(peer0); f[0] = seq; }
+    if (peer1) { volatile int* f = reinterpret_cast<volatile int*>(peer1); f[0] = seq; }
+    __threadfence_system();
+}
+// one thread: spin until both neighbours published `seq` in MY inboxes; err is set on a ~4 s timeout
+__global__ void k_halo_wait(const char* inbox0, const char* inbox1, const int* seq_ptr, int* err) {
+    const int seq = *seq_ptr;
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; side++) {
+        const char* ib = side == 0 ? inbox0 : inbox1;
+        if (!ib) continue;
+        const volatile int* f = reinterpret_cast<const volatile int*>(ib);
+        while (f[0] < seq) {
+            if (clock64() - t0 > 8000000000LL) { *err = 1; break; }
+        }
+    }
+    __threadfence_system();
+}
+__global__ void k_halo_next_seq(int* seq_ptr) { *seq_ptr += 1; }
+
+// receiver, forward only: blocks of the zone in MY owned planes that the neighbour pushed but I do not list yet are
+// appended to my list (the owner of a plane accumulates its nodes' pose gradients)
+__global__ void k_halo_append(int n_grid, const char* inbox, HaloGeom g, int own_lo, int own_hi, const int* seq_ptr, int* listed_stamp,
+                              int* list, int* count) {
+    const int seq = *seq_ptr, par = seq & 1, nbx = n_grid >> kBlkShift;
+    const int* stamps = reinterpret_cast<const int*>(inbox + g.stamps_off) + (long long)par * g.nzb;
+    for (int zb = blockIdx.x * blockDim.x + threadIdx.x; zb < g.nzb; zb += gridDim.x * blockDim.x) {
+        if (stamps[zb] != seq) continue;
+        const int bi = (g.zone_lo >> kBlkShift) + zb / (nbx * nbx);
+        const int i0 = bi << kBlkShift;
+        if (i0 < own_lo || i0 >= own_hi) continue;
+        const int blk = bi * nbx * nbx + zb % (nbx * nbx);
+        if (listed_stamp[blk] == seq) continue;
+        listed_stamp[blk] = seq;
+        list[atomicAdd(count, 1)] = blk;
+    }
+}
+// receiver: add the neighbour's values of this sequence number into my listed blocks
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_halo_add_inbox(int n_grid, Vec4<T>* grid, const char* inbox, HaloGeom g,
+                                                           const int* __restrict__ list, const int* __restrict__ count, const int* seq_ptr) {
+    const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1), n = *count, seq = *seq_ptr, par = seq & 1;
+    const int nbx = n_grid >> kBlkShift;
+    const int* stamps = reinterpret_cast<const int*>(inbox + g.stamps_off) + (long long)par * g.nzb;
+    const Vec4<T>* data = reinterpret_cast<const Vec4<T>*>(inbox + g.data_off) + (long long)par * g.nzb * kBlkNodes;
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
+        const int blk = list[e];
+        const int i0 = (blk / (nbx * nbx)) << kBlkShift;
+        if (i0 < g.zone_lo || i0 + 4 > g.zone_hi) continue;
+        const int zb = zone_block_index(n_grid, blk, g.zone_lo);
+        if (stamps[zb] != seq) continue;
+        const long long node = block_node(n_grid, blk, local);
+        Vec4<T> r = data[(long long)zb * kBlkNodes + local];
+        Vec4<T> v = grid[node];
+        grid[node] = mk4<T>(v.x + r.x, v.y + r.y, v.z + r.z, v.w + r.w);
+    }
+}
+// compaction that also records which blocks are listed at this sequence number (slab peer mode)
+__global__ void k_compact_stamped(int n_blocks, unsigned char* flags, int* list, int* count, int* listed_stamp, const int* seq_ptr) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_blocks && flags[b]) {
+        flags[b] = 0;
+        listed_stamp[b] = *seq_ptr;
+        list[atomicAdd(count, 1)] = b;
+    }
+}
+__global__ void k_stamp_list(const int* __restrict__ list, const int* __restrict__ count, int* listed_stamp, const int* seq_ptr) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < *count) listed_stamp[list[e]] = *seq_ptr;
+}
+
 template <class T> __global__ void k_add_scalar(long long n, T* dst, const T* __restrict__ src) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] += src[i];

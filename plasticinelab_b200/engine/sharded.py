@@ -33,7 +33,7 @@ def _tensor(ptr, nbytes, device, f64=False):
 
 
 class ShardedEnv:
-    def __init__(self, cfg, rank=None, world=None, dtype="float32", device=None, halo_w=8, group=None):
+    def __init__(self, cfg, rank=None, world=None, dtype="float32", device=None, halo_w=8, group=None, peer=None):
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.group = group
@@ -69,6 +69,29 @@ class ShardedEnv:
         self.prim_grad = _tensor(ptr.value, nb.value, self.device, f64=True)
         self.records = []
         self.cur = 0
+        import os
+        self.peer = (os.environ.get("PLB_SLAB_PEER", "1") != "0") if peer is None else bool(peer)
+        if self.peer and self.world > 1:
+            self._setup_peer()
+        else:
+            self.peer = False
+
+    def _setup_peer(self):
+        """Exchange the CUDA-IPC handles of the halo inboxes: afterwards the engine does the per-substep halo itself
+        (P2P stores over NVLink, in-stream flags) and env steps run as CUDA graphs."""
+        eng = self.engine
+        mine = {}
+        for side in self.sides:
+            buf = C.create_string_buffer(64)
+            eng.call("plb_slab_ipc_export", side, buf)
+            mine[side] = buf.raw
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, mine, group=self.group)
+        for side in self.sides:
+            peer = self.rank - 1 if side == 0 else self.rank + 1
+            h = gathered[peer][1 - side]          # the neighbour's inbox that faces me
+            eng.call("plb_slab_ipc_import", side, C.create_string_buffer(h, 64))
+        dist.barrier(group=self.group)
 
     # ---- communication
     def _exchange(self, which):
@@ -104,10 +127,13 @@ class ShardedEnv:
         eng, S, start = self.engine, self.S, self.cur
         self.env.primitives.set_action(start // S, S, action)
         eng.call("plb_kinematics", start, S)
-        for s in range(start, start + S):
-            eng.call("plb_slab_fwd_p2g", s, s + 1)
-            self._exchange(0)
-            eng.call("plb_slab_fwd_finish", s, s + 1, s)
+        if self.peer:
+            eng.call("plb_step_fwd", start, start, S)            # halo inside the engine (peer memory), one graph launch
+        else:
+            for s in range(start, start + S):
+                eng.call("plb_slab_fwd_p2g", s, s + 1)
+                self._exchange(0)
+                eng.call("plb_slab_fwd_finish", s, s + 1, s)
         self.records.append(("step", start, S))
         self.cur = start + S
 
@@ -133,10 +159,13 @@ class ShardedEnv:
                 eng.call("plb_slab_loss_finish", rec[1], rec[1], 1, None)
             else:
                 _, start, n = rec
-                for s in reversed(range(start, start + n)):
-                    eng.call("plb_slab_bwd_begin", s, s)
-                    self._exchange(1)
-                    eng.call("plb_slab_bwd_finish", s, s)
+                if self.peer:
+                    eng.call("plb_step_bwd", start, start, n)
+                else:
+                    for s in reversed(range(start, start + n)):
+                        eng.call("plb_slab_bwd_begin", s, s)
+                        self._exchange(1)
+                        eng.call("plb_slab_bwd_finish", s, s)
         if self.world > 1:
             dist.all_reduce(self.prim_grad, op=dist.ReduceOp.SUM, group=self.group)
         n_steps = sum(1 for r in self.records if r[0] == "step")

@@ -35,6 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--dtype', default='float64')
     ap.add_argument('--steps', type=int, default=2)
+    ap.add_argument('--peer', type=int, default=1)
     args = ap.parse_args()
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -44,7 +45,7 @@ def main():
     actions[:, 1] = -np.abs(actions[:, 1])          # push down into the box
     actions[:, 4] = -np.abs(actions[:, 4])
 
-    senv = ShardedEnv(cfg, dtype=args.dtype, halo_w=8)
+    senv = ShardedEnv(cfg, dtype=args.dtype, halo_w=8, peer=bool(args.peer))
     senv.env.loss.set_weights(10, 10, 1, False)
     senv.begin_episode(666.0)
     for a in actions:
@@ -69,7 +70,7 @@ def main():
         el = abs(loss - rloss) / abs(rloss)
         eg = np.linalg.norm(grad - rgrad) / np.linalg.norm(rgrad)
         ex = np.abs(x_local - xr[senv.index]).max()
-        print(f'[slab parity] world={world} bounds={senv.bounds} local={len(senv.index)}/{senv.n_global} loss {loss:.10f} vs {rloss:.10f} '
+        print(f'[slab parity] peer={int(senv.peer)} world={world} bounds={senv.bounds} local={len(senv.index)}/{senv.n_global} loss {loss:.10f} vs {rloss:.10f} '
               f'(rel {el:.2e}) grad rel {eg:.2e} |grad| {np.linalg.norm(rgrad):.3e} x err {ex:.2e}')
         ok = el < tol_l and eg < tol_g and ex < tol_x
     flag = torch.tensor([1 if ok else 0], device='cuda')

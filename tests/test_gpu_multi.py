@@ -10,12 +10,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize('peer', [1, 0])
 @pytest.mark.parametrize('dtype', ['float64', 'float32'])
-def test_slab_parity_two_ranks(dtype):
+def test_slab_parity_two_ranks(dtype, peer):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
-           '--master-port', '29611', os.path.join(ROOT, 'tests', 'multi', 'slab_parity.py'), '--dtype', dtype]
+           '--master-port', '29611', os.path.join(ROOT, 'tests', 'multi', 'slab_parity.py'), '--dtype', dtype, '--peer', str(peer)]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
