@@ -403,8 +403,11 @@ def main():
             "config": {"workload": args.workload, "description": w["desc"], "n_particles": N, "n_grid": env.simulator.n_grid,
                        "substeps_per_env_step": S, "env_steps": H, "particle_substeps_per_step": units_per_step,
                        "parallelism": "single GPU" if world == 1 else (
-                           f"{world} slabs along grid axis 0, {senv.halo_w}-plane halo zones summed over NCCL send/recv once per "
-                           f"substep (fwd) and once per substep (bwd); bounds {senv.bounds}" if slab
+                           (f"{world} slabs along grid axis 0, {senv.halo_w}-plane halo zones; " +
+                            ("active zone blocks pushed into the neighbour's inbox over NVLink peer memory (CUDA IPC) inside the "
+                             "captured env-step graphs, once per substep fwd and once bwd" if senv.peer else
+                             "zones summed over NCCL send/recv driven from the host, once per substep fwd and once bwd") +
+                            f"; loss scalars / pose gradients all-reduced over NCCL; bounds {senv.bounds}") if slab
                            else f"{world} independent replicas (one env per GPU)"),
                        "n_particles_global": N_global,
                        "l2": "inputs larger than L2: every substep reads a different trajectory frame "
