@@ -46,7 +46,8 @@ WORKLOADS = {
     # multi-GPU weak scaling (north_star / BASELINE configs[4]-style): an elastic-plastic bar along the slab axis,
     # 1M particles and 0.1 of the domain (25.6 planes of 256) per GPU; --gpus N decomposes it into N slabs
     "slab1m": dict(scene="slab", n=1_000_000, quality=4, horizon=2,
-                   desc="bar 0.1*N x 0.1 x 0.1 on the ground, 1M particles per GPU, 256^3 grid, 2 env steps x 79 substeps, fwd+bwd"),
+                   desc="bar (0.109*N) x 0.1 x 0.1 on the ground pressed by two spheres, 1M particles per GPU, 256^3 grid, "
+                        "2 env steps x 79 substeps, fwd+bwd"),
     "rope1m": dict(scene="rope.yml", n=1_000_000, quality=4, horizon=2,
                    desc="Rope-v1 geometry, 1M particles, 256^3 grid, 2 env steps x 79 substeps, fwd+bwd"),
 }
@@ -57,7 +58,7 @@ def build_cfg(w, world=1):
     from plasticinelab_b200 import _capi
     if w["scene"] == "slab":
         from plasticinelab_b200.config import load_dict
-        L = 0.1 * world
+        L = 0.109375 * world          # 28 planes of 256 per GPU: slab boundaries fall on 4-plane block boundaries
         tree = dict(SIMULATOR=dict(quality=w["quality"], yield_stress=50.0, ground_friction=0.3),
                     SHAPES=[dict(shape="box", width=(L, 0.1, 0.1), init_pos=(0.5, 0.06, 0.5), n_particles=w["n"] * world)],
                     PRIMITIVES=[dict(shape="Sphere", radius=0.03, init_pos=(0.5 - 0.3 * L, 0.145, 0.5), friction=0.9,
@@ -251,7 +252,29 @@ def main():
     cfg, S = build_cfg(w, world if slab else 1)
     torch.cuda.set_device(local_rank)
     senv = None
+    n1_reference = None
     if slab:
+        # scaling reference: the per-GPU share of this workload on ONE GPU (rank 0, regular graph path), same process
+        if rank == 0:
+            cfg1, _ = build_cfg(w, 1)
+            env1 = TaichiEnv(cfg1, dtype=args.dtype, device=local_rank)
+            env1.initialize()
+            env1.loss.set_weights(10, 10, 1, False)
+            sol1 = Solver(env1, None, None, n_iters=1, softness=666.0, horizon=w["horizon"])
+            sol1.total_steps = 0
+            a1 = actions_for(w, env1.primitives.action_dim)
+            st1 = env1.get_state()["state"]
+            for _ in range(2):
+                sol1.forward(st1, a1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sol1.forward(st1, a1)
+            torch.cuda.synchronize()
+            n1_reference = {"n_gpus": 1, "value": env1.n_particles * w["horizon"] * S / (time.perf_counter() - t0), "unit": UNIT,
+                            "how": "same per-GPU workload through Solver.forward on rank 0 before the multi-GPU run (1 timed episode)"}
+            env1.engine.close()
+            del env1, sol1
+        dist.barrier()
         from plasticinelab_b200.engine.sharded import ShardedEnv
         senv = ShardedEnv(cfg, dtype=args.dtype, device=local_rank, halo_w=8)
         env = senv.env
@@ -409,7 +432,7 @@ def main():
                              "zones summed over NCCL send/recv driven from the host, once per substep fwd and once bwd") +
                             f"; loss scalars / pose gradients all-reduced over NCCL; bounds {senv.bounds}") if slab
                            else f"{world} independent replicas (one env per GPU)"),
-                       "n_particles_global": N_global,
+                       "n_particles_global": N_global, "scaling_reference": n1_reference,
                        "l2": "inputs larger than L2: every substep reads a different trajectory frame "
                              f"({(H * S + 1) * 96 * N / 1e9:.1f} GB trajectory per episode)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
