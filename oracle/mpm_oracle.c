@@ -439,6 +439,14 @@ void oc_substep_bwd(const oc_params* P, const double* pose0, const double* pose1
     }
 }
 
+void oc_set_threads(int n) {
+    #ifdef _OPENMP
+    omp_set_num_threads(n);
+    #else
+    (void)n;
+    #endif
+}
+
 int oc_max_threads(void) {
     #ifdef _OPENMP
     return omp_get_max_threads();
