@@ -1,4 +1,8 @@
-"""`PlasticineEnv`: the gym surface of the reference (`plb/envs/env.py:12-86`) on top of the CUDA engine."""
+"""`PlasticineEnv`: the gym-style task wrapper (`plb/envs/env.py:12-86`) on top of the CUDA engine.
+
+Observation = [x_i, v_i] of every (N // n_observed)-th particle, flattened, followed by the primitive states; reward and
+the info dict come from `Loss.compute_loss`; episodes never terminate by themselves (`done` is always False, the
+TimeLimit wrapper of `envs.make` ends them after 50 steps)."""
 from __future__ import annotations
 
 import numpy as np
@@ -17,45 +21,42 @@ from .scene import load_variants
 class PlasticineEnv(_EnvBase):
     def __init__(self, cfg_path, version, nn=False, dtype=None, device=0, cfg_overrides=None):
         self.cfg_path = cfg_path
-        cfg = self.load_varaints(cfg_path, version)
-        if cfg_overrides:
-            cfg_overrides(cfg)
-        self.taichi_env = TaichiEnv(cfg, nn, dtype=dtype, device=device)
-        self.taichi_env.initialize()
-        self.cfg = cfg.ENV
-        self.taichi_env.set_copy(True)
-        self._init_state = self.taichi_env.get_state()
+        full_cfg = self.load_varaints(cfg_path, version)
+        if cfg_overrides is not None:
+            cfg_overrides(full_cfg)
+        self.cfg = full_cfg.ENV
         self._n_observed_particles = self.cfg.n_observed_particles
-        obs = self.reset()
-        self.observation_space = Box(-np.inf, np.inf, obs.shape)
-        self.action_space = Box(-1, 1, (self.taichi_env.primitives.action_dim,))
+        self.taichi_env = sim_env = TaichiEnv(full_cfg, nn, dtype=dtype, device=device)
+        sim_env.initialize()
+        sim_env.set_copy(True)                       # RL mode: every step restarts from frame 0
+        self._init_state = sim_env.get_state()
+        first_obs = self.reset()
+        self.observation_space = Box(-np.inf, np.inf, first_obs.shape)
+        self.action_space = Box(-1, 1, (sim_env.primitives.action_dim,))
 
-    def reset(self):
-        self.taichi_env.set_state(**self._init_state)
-        self._recorded_actions = []
-        return self._get_obs()
+    # reference spelling (env.py:62); kept because callers use it
+    load_varaints = staticmethod(load_variants)
 
     def _get_obs(self, t=0):
-        x = self.taichi_env.simulator.get_x(t)
-        v = self.taichi_env.simulator.get_v(t)
-        outs = [p.get_state(t) for p in self.taichi_env.primitives]
-        s = np.concatenate(outs) if outs else np.zeros(0)
-        step_size = len(x) // self._n_observed_particles
-        return np.concatenate((np.concatenate((x[::step_size], v[::step_size]), axis=-1).reshape(-1), s.reshape(-1)))
+        sim = self.taichi_env.simulator
+        stride = sim.n_particles // self._n_observed_particles
+        particles = np.concatenate((sim.get_x(t)[::stride], sim.get_v(t)[::stride]), axis=-1)
+        prims = [p.get_state(t) for p in self.taichi_env.primitives]
+        return np.concatenate([particles.reshape(-1)] + [np.asarray(s).reshape(-1) for s in prims])
+
+    def reset(self):
+        self._recorded_actions = []
+        self.taichi_env.set_state(**self._init_state)
+        return self._get_obs()
 
     def step(self, action):
         self.taichi_env.step(action)
-        loss_info = self.taichi_env.compute_loss()
+        info = self.taichi_env.compute_loss()
         self._recorded_actions.append(action)
-        obs = self._get_obs()
-        r = loss_info["reward"]
-        if np.isnan(obs).any() or np.isnan(r):
-            raise Exception("NaN..")          # the reference also pickles the action log (env.py:50-56)
-        return obs, r, False, loss_info
+        obs, reward = self._get_obs(), info["reward"]
+        if np.isnan(reward) or np.isnan(obs).any():
+            raise Exception("NaN..")          # the reference additionally pickles the action log (env.py:50-56)
+        return obs, reward, False, info
 
     def render(self, mode="human"):
         return self.taichi_env.render(mode)
-
-    @classmethod
-    def load_varaints(cls, cfg_path, version):      # (sic) reference spelling, env.py:62
-        return load_variants(cfg_path, version)
