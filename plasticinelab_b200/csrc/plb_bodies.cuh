@@ -91,6 +91,7 @@ template <class T> struct DirectScatter {
     Vec4<T>* grid;
     int n;
     PLB_HD void add(int slot, int i, int j, int k, Vec4<T> v) const { (void)slot; scatter_add4(grid + node_index(n, i, j, k), v); }
+    PLB_HD void end_plane(int) const {}
 };
 
 template <class T> PLB_HD void load_material(const SimConst<T>& P, const Material<T>& mat, int p, T& mu, T& lam, T& ys) {
@@ -135,6 +136,7 @@ PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const F
                 sc.add((i * 3 + j) * 3 + k, st.b[0] + i, st.b[1] + j, st.b[2] + k, mk4<T>(mom.x, mom.y, mom.z, w * P.p_mass));
             }
         }
+        sc.end_plane(i);
     }
 }
 template <class T>

@@ -171,6 +171,8 @@ struct Engine : plb_engine {
                   int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; bool peer_ready = false; } slab;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     size_t tile_smem = 0;
+    bool plane_tile = false;        // one-plane (9-node) tile for P2G: 1/3 shared memory, PLB_P2G_PLANE=1
+    size_t plane_smem = 0;
     int flush_variant = 0;      // 0 = per-cell groups (measured faster), 1 = chunked runs (PLB_FLUSH overrides)
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
     int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
@@ -253,6 +255,8 @@ struct Engine : plb_engine {
         sparse = c.kernel_variant != 1;
         tile_scatter = c.kernel_variant == 0;
         if (const char* fv = getenv("PLB_FLUSH")) flush_variant = atoi(fv);
+        if (const char* pv = getenv("PLB_P2G_PLANE")) plane_tile = atoi(pv) != 0;
+        plane_smem = (size_t)(kBlock / 32) * kPlaneVec4 * sizeof(Vec4<T>);
         tile_smem = (size_t)(kBlock / 32) * kTileVec4 * sizeof(Vec4<T>);
         if (tile_scatter) {
             PLB_CUDA(cudaFuncSetAttribute(k_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
@@ -489,10 +493,7 @@ struct Engine : plb_engine {
     void enqueue_fwd(SlotRef si, SlotRef so, SlotRef pf) {
         const int nb = blocks(cfg.n_particles);
         prof_begin(K_P2G);
-        if (tile_scatter)
-            k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr, flush_variant);
-        else
-            k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, 1, material(), grid_in, sparse ? d_flags : nullptr);
+        launch_p2g(si, so, 1);
         prof_end(); prof_begin(K_GRID_FWD);
         if (sparse) {
             if (slab.peer_ready) {
@@ -526,10 +527,7 @@ struct Engine : plb_engine {
         if (restore) {
             k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid_in, d_list, d_nactive, store, si);
         } else {
-            if (tile_scatter)
-                k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr, flush_variant);
-            else
-                k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, si, 0, material(), grid_in, sparse ? d_flags : nullptr);
+            launch_p2g(si, si, 0);
             if (sparse) compact_blocks();
         }
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
@@ -573,6 +571,16 @@ struct Engine : plb_engine {
     }
     int own_lo() const { return slab.on ? slab.own_lo : 0; }
     int own_hi() const { return slab.on ? slab.own_hi : cfg.n_grid; }
+    void launch_p2g(SlotRef si, SlotRef so, int store_F) {
+        const int nb = blocks(cfg.n_particles);
+        unsigned char* fl = sparse ? d_flags : nullptr;
+        if (tile_scatter && plane_tile)
+            k_p2g_plane<T><<<nb, kBlock, plane_smem, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+        else if (tile_scatter)
+            k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_variant);
+        else
+            k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+    }
     static SlotRef abs_ref(int v) { SlotRef r; r.cur = nullptr; r.idx = 0; r.rel = v; return r; }
     SlotRef cur_ref(int idx, int rel) const { SlotRef r; r.cur = d_cursor; r.idx = idx; r.rel = rel; return r; }
 
@@ -695,7 +703,7 @@ struct Engine : plb_engine {
         if (int r = check_slot(so)) return r;
         PLB_REQUIRE(slab.on && si != so, "slab mode not configured");
         prof_begin(K_P2G);
-        k_p2g_tile<T><<<blocks(cfg.n_particles), kBlock, tile_smem, stream>>>(P, frames, n_pad, abs_ref(si), abs_ref(so), 1, material(), grid_in, d_flags, flush_variant);
+        launch_p2g(abs_ref(si), abs_ref(so), 1);
         prof_end();
         launches++;
         PLB_CUDA(cudaGetLastError());

@@ -124,6 +124,49 @@ template <class T> struct WarpTileScatter {
     Vec4<T>* tile;     // this warp's tile
     int lane;
     __device__ __forceinline__ void add(int slot, int, int, int, Vec4<T> v) const { tile[slot * kTileStride + lane] = v; }
+    __device__ __forceinline__ void end_plane(int) const {}
+};
+
+// 3-pass variant: the tile holds ONE stencil plane (9 nodes); after each plane the warp flushes it.  A third of the shared
+// memory per warp (4.75 KB instead of 14.25 KB), so the scatter kernel is no longer shared-memory-limited in occupancy.
+// Flush: lanes 0..26 = (node q = lane % 9, part r = lane / 9); part r sums the group members sitting in lanes
+// [11 r, 11 r + 11); the three partial sums meet in lanes 0..8 through two shuffles; one vector RED per node and group.
+constexpr int kPlaneVec4 = 9 * kTileStride;
+template <class T> struct WarpPlaneScatter {
+    Vec4<T>* tile; Vec4<T>* grid;
+    int lane, key, n_grid;          // key < 0: this lane carries no particle
+    __device__ __forceinline__ void add(int slot, int, int, int, Vec4<T> v) const { tile[(slot % 9) * kTileStride + lane] = v; }
+    __device__ __forceinline__ void end_plane(int plane) const {
+        const unsigned full = 0xffffffffu;
+        __syncwarp();
+        unsigned remaining = __ballot_sync(full, key >= 0);
+        const int q = lane % 9, r = lane / 9;
+        const unsigned part_mask = r == 0 ? 0x000007ffu : (r == 1 ? 0x003ff800u : (r == 2 ? 0xffc00000u : 0u));
+        const Vec4<T>* row = tile + q * kTileStride;
+        while (remaining) {
+            const int leader = __ffs(remaining) - 1;
+            const int lkey = __shfl_sync(full, key, leader);
+            const unsigned group = __ballot_sync(full, key == lkey);
+            remaining &= ~group;
+            Vec4<T> acc = mk4<T>(T(0), T(0), T(0), T(0));
+            unsigned g = group & part_mask;
+            while (g) {
+                const int j = __ffs(g) - 1;
+                g &= g - 1;
+                const Vec4<T> v = row[j];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            acc.x += __shfl_down_sync(full, acc.x, 9) + __shfl_down_sync(full, acc.x, 18);
+            acc.y += __shfl_down_sync(full, acc.y, 9) + __shfl_down_sync(full, acc.y, 18);
+            acc.z += __shfl_down_sync(full, acc.z, 9) + __shfl_down_sync(full, acc.z, 18);
+            acc.w += __shfl_down_sync(full, acc.w, 9) + __shfl_down_sync(full, acc.w, 18);
+            if (lane < 9) {
+                const int bk = lkey % n_grid, bj = (lkey / n_grid) % n_grid, bi = lkey / (n_grid * n_grid);
+                scatter_add4(grid + node_index(n_grid, bi + plane, bj + q / 3, bk + q % 3), acc);
+            }
+        }
+        __syncwarp();
+    }
 };
 // payload helpers: the tile carries Vec4 (momentum+mass, velocity adjoint) or a scalar (loss mass)
 template <class T> __device__ __forceinline__ void pay_zero(Vec4<T>& a) { a = mk4<T>(T(0), T(0), T(0), T(0)); }
@@ -433,6 +476,29 @@ __global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, l
         tile_zero_column(tile, lane);
     }
     warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, grid_in, flush_variant);
+}
+
+// P2G with the one-plane tile (dynamic shared memory: kBlock/32 plane tiles).  Every lane runs the particle math (lanes
+// past the end re-do the last particle with key = -1 and no stores) because the per-plane flush is warp-collective.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_p2g_plane(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
+                                                      int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    if (!valid) p = P.n_particles - 1;
+    FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
+    V3<T> x = load_x(fin, p);
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    WarpPlaneScatter<T> sc;
+    sc.tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kPlaneVec4;
+    sc.grid = grid_in; sc.lane = lane; sc.n_grid = P.n_grid;
+    sc.key = valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1;
+    p2g_body<T, WarpPlaneScatter<T>>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0 && valid, mat, sc);
+    if (flags && valid) mark_blocks<T>(P, x, flags);
 }
 
 template <class T>
