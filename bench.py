@@ -275,20 +275,39 @@ def main():
             env1 = TaichiEnv(cfg1, dtype=args.dtype, device=local_rank)
             env1.initialize()
             env1.loss.set_weights(10, 10, 1, False)
-            sol1 = Solver(env1, None, None, n_iters=1, softness=666.0, horizon=w["horizon"])
-            sol1.total_steps = 0
             a1 = actions_for(w, env1.primitives.action_dim)
-            st1 = env1.get_state()["state"]
-            for _ in range(2):
-                sol1.forward(st1, a1)
+            g1 = np.zeros((w["horizon"], env1.primitives.action_dim))
+            e1 = env1.engine
+
+            def episode1():          # device-resident episode, identical to episode_device() below
+                env1.simulator.cur = 0
+                env1._is_copy = False
+                for p in env1.primitives:
+                    p.set_state(0, p.init_state)
+                e1.call("plb_zero_grads")
+                for i in range(w["horizon"]):
+                    e1.call("plb_set_action", i, S, _capi.dptr(np.ascontiguousarray(a1[i])), a1.shape[1])
+                    e1.call("plb_kinematics", i * S, S)
+                    e1.call("plb_step_fwd", i * S, i * S, S)
+                    e1.call("plb_loss_fwd", (i + 1) * S, (i + 1) * S, None)
+                for i in reversed(range(w["horizon"])):
+                    e1.call("plb_loss_bwd", (i + 1) * S, (i + 1) * S)
+                    e1.call("plb_step_bwd", i * S, i * S, S)
+                e1.call("plb_get_action_grad", w["horizon"], S, _capi.dptr(g1))
+
+            env1.primitives.set_softness(666.0)
+            for _ in range(3):
+                episode1()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            sol1.forward(st1, a1)
+            for _ in range(args.steps):
+                episode1()
             torch.cuda.synchronize()
-            n1_reference = {"n_gpus": 1, "value": env1.n_particles * w["horizon"] * S / (time.perf_counter() - t0), "unit": UNIT,
-                            "how": "same per-GPU workload through Solver.forward on rank 0 before the multi-GPU run (1 timed episode)"}
+            n1_reference = {"n_gpus": 1, "value": env1.n_particles * w["horizon"] * S * args.steps / (time.perf_counter() - t0), "unit": UNIT,
+                            "how": "the per-GPU share of this workload on one GPU (rank 0, regular single-GPU path, state resident in HBM, "
+                                   "same episode structure), measured in this process before the multi-GPU run"}
             env1.engine.close()
-            del env1, sol1
+            del env1
         dist.barrier()
         from plasticinelab_b200.engine.sharded import ShardedEnv
         senv = ShardedEnv(cfg, dtype=args.dtype, device=local_rank, halo_w=8)
