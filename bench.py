@@ -40,6 +40,10 @@ WORKLOADS = {
     # north_star roofline target size
     "move1m": dict(scene="move.yml", n=1_000_000, quality=2, horizon=10,
                    desc="Move-v1 geometry, 1M particles, 128^3 grid, 10 env steps x 39 substeps, fwd+bwd"),
+    # the full 50-step episode at 1M particles: 1951 frames would need 187 GB, so env-step checkpointing (91 frames, 8.7 GB)
+    "move1m_ckpt": dict(scene="move.yml", n=1_000_000, quality=2, horizon=50, checkpoint=True,
+                        desc="Move-v1 geometry, 1M particles, 128^3 grid, 50 env steps x 39 substeps, fwd+bwd with env-step "
+                             "checkpointing (one extra forward pass; a fwd+bwd substep still counts once)"),
     # BASELINE.json configs[0] (the reference's own CPU-runnable case), here as fwd+bwd
     "move10k": dict(scene="move.yml", n=10_000, quality=1, horizon=50,
                     desc="Move-v1 stock, 10k particles, 64^3 grid, 50 env steps x 19 substeps, fwd+bwd"),
@@ -72,7 +76,7 @@ def build_cfg(w, world=1):
         cfg.SIMULATOR.quality = w["quality"]
         cfg.SHAPES[0]["n_particles"] = w["n"]
     S = _capi.sim_constants(dict(cfg.SIMULATOR))["substeps"]
-    cfg.SIMULATOR.max_steps = w["horizon"] * S + 2
+    cfg.SIMULATOR.max_steps = (S + 1 + w["horizon"] + 2) if w.get("checkpoint") else (w["horizon"] * S + 2)
     return cfg, S
 
 
@@ -313,10 +317,14 @@ def main():
         senv = ShardedEnv(cfg, dtype=args.dtype, device=local_rank, halo_w=8)
         env = senv.env
     else:
-        env = TaichiEnv(cfg, dtype=args.dtype, device=local_rank)
+        env = TaichiEnv(cfg, dtype=args.dtype, device=local_rank, max_prim_frames=w["horizon"] * S + 2)
         env.initialize()
     env.loss.set_weights(10, 10, 1, False)
     eng = env.engine
+    ckpt = None
+    if w.get("checkpoint"):
+        from plasticinelab_b200.engine.checkpoint import CheckpointedEpisode
+        ckpt = CheckpointedEpisode(env, w["horizon"])
     eng.call("plb_set_stream", C.c_void_p(torch.cuda.current_stream().cuda_stream))
     N, H = env.n_particles, w["horizon"]
     N_global = senv.n_global if slab else N * world
@@ -342,6 +350,9 @@ def main():
         """state resident in HBM (frame 0), no host read-back except the final action gradient"""
         if slab:
             return episode_slab(False)
+        if ckpt is not None:
+            grad_out[:, :A] = ckpt.forward_backward(pinned_actions.numpy())[1]
+            return
         env.simulator.cur = 0
         env._is_copy = False
         for p in env.primitives:
@@ -361,6 +372,9 @@ def main():
     def episode_e2e():
         if slab:
             return episode_slab(True)
+        if ckpt is not None:
+            env.set_state(host_state, 666.0, False)
+            return ckpt.forward_backward(pinned_actions.numpy(), sync_losses=True)
         return solver.forward(host_state, pinned_actions.numpy())
 
     def timed(fn, k):
@@ -416,7 +430,7 @@ def main():
 
     # ---- roofline of the dominant kernel + of the fused substep
     na = C.c_longlong()
-    eng.call("plb_count_active", (H // 2) * S, C.byref(na))
+    eng.call("plb_count_active", (S // 2) if ckpt is not None else (H // 2) * S, C.byref(na))
     n_active = int(na.value)
     peak, peak_src = measured_peak_gbs()
     names = [eng.lib.plb_kernel_name(i).decode() for i in range(nk)]

@@ -304,3 +304,36 @@ def test_engine_matches_committed_golden_vectors():
     assert abs(info['loss'] - float(m['step_loss'])) < 1e-9 * float(m['step_loss'])
     assert np.abs(st[0][m['sel']] - m['x']).max() < 1e-12 and np.abs(st[1][m['sel']] - m['v']).max() < 1e-9
     assert np.abs(st[2][m['sel']] - m['F']).max() < 1e-11
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+def test_checkpointed_gradient_equals_full_tape(dtype):
+    """The reference's only numerical self-check (plb/optimizer/long_term_gradient.ipynb cell 4): the gradient from env-step
+    checkpointing equals the full-tape gradient (there: max abs diff 1.5e-5 < 1e-4 in f64; here 1e-9 relative in f64)."""
+    from plasticinelab_b200.config import load_dict
+    from plasticinelab_b200.engine.checkpoint import CheckpointedEpisode
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.optimizer.solver import Solver
+    H_ = 4
+    actions = np.random.RandomState(4).uniform(-1, 1, (H_, 6))
+    results = []
+    for mode in ('full', 'ckpt'):
+        cfg = _episode_cfg(500)
+        S = _capi.sim_constants(dict(cfg.SIMULATOR))['substeps']
+        cfg.SIMULATOR.max_steps = (H_ * S + 2) if mode == 'full' else (S + 1 + H_ + 2)
+        env = TaichiEnv(cfg, dtype=dtype, max_prim_frames=H_ * S + 2)
+        env.initialize()
+        env.loss.load_target_density(grids=_target32(env))
+        env.loss.set_weights(10, 10, 1, False)
+        if mode == 'full':
+            solver = Solver(env, None, None, n_iters=1, softness=666., horizon=H_)
+            solver.total_steps = 0
+            results.append(solver.forward(env.get_state()['state'], actions))
+        else:
+            env.set_state(env.get_state()['state'], 666.0, False)
+            results.append(CheckpointedEpisode(env, H_).forward_backward(actions))
+    (l0, g0), (l1, g1) = results
+    tol = 1e-9 if dtype == 'float64' else 1e-3
+    assert abs(l0 - l1) < tol * abs(l0)
+    assert H.relerr(g1, g0) < tol
+    assert np.abs(g1 - g0).max() < 1e-4                 # the notebook's own bound
