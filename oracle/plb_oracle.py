@@ -93,7 +93,7 @@ def qmul(q, r):
 def w2quat(w):
     """plb/engine/primitive/utils.py:29-41.  For |w| <= 1e-9 the identity is returned and no
     gradient reaches w (the oracle defines the Taichi 0*inf case as 0)."""
-    n2 = float((w * w).sum())
+    n2 = float((w * w).sum().detach())
     if math.sqrt(n2) > 1e-9:
         n = torch.sqrt((w * w).sum())
         v = (w / n) * torch.sin(n / 2)

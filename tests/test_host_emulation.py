@@ -171,3 +171,48 @@ def test_substep_adjoint_mixed_and_elastic_f64(emul_lib, fscale, ys):
                               D(gxn), D(gvn), D(gFn), D(gCn), D(gx), D(gv), D(gF), D(gC), D(gp0), D(gp1))
     for a, b in zip((gx, gv, gC, gF), o_adj):
         assert H.relerr(a, b.numpy()) < 1e-7
+
+
+@pytest.mark.parametrize('name', ['capsule', 'chopsticks', 'rollingpin', 'spheres'])
+def test_kinematics_forward_and_adjoint(emul_lib, name):
+    """forward_kinematics + its adjoint in the engine's C++ (csrc/plb_kinematics.hpp) against torch autograd through the
+    oracle's `fk` (base class: left-multiplied rotation; Chopsticks: right-multiplied + gap; RollingPin: custom)."""
+    sets = dict(PRIM_SETS)
+    sets['rollingpin'] = [dict(shape='RollingPin', h=0.3, r=0.03, init_pos=(0.5, 0.3, 0.5), init_rot=(0.707, 0.707, 0., 0.), friction=0.9,
+                               lower_bound=(0., 0.05, 0.), action=dict(dim=3, scale=(0.7, 0.005, 0.005)))]
+    cfg = H.small_cfg(sets[name], n_particles=10)
+    osim = O.OracleSim(dict(cfg.SIMULATOR), [dict(p) for p in cfg.PRIMITIVES])
+    rng = np.random.RandomState(12)
+    for k, prim in enumerate(osim.prims):
+        desc = _capi.primitive_desc(dict(cfg.PRIMITIVES[k]))
+        st = prim.init_state().numpy().copy()
+        st[3:7] = st[3:7] / np.linalg.norm(st[3:7])
+        for trial in range(3):
+            v = 0.01 * rng.randn(3)
+            w = 0.02 * rng.randn(3) if trial < 2 else np.zeros(3)          # trial 2: |w| <= 1e-9 branch
+            gv = 0.003 * rng.rand()
+            if trial == 1:
+                st[1] = float(prim.lower[1]) + 1e-4                        # lower clamp active on y
+                v[1] = -abs(v[1]) - 1e-3
+            st8 = np.zeros(8); st8[:len(st)] = st
+            out = np.zeros(8)
+            emul_lib.emul_fk(C.byref(desc), D(st8), D(np.ascontiguousarray(v)), D(np.ascontiguousarray(w)), C.c_double(gv), D(out))
+            ts = torch.as_tensor(st.copy()).requires_grad_(True)
+            tv = torch.as_tensor(v.copy()).requires_grad_(True)
+            tw = torch.as_tensor(w.copy()).requires_grad_(True)
+            tg = torch.tensor(gv, dtype=torch.float64, requires_grad=True)
+            ref = prim.fk(ts, tv, tw, tg)
+            assert np.abs(out[:len(st)] - ref.detach().numpy()).max() < 1e-13
+            gout = rng.randn(len(st))
+            grads = torch.autograd.grad(ref, [ts, tv, tw, tg], grad_outputs=torch.as_tensor(gout), allow_unused=True)
+            grads = [np.zeros_like(x.detach().numpy()) if g is None else g.numpy() for g, x in zip(grads, (ts, tv, tw, tg))]
+            g8 = np.zeros(8); g8[:len(st)] = gout
+            gst, gvel, gw, ggv = np.zeros(8), np.zeros(3), np.zeros(3), C.c_double(0.0)
+            emul_lib.emul_fk_bwd(C.byref(desc), D(st8), D(np.ascontiguousarray(v)), D(np.ascontiguousarray(w)), C.c_double(gv), D(g8),
+                                 D(gst), D(gvel), D(gw), C.byref(ggv))
+            assert np.abs(gst[:len(st)] - grads[0]).max() < 1e-12, (name, trial, gst, grads[0])
+            assert np.abs(gvel - grads[1]).max() < 1e-12
+            if name != 'rollingpin':
+                assert np.abs(gw - grads[2]).max() < 1e-12
+            if name == 'chopsticks':
+                assert abs(ggv.value - float(grads[3])) < 1e-12
