@@ -391,7 +391,7 @@ template <class T>
 PLB_HD void loss_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj,
                           const T* grid_mass, const T* target, const T* target_sdf, T w_sdf, T w_density, T w_contact,
                           const PrimSet<T>& prims, const Pose<T>* s0, const double* min_dist, int contact_all,
-                          PoseGrad<T>* gpose, unsigned& touched) {
+                          PoseGrad<T>* gpose, unsigned& touched, int soft = 0, const double* soft_norm = nullptr) {
     V3<T> x = load_x(in, p);
     Stencil<T> st = make_stencil(x, P.inv_dx);
     T gw[3][3];
@@ -419,9 +419,19 @@ PLB_HD void loss_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, co
         if (!prims.s[k].movable) continue;
         T d = prim_sdf(prims.s[k], s0[k], x);
         if (!(T(0) < d)) continue;                           // max(sdf, 0): gradient only where 0 < sdf
-        T md = (T)min_dist[k];
-        if (!contact_all && d > md) continue;
-        T g = T(2) * md * w_contact;
+        T g;
+        if (soft) {
+            // min_dist = S1 / S0, S1 = sum d sw, S0 = sum sw (loss.py:116-135).  min_dist[k] holds S1, soft_norm[k] holds S0.
+            // d(min_dist^2 w_c)/dd_i = g_md [ (sw + d sw') / S0  -  (S1 / S0^2) sw' ],  sw' = -2e4 d sw^2
+            double S0 = soft_norm[k], md_ = min_dist[k] / S0, dd = (double)d;
+            double sw = 1.0 / (1.0 + dd * dd * 10000.0), dsw = -20000.0 * dd * sw * sw;
+            double g_md = 2.0 * md_ * (double)w_contact;
+            g = (T)(g_md * ((sw + dd * dsw) / S0 - md_ / S0 * dsw));
+        } else {
+            T md = (T)min_dist[k];
+            if (!contact_all && d > md) continue;
+            g = T(2) * md * w_contact;
+        }
         if (g != T(0)) {
             prim_sdf_vjp(prims.s[k], s0[k], x, g, gpose[k], &gx);
             touched |= 1u << k;

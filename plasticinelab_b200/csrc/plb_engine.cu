@@ -768,7 +768,7 @@ struct Engine : plb_engine {
     int slab_loss_begin(int slot) override {
         if (int r = check_slot(slot)) return r;
         PLB_REQUIRE(slab.on && has_target, "slab loss needs slab mode and a target");
-        k_loss_init<<<1, 32, 0, stream>>>(d_acc);
+        k_loss_init<<<1, 32, 0, stream>>>(d_acc, lw.soft);
         PLB_CUDA(cudaMemsetAsync(grid_mass, 0, n_nodes * sizeof(T), stream));
         k_loss_mass_tile<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass, flush_variant);
         launches += 2;
@@ -787,7 +787,7 @@ struct Engine : plb_engine {
         size_t off = (size_t)slab.own_lo * plane;
         int rb = (int)std::min<long long>((own_nodes + 255) / 256, 148 * 8);
         k_loss_reduce<T><<<rb, 256, 0, stream>>>(grid_mass + off, target + off, target_sdf + off, own_nodes, d_acc);
-        k_loss_contact<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, d_acc);
+        k_loss_contact<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, d_acc, lw.soft);
         launches += 2;
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
@@ -996,19 +996,18 @@ struct Engine : plb_engine {
         return PLB_OK;
     }
     int set_loss_weights(double sdf, double density, double contact, int soft, int all) override {
-        if (soft) { err = "soft contact loss is not implemented in the CUDA engine yet"; return PLB_ERR_UNSUPPORTED; }
         lw.sdf = sdf; lw.density = density; lw.contact = contact; lw.soft = soft; contact_all = all;
         return PLB_OK;
     }
     int loss_terms(int slot, int pf) {
         int nb = blocks(cfg.n_particles);
-        k_loss_init<<<1, 32, 0, stream>>>(d_acc);
+        k_loss_init<<<1, 32, 0, stream>>>(d_acc, lw.soft);
         PLB_CUDA(cudaMemsetAsync(grid_mass, 0, n_nodes * sizeof(T), stream));
         if (tile_scatter) k_loss_mass_tile<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass, flush_variant);
         else k_loss_mass<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
         int rb = (int)std::min<long long>((n_nodes + 255) / 256, 148 * 8);
         k_loss_reduce<T><<<rb, 256, 0, stream>>>(grid_mass, target, target_sdf, n_nodes, d_acc);
-        k_loss_contact<T><<<nb, kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, d_acc);
+        k_loss_contact<T><<<nb, kBlock, 0, stream>>>(P, prims, d_traj, pf, frames, n_pad, slot, d_acc, lw.soft);
         launches += 4;
         return PLB_OK;
     }

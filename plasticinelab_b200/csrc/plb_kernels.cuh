@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(kBlock, Occ<T>::p2g_bwd) k_p2g_bwd(SimConst<T>
 
 // ------------------------------------------------------------------------------------------------ loss
 // accumulator layout (doubles): [0] density  [1] sdf  [2] sum m*t  [3] sum m  [4] max m (bits)  [8+k] min_dist_k (bits)
-constexpr int kAccN = 8 + PLB_MAX_PRIM;
+constexpr int kAccN = 8 + 2 * PLB_MAX_PRIM;    // [8+k] hard: min distance | soft: sum d*sw (-> soft distance), [16+k] soft: sum sw
 
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_loss_mass(SimConst<T> P, T* frames, long long n_pad, int slot, T* grid_mass) {
@@ -696,9 +696,9 @@ __global__ void __launch_bounds__(kBlock) k_loss_mass_tile(SimConst<T> P, T* fra
     warp_tile_flush<T, T>(tile, lane, valid, b, P.n_grid, grid_mass, flush_variant);
 }
 
-__global__ void k_loss_init(double* acc) {
+__global__ void k_loss_init(double* acc, int soft) {
     int i = threadIdx.x;
-    if (i < kAccN) acc[i] = (i >= 8) ? 100000.0 : 0.0;
+    if (i < kAccN) acc[i] = (i >= 8 && i < 8 + PLB_MAX_PRIM && !soft) ? 100000.0 : 0.0;
 }
 
 template <class T>
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(256) k_loss_reduce(const T* __restrict__ grid_
 
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_loss_contact(SimConst<T> P, PrimSet<T> prims, const double* traj, int pf,
-                                                         T* frames, long long n_pad, int slot, double* acc) {
+                                                         T* frames, long long n_pad, int slot, double* acc, int soft) {
     __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
     load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -735,12 +735,20 @@ __global__ void __launch_bounds__(kBlock) k_loss_contact(SimConst<T> P, PrimSet<
     V3<T> x = ok ? load_x(frame_at(frames, slot, n_pad), p) : zero3<T>();
     for (int k = 0; k < P.n_prim; k++) {
         if (!prims.s[k].movable) continue;
-        double d = 1e30;
-        if (ok) d = (double)tmax(tmax(prim_sdf(prims.s[k], s0[k], x), T(0)), T(0));
+        if (soft) {
+            // soft minimum (loss.py:112-135): sum_i sw(d_i) and sum_i d_i sw(d_i), sw(d) = 1 / (1 + 1e4 d^2)
+            double d = ok ? (double)tmax(prim_sdf(prims.s[k], s0[k], x), T(0)) : 0.0;
+            double sw = ok ? 1.0 / (1.0 + d * d * 10000.0) : 0.0;
+            double a = warp_sum(sw), b = warp_sum(d * sw);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(acc + 8 + PLB_MAX_PRIM + k, a); if (b != 0.0) atomicAdd(acc + 8 + k, b); }
+        } else {
+            double d = 1e30;
+            if (ok) d = (double)tmax(tmax(prim_sdf(prims.s[k], s0[k], x), T(0)), T(0));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) d = fmin(d, __shfl_xor_sync(0xffffffffu, d, o));
-        if ((threadIdx.x & 31) == 0)
-            atomicMin(reinterpret_cast<unsigned long long*>(acc + 8 + k), (unsigned long long)__double_as_longlong(d));
+            for (int o = 16; o > 0; o >>= 1) d = fmin(d, __shfl_xor_sync(0xffffffffu, d, o));
+            if ((threadIdx.x & 31) == 0)
+                atomicMin(reinterpret_cast<unsigned long long*>(acc + 8 + k), (unsigned long long)__double_as_longlong(d));
+        }
     }
 }
 
@@ -750,7 +758,10 @@ __global__ void k_loss_finalize(PrimSet<T> prims, int n_prim, LossWeights w, con
                                 double target_sum, double* loss_total, double* record) {
     double contact = 0;
     for (int k = 0; k < n_prim; k++)
-        if (prims.s[k].movable) contact += acc[8 + k] * acc[8 + k];
+        if (prims.s[k].movable) {
+            double md = w.soft ? acc[8 + k] / acc[8 + PLB_MAX_PRIM + k] : acc[8 + k];
+            contact += md * md;
+        }
     double step = contact * w.contact + acc[0] * w.density + acc[1] * w.sdf;
     *loss_total += step;
     double ma = __longlong_as_double((long long)reinterpret_cast<const unsigned long long*>(acc)[4]);
@@ -773,7 +784,7 @@ __global__ void __launch_bounds__(kBlock) k_loss_bwd(SimConst<T> P, PrimSet<T> p
     if (p < P.n_particles) {
         for (int k = 0; k < P.n_prim; k++) g[k].clear();
         loss_bwd_body<T>(p, P, frame_at(frames, slot, n_pad), frame_at(adj, 0, n_pad), grid_mass, target, target_sdf,
-                         (T)w.sdf, (T)w.density, (T)w.contact, prims, s0, acc + 8, contact_all, g, touched);
+                         (T)w.sdf, (T)w.density, (T)w.contact, prims, s0, acc + 8, contact_all, g, touched, w.soft, acc + 8 + PLB_MAX_PRIM);
     }
     for (int k = 0; k < P.n_prim; k++) {
         unsigned any = __ballot_sync(0xffffffffu, (touched >> k) & 1u);

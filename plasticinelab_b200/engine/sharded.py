@@ -110,7 +110,10 @@ class ShardedEnv:
             return
         dist.all_reduce(self.acc[0:4], op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(self.acc[4:5], op=dist.ReduceOp.MAX, group=self.group)
-        dist.all_reduce(self.acc[8:16], op=dist.ReduceOp.MIN, group=self.group)
+        if self.env.loss.soft_contact_loss:      # soft minimum: both partial sums add up
+            dist.all_reduce(self.acc[8:24], op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(self.acc[8:16], op=dist.ReduceOp.MIN, group=self.group)
 
     # ---- episode (trajectory mode), same call pattern as TaichiEnv under the tape
     def begin_episode(self, softness=666.0):

@@ -121,7 +121,7 @@ int substep_bwd(const plb_config* c, const plb_primitive_desc* pd, double softne
 template <class T>
 int loss_both(const plb_config* c, const plb_primitive_desc* pd, const double* x, const double* pose, const double* target,
               const double* target_sdf, double w_sdf, double w_density, double w_contact, int contact_all, double* out4,
-              double* gx, double* gpose) {
+              double* gx, double* gpose, int soft) {
     Host<T> h(*c, pd, 0.0);
     std::vector<double> zero3v(3 * c->n_particles, 0.0), zero9(9 * c->n_particles, 0.0);
     h.pack(h.frame_in, x, zero3v.data(), zero9.data(), zero9.data());
@@ -133,15 +133,17 @@ int loss_both(const plb_config* c, const plb_primitive_desc* pd, const double* x
     for (long long n = 0; n < h.n_nodes; n++) { density += std::fabs((double)gm[n] - (double)tg[n]); sdf += (double)ts[n] * (double)gm[n]; }
     Pose<T> s0[PLB_MAX_PRIM];
     for (int k = 0; k < c->n_primitives; k++) s0[k] = load_pose<T>(pose + k * 8);
-    double md[PLB_MAX_PRIM], contact = 0;
+    double md[PLB_MAX_PRIM], nrm[PLB_MAX_PRIM], contact = 0;
     for (int k = 0; k < c->n_primitives; k++) {
-        md[k] = 100000.0;
+        md[k] = soft ? 0.0 : 100000.0; nrm[k] = 0.0;
         if (!h.prims.s[k].movable) continue;
         for (int p = 0; p < c->n_particles; p++) {
             double d = (double)tmax(prim_sdf(h.prims.s[k], s0[k], load_x(fi, p)), T(0));
-            if (d < md[k]) md[k] = d;
+            if (soft) { double sw = 1.0 / (1.0 + d * d * 10000.0); nrm[k] += sw; md[k] += d * sw; }
+            else if (d < md[k]) md[k] = d;
         }
-        contact += md[k] * md[k];
+        double v = soft ? md[k] / nrm[k] : md[k];
+        contact += v * v;
     }
     out4[0] = contact * w_contact + density * w_density + sdf * w_sdf; out4[1] = contact; out4[2] = density; out4[3] = sdf;
     std::memset(gpose, 0, sizeof(double) * 8 * c->n_primitives);
@@ -150,7 +152,7 @@ int loss_both(const plb_config* c, const plb_primitive_desc* pd, const double* x
         for (int k = 0; k < c->n_primitives; k++) g[k].clear();
         unsigned touched = 0;
         loss_bwd_body<T>(p, h.P, fi, ad, gm.data(), tg.data(), ts.data(), (T)w_sdf, (T)w_density, (T)w_contact, h.prims, s0, md,
-                         contact_all, g, touched);
+                         contact_all, g, touched, soft, nrm);
         for (int k = 0; k < c->n_primitives; k++) {
             if (!((touched >> k) & 1u)) continue;
             double* d = gpose + k * 8;
@@ -182,9 +184,9 @@ int emul_substep_bwd(int dtype, const plb_config* c, const plb_primitive_desc* p
 }
 int emul_loss(int dtype, const plb_config* c, const plb_primitive_desc* pd, const double* x, const double* pose, const double* target,
               const double* target_sdf, double w_sdf, double w_density, double w_contact, int contact_all, double* out4, double* gx,
-              double* gpose) {
-    return dtype == PLB_F32 ? loss_both<float>(c, pd, x, pose, target, target_sdf, w_sdf, w_density, w_contact, contact_all, out4, gx, gpose)
-                            : loss_both<double>(c, pd, x, pose, target, target_sdf, w_sdf, w_density, w_contact, contact_all, out4, gx, gpose);
+              double* gpose, int soft) {
+    return dtype == PLB_F32 ? loss_both<float>(c, pd, x, pose, target, target_sdf, w_sdf, w_density, w_contact, contact_all, out4, gx, gpose, soft)
+                            : loss_both<double>(c, pd, x, pose, target, target_sdf, w_sdf, w_density, w_contact, contact_all, out4, gx, gpose, soft);
 }
 void emul_fk(const plb_primitive_desc* d, const double* st, const double* v, const double* w, double gv, double* out) {
     kin::fk_forward(make_kindesc(*d), st, v, w, gv, out);

@@ -389,3 +389,23 @@ def test_all_ten_tasks_step_and_differentiate():
         loss, grad = solver.forward(tenv.get_state()['state'], np.tile(a, (2, 1)))
         assert np.isfinite(loss) and np.isfinite(grad).all() and grad.shape == (2, len(a)), task
         tenv.engine.close()
+
+
+def test_soft_contact_loss_episode_f64():
+    """`make(..., soft_contact_loss=True)` path: soft-minimum contact distance (loss.py:112-135) and its adjoint, episode level."""
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.optimizer.solver import Solver
+    cfg = _episode_cfg()
+    env = TaichiEnv(cfg, dtype='float64')
+    env.initialize()
+    t32 = _target32(env)
+    env.loss.load_target_density(grids=t32)
+    env.loss.set_weights(10, 10, 1, True)
+    actions = np.random.RandomState(8).uniform(-1, 1, (2, 6))
+    solver = Solver(env, None, None, n_iters=1, softness=666., horizon=2)
+    solver.total_steps = 0
+    loss, grad = solver.forward(env.get_state()['state'], actions)
+    oenv = O.OracleEnv(cfg, env.init_particles, t32, target_sdf=O.build_target_sdf_c(t32, 1 / 32), soft_contact=True)
+    out = oenv.rollout(actions, softness=666.0)
+    assert abs(loss - out['loss']) < 1e-9 * abs(out['loss'])
+    assert H.relerr(grad, out['grad']) < 1e-6

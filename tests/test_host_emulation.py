@@ -216,3 +216,38 @@ def test_kinematics_forward_and_adjoint(emul_lib, name):
                 assert np.abs(gw - grads[2]).max() < 1e-12
             if name == 'chopsticks':
                 assert abs(ggv.value - float(grads[3])) < 1e-12
+
+
+@pytest.mark.parametrize('mode', ['hard_taichi', 'hard_argmin', 'soft'])
+def test_loss_value_and_adjoint(emul_lib, mode):
+    """Per-step loss (density + target-SDF + contact) and its adjoint wrt particle positions and primitive poses
+    (plb/engine/losses/loss.py:116-153,186-237), hard contact in both gradient conventions and the soft minimum."""
+    n = 500
+    prims = PRIM_SETS['spheres'] + [dict(shape='Capsule', h=0.1, r=0.03, init_pos=(0.45, 0.62, 0.5), init_rot=(0.9, 0.1, 0.3, 0.2),
+                                         friction=0.9, action=dict(dim=6, scale=(0.01,) * 6))]
+    cfg = H.small_cfg(prims, n_particles=n)
+    osim = O.OracleSim(dict(cfg.SIMULATOR), [dict(p) for p in cfg.PRIMITIVES])
+    osim.set_materials(n)
+    rng = np.random.RandomState(21)
+    x = rng.uniform(0.3, 0.7, (n, 3))
+    G = osim.n_grid
+    target = np.zeros((G, G, G)); target[10:18, 10:20, 12:20] = rng.rand(8, 10, 8) * 1e-3
+    tsdf = rng.rand(G, G, G)
+    soft = mode == 'soft'
+    oloss = O.OracleLoss(osim, target, (3.0, 7.0, 2.0), soft_contact=soft, contact_grad='taichi' if mode != 'hard_argmin' else 'argmin',
+                         target_sdf=tsdf)
+    poses = [p.init_state().numpy().copy() for p in osim.prims]
+    for s in poses:
+        s[3:7] /= np.linalg.norm(s[3:7])
+    pf = [torch.as_tensor(s) for s in poses]
+    val = oloss.value(torch.as_tensor(x), pf)
+    ogx, ogp = oloss.vjp(torch.as_tensor(x), pf)
+    conf, parr, _ = H.c_setup(cfg, n, 'float64')
+    out4, gx, gp = np.zeros(4), np.zeros((n, 3)), np.zeros((len(poses), 8))
+    emul_lib.emul_loss(conf.dtype, C.byref(conf), parr, D(np.ascontiguousarray(x)), D(H.pose_array(poses)), D(target), D(tsdf),
+                       C.c_double(3.0), C.c_double(7.0), C.c_double(2.0), int(mode != 'hard_argmin'), D(out4), D(gx), D(gp), int(soft))
+    assert abs(out4[0] - val['loss']) < 1e-12 * abs(val['loss']) and abs(out4[1] - val['contact_loss']) < 1e-14 + 1e-12 * val['contact_loss']
+    assert H.relerr(gx, ogx.numpy()) < 1e-10
+    for k in range(len(poses)):
+        ref = ogp[k].numpy()
+        assert np.abs(gp[k, :7] - ref).max() < 1e-9 * max(np.abs(ref).max(), 1e-12) + 1e-13, (k, gp[k], ref)
