@@ -36,6 +36,7 @@ def main():
     ap.add_argument('--dtype', default='float64')
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--peer', type=int, default=1)
+    ap.add_argument('--materials', type=int, default=0)
     args = ap.parse_args()
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -47,6 +48,13 @@ def main():
 
     senv = ShardedEnv(cfg, dtype=args.dtype, halo_w=8, peer=bool(args.peer))
     senv.env.loss.set_weights(10, 10, 1, False)
+
+    def materials(x0):      # two materials split at x = 0.5 (BASELINE config 4 style)
+        stiff = x0[:, 0] >= 0.5
+        E = np.where(stiff, 2e4, 5e3)
+        return E / 2.4, E * 0.2 / (1.2 * 0.6), np.where(stiff, 200.0, 50.0)
+    if args.materials:
+        senv.env.simulator.set_materials(*materials(senv.env.init_particles))
     senv.begin_episode(666.0)
     for a in actions:
         senv.step(a)
@@ -61,6 +69,8 @@ def main():
         ref = TaichiEnv(scene(), dtype=args.dtype, device=local)
         ref.initialize()
         ref.loss.set_weights(10, 10, 1, False)
+        if args.materials:
+            ref.simulator.set_materials(*materials(ref.init_particles))
         from plasticinelab_b200.optimizer.solver import Solver
         solver = Solver(ref, None, None, n_iters=1, softness=666., horizon=args.steps)
         solver.total_steps = 0

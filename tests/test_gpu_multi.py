@@ -20,3 +20,13 @@ def test_slab_parity_two_ranks(dtype, peer):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+def test_slab_parity_two_ranks_multi_material():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29617', os.path.join(ROOT, 'tests', 'multi', 'slab_parity.py'), '--dtype', 'float64', '--materials', '1']
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0

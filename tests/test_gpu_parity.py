@@ -409,3 +409,31 @@ def test_soft_contact_loss_episode_f64():
     out = oenv.rollout(actions, softness=666.0)
     assert abs(loss - out['loss']) < 1e-9 * abs(out['loss'])
     assert H.relerr(grad, out['grad']) < 1e-6
+
+
+def test_per_particle_materials_episode_f64():
+    """BASELINE config 4 style multi-material scene: per-particle mu / lam / yield_stress arrays (fields
+    mpm_simulator.py:29-31), set before the spatial sort and after it (the engine keeps host order through its permutation)."""
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.optimizer.solver import Solver
+    cfg = _episode_cfg()
+    env = TaichiEnv(cfg, dtype='float64')
+    env.initialize()
+    t32 = _target32(env)
+    env.loss.load_target_density(grids=t32)
+    env.loss.set_weights(10, 10, 1, False)
+    x0 = env.init_particles
+    stiff = x0[:, 0] >= 0.5
+    E, nu = np.where(stiff, 2e4, 5e3), 0.2
+    mu, lam = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    ys = np.where(stiff, 200.0, 50.0)
+    env.simulator.set_materials(mu, lam, ys)                  # after initialize(): particles are already sorted
+    actions = np.random.RandomState(9).uniform(-1, 1, (2, 6))
+    solver = Solver(env, None, None, n_iters=1, softness=666., horizon=2)
+    solver.total_steps = 0
+    loss, grad = solver.forward(env.get_state()['state'], actions)      # set_state re-sorts: materials must follow
+    oenv = O.OracleEnv(cfg, x0, t32, target_sdf=O.build_target_sdf_c(t32, 1 / 32), materials=dict(mu=mu, lam=lam, yield_stress=ys))
+    out = oenv.rollout(actions, softness=666.0)
+    assert abs(loss - out['loss']) < 1e-9 * abs(out['loss'])
+    assert H.relerr(grad, out['grad']) < 1e-6
+    assert np.abs(env.simulator.get_state(env.simulator.cur)[2] - out['final_state'][3].numpy()).max() < 1e-10     # F
