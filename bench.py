@@ -147,6 +147,12 @@ KERNEL_BYTES = {
 }
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` capture of the final kernels
+# at 1M particles / 128^3 (profiles/r1_final_move1m_ncu_full_summary.md); reported as `roofline.traffic` only for
+# workloads of that size, null otherwise.
+NCU_TRAFFIC_1M = {"p2g": 111.8e6, "g2p": 20.9e6, "g2p_bwd": 80.7e6, "p2g_bwd": 206.8e6}
+
+
 def oracle_sample(cfg, w, S, n_sub, threads):
     """Bounded CPU sample: n_sub fwd+bwd substeps of the same scene on the host cores.
     Sphere-only scenes use the plain-C/OpenMP port of the reference kernels (oracle/mpm_oracle.c, dense grid sweeps and
@@ -448,7 +454,9 @@ def main():
     peak_job = peak * world
     kernel_ms_total = sum(v["total_ms"] for v in per_kernel.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": (NCU_TRAFFIC_1M.get(dom) if (N == 1_000_000 and args.dtype == "float32") else None),
+                "traffic_source": "ncu --set full capture at 1M particles, profiles/r1_final_move1m_ncu_full_summary.md (null for other sizes)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_us": sub[dom]["avg_us"], "share_of_kernel_time": sub[dom]["total_ms"] / max(kernel_ms_total, 1e-9),
                 "n_active_nodes": n_active,
                 "timing": "CUDA events around every launch of one extra episode run inside bench.py right after the timed "
