@@ -104,17 +104,11 @@ template <class T> PLB_HD void load_material(const SimConst<T>& P, const Materia
 // forward substep
 // ================================================================================================
 // P2G: F_tmp, SVD, return mapping, stress, 27-node scatter.  `out` may alias nothing (F[f+1] store skipped if !store_F_out).
+// register-level core: particle state in, new_F out, 27 contributions through the scatter policy
 template <class T, class Sc>
-PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,
-                     const Material<T>& mat, const Sc& sc) {
-    V3<T> x, v; M3<T> C;
-    load_xvC(in, p, x, v, C);
-    M3<T> F = load_F(in, p);
-    T mu, lam, ys;
-    load_material(P, mat, p, mu, lam, ys);
-    M3<T> new_F, affine;
+PLB_HD void p2g_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys, M3<T>& new_F, const Sc& sc) {
+    M3<T> affine;
     p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine);
-    if (store_F_out) store_F(out, p, new_F);
     Stencil<T> st = make_stencil(x, P.inv_dx);
     // momentum_o = w_o (p_mass v + affine ((o - fx) dx)) = w_o (m0 + i c0 + j c1 + k c2): the affine part is evaluated
     // incrementally along the three stencil axes (81 + 27 + 9 FMAs instead of 27 mat-vecs)
@@ -139,6 +133,18 @@ PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const F
         sc.end_plane(i);
     }
 }
+template <class T, class Sc>
+PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,
+                     const Material<T>& mat, const Sc& sc) {
+    V3<T> x, v; M3<T> C;
+    load_xvC(in, p, x, v, C);
+    M3<T> F = load_F(in, p);
+    T mu, lam, ys;
+    load_material(P, mat, p, mu, lam, ys);
+    M3<T> new_F;
+    p2g_core<T, Sc>(P, x, v, C, F, mu, lam, ys, new_F, sc);
+    if (store_F_out) store_F(out, p, new_F);
+}
 template <class T>
 PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,
                      const Material<T>& mat, Vec4<T>* grid_in) {
@@ -161,8 +167,7 @@ PLB_HD void grid_fwd_body(long long node, const SimConst<T>& P, const PrimSet<T>
 
 // G2P: 27-node gather, APIC C, advection
 template <class T>
-PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, const Vec4<T>* grid_out) {
-    V3<T> x = load_x(in, p);
+PLB_HD void g2p_core(const SimConst<T>& P, V3<T> x, const Vec4<T>* grid_out, V3<T>& nx, V3<T>& nv_out, M3<T>& nC_out) {
     Stencil<T> st = make_stencil(x, P.inv_dx);
     // v' = sum w g;  C' = 4 inv_dx sum w g (x) (o - fx) = 4 inv_dx (sum w g (x) o - v' (x) fx): accumulate sum w g and the
     // three offset-weighted sums (offsets are 0/1/2, so these are adds), one rank-1 correction at the end
@@ -194,8 +199,31 @@ PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const F
         nC.m[r][1] = c4 * (sj[r] - nv[r] * st.fx.y);
         nC.m[r][2] = c4 * (sk[r] - nv[r] * st.fx.z);
     }
-    V3<T> nx = advect(P, x, nv);
+    nx = advect(P, x, nv);
+    nv_out = nv;
+    nC_out = nC;
+}
+template <class T>
+PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, const Vec4<T>* grid_out) {
+    V3<T> nx, nv; M3<T> nC;
+    g2p_core<T>(P, load_x(in, p), grid_out, nx, nv, nC);
     store_xvC(out, p, nx, nv, nC);
+}
+
+// fused forward kernel body: G2P of substep s (frame `in` -> frame `mid`), then P2G of substep s+1 straight from registers
+// (F[s+1] was written by the previous P2G; F[s+2] goes to frame `out`).  Saves one pass over x,v,C and one launch.
+template <class T, class Sc>
+PLB_HD void g2p_p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& mid, const FramePtr<T>& out, bool store,
+                         const Material<T>& mat, const Vec4<T>* grid_out, const Sc& sc) {
+    V3<T> nx, nv; M3<T> nC;
+    g2p_core<T>(P, load_x(in, p), grid_out, nx, nv, nC);
+    if (store) store_xvC(mid, p, nx, nv, nC);
+    M3<T> F = load_F(mid, p);
+    T mu, lam, ys;
+    load_material(P, mat, p, mu, lam, ys);
+    M3<T> new_F;
+    p2g_core<T, Sc>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
+    if (store) store_F(out, p, new_F);
 }
 
 // ================================================================================================
@@ -204,11 +232,7 @@ PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const F
 // g2p.grad: reads adjoint of (x,v,C)[f+1], scatters the adjoint of grid_out, writes the partial x-adjoint of frame f
 // into adj_cur.A0 (xyz lanes; the w lane is finished by p2g_bwd_body).
 template <class T, class Sc>
-PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
-                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, const Sc& sc) {
-    V3<T> x = load_x(in, p);
-    V3<T> gxn, gvn; M3<T> gCn;
-    load_xvC(adj_next, p, gxn, gvn, gCn);
+PLB_HD V3<T> g2p_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> gxn, V3<T> gvn, const M3<T>& gCn, const Vec4<T>* grid_out, const Sc& sc) {
     Stencil<T> st = make_stencil(x, P.inv_dx);
     // recompute new_v = sum w g (clamp masks of the advection; it is also the sum the dpos adjoint needs)
     V3<T> nv = zero3<T>();
@@ -264,6 +288,14 @@ PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
     }
     gfx = (-c4) * mTv(gCn, nv);
     gx += stencil_backward(st, gw, gfx, P.inv_dx);
+    return gx;
+}
+template <class T, class Sc>
+PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
+                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, const Sc& sc) {
+    V3<T> gxn, gvn; M3<T> gCn;
+    load_xvC(adj_next, p, gxn, gvn, gCn);
+    V3<T> gx = g2p_bwd_core<T, Sc>(P, load_x(in, p), gxn, gvn, gCn, grid_out, sc);
     adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
 }
 template <class T>
@@ -292,14 +324,10 @@ PLB_HD void grid_bwd_body(long long node, const SimConst<T>& P, const PrimSet<T>
 }
 
 // p2g.grad + svd_grad + compute_F_tmp.grad: gathers g_in at 27 nodes, finishes the adjoint of frame f in adj_cur.
+// register-level core: state of frame f, adjoint of F[f+1], partial x-adjoint -> full adjoint of frame f
 template <class T>
-PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
-                         const FramePtr<T>& adj_cur, const Material<T>& mat, const Vec4<T>* g_in) {
-    V3<T> x, v; M3<T> C;
-    load_xvC(in, p, x, v, C);
-    M3<T> F = load_F(in, p);
-    T mu, lam, ys;
-    load_material(P, mat, p, mu, lam, ys);
+PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys, const Vec4<T>* g_in,
+                         const M3<T>& gF_next, V3<T> gx_partial, V3<T>& gx_out, V3<T>& gv_out, M3<T>& gC, M3<T>& gF) {
     M3<T> new_F, affine;
     P2GState<T> keep;
     p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine, &keep);
@@ -353,14 +381,44 @@ PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
     }
     V3<T> gfx = (-P.dx) * mTv(affine, gv);
     gv = P.p_mass * gv;
-    V3<T> gx = stencil_backward(st, gw, gfx, P.inv_dx);
-    Vec4<T> part = adj_cur.A0[p];                           // partial x-adjoint from g2p_bwd_body
-    gx += mk3<T>(part.x, part.y, part.z);
-    M3<T> gF_next = load_F(adj_next, p);
-    M3<T> gC, gF;
+    gx_out = stencil_backward(st, gw, gfx, P.inv_dx) + gx_partial;
+    gv_out = gv;
     p2g_particle_backward<T>(P, C, F, mu, lam, keep, g_aff, gF_next, gC, gF);
+}
+template <class T>
+PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
+                         const FramePtr<T>& adj_cur, const Material<T>& mat, const Vec4<T>* g_in) {
+    V3<T> x, v; M3<T> C;
+    load_xvC(in, p, x, v, C);
+    M3<T> F = load_F(in, p);
+    T mu, lam, ys;
+    load_material(P, mat, p, mu, lam, ys);
+    Vec4<T> part = adj_cur.A0[p];                           // partial x-adjoint from g2p_bwd_body
+    V3<T> gx, gv; M3<T> gC, gF;
+    p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(adj_next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
     store_xvC(adj_cur, p, gx, gv, gC);
     store_F(adj_cur, p, gF);
+}
+
+// fused backward kernel body: p2g.grad of substep s (frame `in_s`), then g2p.grad of substep s-1 (frame `in_prev`) with the
+// adjoint of (x,v,C)[s] kept in registers.  Buffers: `next` holds dF[s+1] in its F planes, `cur.A0` holds the partial
+// x-adjoint of frame s; written: `cur` F planes <- dF[s], `next.A0` <- partial x-adjoint of frame s-1 (after the caller's
+// ping-pong swap these are exactly what the following fused / final p2g_bwd_body call reads).
+template <class T, class Sc>
+PLB_HD void p2g_bwd_g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in_s, const FramePtr<T>& in_prev, const FramePtr<T>& next,
+                                 const FramePtr<T>& cur, bool store, const Material<T>& mat, const Vec4<T>* g_in, const Vec4<T>* grid_out,
+                                 const Sc& sc) {
+    V3<T> x, v; M3<T> C;
+    load_xvC(in_s, p, x, v, C);
+    M3<T> F = load_F(in_s, p);
+    T mu, lam, ys;
+    load_material(P, mat, p, mu, lam, ys);
+    Vec4<T> part = cur.A0[p];
+    V3<T> gx, gv; M3<T> gC, gF;
+    p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
+    if (store) store_F(cur, p, gF);
+    V3<T> gxp = g2p_bwd_core<T, Sc>(P, load_x(in_prev, p), gx, gv, gC, grid_out, sc);
+    if (store) next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
 }
 
 // ================================================================================================

@@ -171,6 +171,7 @@ struct Engine : plb_engine {
                   int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; bool peer_ready = false; } slab;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     size_t tile_smem = 0;
+    bool fuse = true;               // fused G2P+P2G / P2G.grad+G2P.grad particle kernels inside env-step graphs (PLB_FUSE=0 disables)
     bool plane_tile = false;        // one-plane (9-node) tile for P2G: 1/3 shared memory, PLB_P2G_PLANE=1
     size_t plane_smem = 0;
     int flush_variant = 0;      // 0 = per-cell groups (measured faster), 1 = chunked runs (PLB_FLUSH overrides)
@@ -258,7 +259,10 @@ struct Engine : plb_engine {
         if (const char* pv = getenv("PLB_P2G_PLANE")) plane_tile = atoi(pv) != 0;
         plane_smem = (size_t)(kBlock / 32) * kPlaneVec4 * sizeof(Vec4<T>);
         tile_smem = (size_t)(kBlock / 32) * kTileVec4 * sizeof(Vec4<T>);
+        fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
         if (tile_scatter) {
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
             PLB_CUDA(cudaFuncSetAttribute(k_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
         }
@@ -490,11 +494,9 @@ struct Engine : plb_engine {
     }
     // Enqueue one forward substep.  Slots/poses are given as SlotRef so the same code serves direct launches
     // (absolute indices) and graph capture (cursor-relative indices).
-    void enqueue_fwd(SlotRef si, SlotRef so, SlotRef pf) {
-        const int nb = blocks(cfg.n_particles);
-        prof_begin(K_P2G);
-        launch_p2g(si, so, 1);
-        prof_end(); prof_begin(K_GRID_FWD);
+    // grid stage of a forward substep: (halo) + active-block list + grid operator (+ store of the forward grid for slot `si`)
+    void enqueue_grid_fwd_stage(SlotRef si, SlotRef pf) {
+        prof_begin(K_GRID_FWD);
         if (sparse) {
             if (slab.peer_ready) {
                 k_halo_next_seq<<<1, 1, 0, stream>>>(slab.seq);
@@ -514,13 +516,43 @@ struct Engine : plb_engine {
         } else {
             k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
         }
-        prof_end(); prof_begin(K_G2P);
+        prof_end();
+        launches++;
+    }
+    void enqueue_fwd(SlotRef si, SlotRef so, SlotRef pf) {
+        const int nb = blocks(cfg.n_particles);
+        prof_begin(K_P2G);
+        launch_p2g(si, so, 1);
+        prof_end();
+        enqueue_grid_fwd_stage(si, pf);
+        prof_begin(K_G2P);
         k_g2p<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, grid_out);
         prof_end();
-        launches += 3;
+        launches += 2;
     }
-    // One backward substep; `restore` = the forward grid of this slot is in the store.
-    void enqueue_bwd(SlotRef si, SlotRef pf, bool restore, T* a_next, T* a_cur) {
+    // n >= 2 forward substeps with G2P(i-1) and P2G(i) fused into one particle kernel (refs are cursor-relative or absolute)
+    void enqueue_fwd_fused(int n, SlotRef (*mk)(const Engine*, int, int)) {
+        const int nb = blocks(cfg.n_particles);
+        unsigned char* fl = sparse ? d_flags : nullptr;
+        prof_begin(K_P2G);
+        launch_p2g(mk(this, 0, 0), mk(this, 1, 0), 1);
+        prof_end();
+        enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0));
+        for (int i = 1; i < n; i++) {
+            prof_begin(K_P2G);
+            k_g2p_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(),
+                                                                 grid_out, grid_in, fl, flush_variant);
+            prof_end();
+            enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i));
+            launches++;
+        }
+        prof_begin(K_G2P);
+        k_g2p<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, mk(this, 0, n - 1), mk(this, 1, n - 1), grid_out);
+        prof_end();
+        launches += 2;
+    }
+    // backward stages of one substep
+    void enqueue_bwd_grid_pre(SlotRef si, SlotRef pf, bool restore) {       // forward grid of the substep + grid_out
         const int nb = blocks(cfg.n_particles), ng = blocks(n_nodes);
         GridStore<T> nostore{nullptr, nullptr, nullptr, nullptr, 0};
         prof_begin(K_P2G_RECOMPUTE);
@@ -535,12 +567,13 @@ struct Engine : plb_engine {
             k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, d_list, d_nactive, nostore, si);
         else
             k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
-        prof_end(); prof_begin(K_G2P_BWD);
-        if (tile_scatter)
-            k_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out, flush_variant);
-        else
-            k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
-        prof_end(); prof_begin(K_GRID_BWD);
+        prof_end();
+        launches += 2;
+        (void)nb;
+    }
+    void enqueue_bwd_grid_adj(SlotRef pf) {                                  // (halo of g_out) + grid_op.grad
+        const int ng = blocks(n_nodes);
+        prof_begin(K_GRID_BWD);
         if (slab.peer_ready) {
             k_halo_next_seq<<<1, 1, 0, stream>>>(slab.seq);
             halo_exchange(g_out);
@@ -551,10 +584,49 @@ struct Engine : plb_engine {
             k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive, own_lo(), own_hi());
         else
             k_grid_bwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, n_nodes);
-        prof_end(); prof_begin(K_P2G_BWD);
-        k_p2g_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in);
         prof_end();
-        launches += 5;
+        launches++;
+    }
+    void launch_g2p_bwd(SlotRef si, T* a_next, T* a_cur) {
+        const int nb = blocks(cfg.n_particles);
+        prof_begin(K_G2P_BWD);
+        if (tile_scatter)
+            k_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out, flush_variant);
+        else
+            k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
+        prof_end();
+        launches++;
+    }
+    void launch_p2g_bwd(SlotRef si, T* a_next, T* a_cur) {
+        prof_begin(K_P2G_BWD);
+        k_p2g_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in);
+        prof_end();
+        launches++;
+    }
+    // One backward substep; `restore` = the forward grid of this slot is in the store.
+    void enqueue_bwd(SlotRef si, SlotRef pf, bool restore, T* a_next, T* a_cur) {
+        enqueue_bwd_grid_pre(si, pf, restore);
+        launch_g2p_bwd(si, a_next, a_cur);
+        enqueue_bwd_grid_adj(pf);
+        launch_p2g_bwd(si, a_next, a_cur);
+    }
+    // n >= 2 backward substeps (i = n-1 .. 0) with p2g.grad(i) and g2p.grad(i-1) fused; c = adjoint ping-pong parity at entry
+    void enqueue_bwd_fused(int n, bool restore, int c, SlotRef (*mk)(const Engine*, int, int)) {
+        const int nb = blocks(cfg.n_particles);
+        enqueue_bwd_grid_pre(mk(this, 0, n - 1), mk(this, 2, n - 1), restore);
+        launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1]);
+        enqueue_bwd_grid_adj(mk(this, 2, n - 1));
+        for (int i = n - 1; i >= 1; i--) {
+            enqueue_bwd_grid_pre(mk(this, 0, i - 1), mk(this, 2, i - 1), restore);
+            prof_begin(K_P2G_BWD);
+            k_p2g_bwd_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1],
+                                                                         material(), g_in, grid_out, g_out, flush_variant);
+            prof_end();
+            launches++;
+            c ^= 1;
+            enqueue_bwd_grid_adj(mk(this, 2, i - 1));
+        }
+        launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1]);
     }
     // push my listed zone blocks of `grid` into the neighbours' inboxes, publish, wait for theirs
     void halo_exchange(const Vec4<T>* grid) {
@@ -581,6 +653,8 @@ struct Engine : plb_engine {
         else
             k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
     }
+    // (which: 0 slot_in base, 1 slot_out base, 2 pose frame base; rel) -> cursor-relative reference
+    static SlotRef mk_cursor(const Engine* e, int which, int rel) { SlotRef r; r.cur = e->d_cursor; r.idx = which; r.rel = rel; return r; }
     static SlotRef abs_ref(int v) { SlotRef r; r.cur = nullptr; r.idx = 0; r.rel = v; return r; }
     SlotRef cur_ref(int idx, int rel) const { SlotRef r; r.cur = d_cursor; r.idx = idx; r.rel = rel; return r; }
 
@@ -611,11 +685,14 @@ struct Engine : plb_engine {
             cudaGraph_t g = nullptr;
             long long l0 = launches;
             PLB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            const bool fused = fuse && tile_scatter && sparse && !plane_tile && key.n >= 2;
             if (key.dir == 0) {
-                for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
+                if (fused) enqueue_fwd_fused(key.n, &Engine::mk_cursor);
+                else for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
             } else {
                 int c = key.parity;
-                for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), key.stored != 0, adj[c], adj[c ^ 1]); c ^= 1; }
+                if (fused) enqueue_bwd_fused(key.n, key.stored != 0, c, &Engine::mk_cursor);
+                else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), key.stored != 0, adj[c], adj[c ^ 1]); c ^= 1; }
             }
             cudaError_t ce = cudaStreamEndCapture(stream, &g);
             launches = l0;

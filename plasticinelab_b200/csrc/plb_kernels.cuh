@@ -628,6 +628,59 @@ __global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_tile(SimCon
     warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, g_out, flush_variant);
 }
 
+// ---- fused particle kernels (see g2p_p2g_body / p2g_bwd_g2p_bwd_body) -------------------------------------------------------
+// Every lane runs the math (lanes past the end redo the last particle, store nothing, and zero their tile column) because
+// the tile flush is warp-collective.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_g2p_p2g_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_mid,
+                                                         SlotRef slot_out, Material<T> mat, const Vec4<T>* grid_out, Vec4<T>* grid_in,
+                                                         unsigned char* flags, int flush_variant) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    int b[3] = {0, 0, 0};
+    if (valid) {
+        FramePtr<T> fmid = frame_at(frames, slot_mid.get(), n_pad);
+        WarpTileScatter<T> sc{tile, lane};
+        g2p_p2g_body<T, WarpTileScatter<T>>(p, P, frame_at(frames, slot_in.get(), n_pad), fmid, frame_at(frames, slot_out.get(), n_pad), true,
+                                            mat, grid_out, sc);
+        V3<T> x = load_x(fmid, p);                       // the advected position this thread just stored
+#pragma unroll
+        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+        if (flags) mark_blocks<T>(P, x, flags);
+    } else {
+        tile_zero_column(tile, lane);
+    }
+    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, grid_in, flush_variant);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_p2g_bwd_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
+                                                                                   SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
+                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out,
+                                                                                   int flush_variant) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    int b[3] = {0, 0, 0};
+    if (valid) {
+        FramePtr<T> fprev = frame_at(frames, slot_prev.get(), n_pad);
+        WarpTileScatter<T> sc{tile, lane};
+        p2g_bwd_g2p_bwd_body<T, WarpTileScatter<T>>(p, P, frame_at(frames, slot_s.get(), n_pad), fprev, frame_at(adj_next, 0, n_pad),
+                                                    frame_at(adj_cur, 0, n_pad), true, mat, g_in, grid_out, sc);
+        V3<T> x = load_x(fprev, p);
+#pragma unroll
+        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    } else {
+        tile_zero_column(tile, lane);
+    }
+    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, g_out, flush_variant);
+}
+
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_grid_bwd(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pfr,
                                                      Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, int clear,
