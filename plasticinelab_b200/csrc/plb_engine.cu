@@ -163,6 +163,7 @@ struct Engine : plb_engine {
     struct GraphKey { int dir, n, parity, stored; bool operator<(const GraphKey& o) const {
         return std::tie(dir, n, parity, stored) < std::tie(o.dir, o.n, o.parity, o.stored); } };
     std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<GraphKey, long long> graph_nodes;
     // slab decomposition (multi-GPU): owned planes [own_lo, own_hi), zones of +-halo_w planes around the boundaries
     struct Slab { bool on = false; int own_lo = 0, own_hi = 0, w = 0; bool has[2] = {false, false}; int zlo[2] = {0, 0}, zhi[2] = {0, 0};
                   void* recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -695,6 +696,7 @@ struct Engine : plb_engine {
                 else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), key.stored != 0, adj[c], adj[c ^ 1]); c ^= 1; }
             }
             cudaError_t ce = cudaStreamEndCapture(stream, &g);
+            graph_nodes[key] = launches - l0;
             launches = l0;
             if (ce != cudaSuccess) { err = std::string("graph capture: ") + cudaGetErrorString(ce); return PLB_ERR_CUDA; }
             cudaGraphExec_t ge = nullptr;
@@ -704,7 +706,8 @@ struct Engine : plb_engine {
         }
         k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
         PLB_CUDA(cudaGraphLaunch(it->second, stream));
-        launches += (key.dir == 0 ? 4 : (key.stored ? 6 : 7)) * (long long)key.n + 1;
+        // kernels + memset nodes inside the replayed graph (the capture counted them once into graph_nodes[key])
+        launches += graph_nodes[key] + 1;
         return PLB_OK;
     }
     int step_fwd(int slot0, int pf0, int n) override {
