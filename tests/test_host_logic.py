@@ -107,3 +107,11 @@ def test_optimizers_match_reference_update_rule():
     assert np.allclose(m.step(g), -0.1 * 0.1 * g)
     big = Adam(np.full((1, 1), 0.95), None, lr=0.1)
     assert big.step(np.array([[-1.0]]))[0, 0] == 1.0            # clipped to the bounds
+
+
+def test_taichi_shim_exposes_tape():
+    import plasticinelab_b200.ti_shim as shim
+    from plasticinelab_b200.engine.tape import Tape
+    mod = shim.install()
+    import taichi as ti
+    assert ti is mod and ti.Tape is Tape and ti.init(arch=ti.gpu) is None
