@@ -337,7 +337,8 @@ def main():
     A = env.primitives.action_dim
     actions = actions_for(w, A)
     pinned_actions = torch.from_numpy(actions).pin_memory()
-    host_state = env.get_state()["state"]
+    # e2e inputs live in pinned host memory (particle state as float64 like the reference's get_state(), actions)
+    host_state = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in env.get_state()["state"]]
     solver = Solver(env, None, None, n_iters=1, softness=666.0, horizon=H)
     solver.total_steps = 0
     grad_out = np.zeros((H, max(A, 1)))
