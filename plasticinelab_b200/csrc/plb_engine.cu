@@ -172,6 +172,7 @@ struct Engine : plb_engine {
                   int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; bool peer_ready = false; } slab;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     size_t tile_smem = 0;
+    bool combine = false;           // pair/quad pre-combining tile policy (PLB_TILE_COMBINE=1)
     bool fuse = true;               // fused G2P+P2G / P2G.grad+G2P.grad particle kernels inside env-step graphs (PLB_FUSE=0 disables)
     bool plane_tile = false;        // one-plane (9-node) tile for P2G: 1/3 shared memory, PLB_P2G_PLANE=1
     size_t plane_smem = 0;
@@ -261,7 +262,12 @@ struct Engine : plb_engine {
         plane_smem = (size_t)(kBlock / 32) * kPlaneVec4 * sizeof(Vec4<T>);
         tile_smem = (size_t)(kBlock / 32) * kTileVec4 * sizeof(Vec4<T>);
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
+        if (const char* cv = getenv("PLB_TILE_COMBINE")) combine = atoi(cv) != 0;
         if (tile_scatter) {
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_comb<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_comb<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_comb<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_comb<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
             PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
             PLB_CUDA(cudaFuncSetAttribute(k_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
@@ -541,8 +547,12 @@ struct Engine : plb_engine {
         enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0));
         for (int i = 1; i < n; i++) {
             prof_begin(K_P2G);
-            k_g2p_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(),
-                                                                 grid_out, grid_in, fl, flush_variant);
+            if (combine)
+                k_g2p_p2g_comb<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(),
+                                                                     grid_out, grid_in, fl);
+            else
+                k_g2p_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(),
+                                                                     grid_out, grid_in, fl, flush_variant);
             prof_end();
             enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i));
             launches++;
@@ -591,7 +601,9 @@ struct Engine : plb_engine {
     void launch_g2p_bwd(SlotRef si, T* a_next, T* a_cur) {
         const int nb = blocks(cfg.n_particles);
         prof_begin(K_G2P_BWD);
-        if (tile_scatter)
+        if (tile_scatter && combine)
+            k_g2p_bwd_comb<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
+        else if (tile_scatter)
             k_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out, flush_variant);
         else
             k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
@@ -620,8 +632,12 @@ struct Engine : plb_engine {
         for (int i = n - 1; i >= 1; i--) {
             enqueue_bwd_grid_pre(mk(this, 0, i - 1), mk(this, 2, i - 1), restore);
             prof_begin(K_P2G_BWD);
-            k_p2g_bwd_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1],
-                                                                         material(), g_in, grid_out, g_out, flush_variant);
+            if (combine)
+                k_p2g_bwd_g2p_bwd_comb<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1],
+                                                                             material(), g_in, grid_out, g_out);
+            else
+                k_p2g_bwd_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1],
+                                                                             material(), g_in, grid_out, g_out, flush_variant);
             prof_end();
             launches++;
             c ^= 1;
@@ -647,7 +663,9 @@ struct Engine : plb_engine {
     void launch_p2g(SlotRef si, SlotRef so, int store_F) {
         const int nb = blocks(cfg.n_particles);
         unsigned char* fl = sparse ? d_flags : nullptr;
-        if (tile_scatter && plane_tile)
+        if (tile_scatter && combine)
+            k_p2g_comb<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+        else if (tile_scatter && plane_tile)
             k_p2g_plane<T><<<nb, kBlock, plane_smem, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
         else if (tile_scatter)
             k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_variant);

@@ -168,6 +168,38 @@ template <class T> struct WarpPlaneScatter {
         __syncwarp();
     }
 };
+// Pre-combining policy: before a contribution is parked in the tile, lanes that sit in the same cell as their xor-1
+// partner (and, second level, as their whole quad) add their values with shuffles; only the first lane of such a pair / quad
+// writes a column and takes part in the flush.  The flush -- a serial LDS -> FADD walk over the member columns, >50 % of the
+// stall samples of k_p2g_tile in the ncu source view -- then visits a half / a quarter of the columns.  All 32 lanes must
+// call add() (the shuffles are warp-collective), so the kernels run the particle math on every lane (lanes past the end
+// redo the last particle with key = -1).
+template <class T> struct WarpCombineScatter {
+    Vec4<T>* tile;
+    int lane;
+    bool comb1, comb2, writer;
+    __device__ __forceinline__ void setup(int key) {
+        const unsigned full = 0xffffffffu;
+        const int k1 = __shfl_xor_sync(full, key, 1);
+        comb1 = key >= 0 && k1 == key;
+        const bool pair_ok = comb1;
+        const bool other_pair_ok = __shfl_xor_sync(full, (int)pair_ok, 2) != 0;
+        const int k2 = __shfl_xor_sync(full, key, 2);
+        comb2 = pair_ok && other_pair_ok && k2 == key;
+        writer = comb2 ? (lane & 3) == 0 : (comb1 ? (lane & 1) == 0 : true);
+    }
+    __device__ __forceinline__ void add(int slot, int, int, int, Vec4<T> v) const {
+        const unsigned full = 0xffffffffu;
+        Vec4<T> o;
+        o.x = __shfl_xor_sync(full, v.x, 1); o.y = __shfl_xor_sync(full, v.y, 1); o.z = __shfl_xor_sync(full, v.z, 1); o.w = __shfl_xor_sync(full, v.w, 1);
+        if (comb1) { v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        o.x = __shfl_xor_sync(full, v.x, 2); o.y = __shfl_xor_sync(full, v.y, 2); o.z = __shfl_xor_sync(full, v.z, 2); o.w = __shfl_xor_sync(full, v.w, 2);
+        if (comb2) { v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        if (writer) tile[slot * kTileStride + lane] = v;
+    }
+    __device__ __forceinline__ void end_plane(int) const {}
+};
+
 // payload helpers: the tile carries Vec4 (momentum+mass, velocity adjoint) or a scalar (loss mass)
 template <class T> __device__ __forceinline__ void pay_zero(Vec4<T>& a) { a = mk4<T>(T(0), T(0), T(0), T(0)); }
 template <class T> __device__ __forceinline__ void pay_acc(Vec4<T>& a, const Vec4<T>& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
@@ -499,6 +531,119 @@ __global__ void __launch_bounds__(kBlock) k_p2g_plane(SimConst<T> P, T* frames, 
     sc.key = valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1;
     p2g_body<T, WarpPlaneScatter<T>>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0 && valid, mat, sc);
     if (flags && valid) mark_blocks<T>(P, x, flags);
+}
+
+// P2G / fused kernels with the pre-combining tile policy
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_p2g_comb(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
+                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    if (!valid) p = P.n_particles - 1;
+    FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
+    V3<T> x = load_x(fin, p);
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    WarpCombineScatter<T> sc;
+    sc.tile = tile; sc.lane = lane;
+    sc.setup(valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1);
+    p2g_body<T, WarpCombineScatter<T>>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0 && valid, mat, sc);
+    if (flags && valid) mark_blocks<T>(P, x, flags);
+    warp_tile_flush_groups<T, Vec4<T>>(tile, lane, valid && sc.writer, b, P.n_grid, grid_in);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_g2p_p2g_comb(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_mid,
+                                                         SlotRef slot_out, Material<T> mat, const Vec4<T>* grid_out, Vec4<T>* grid_in,
+                                                         unsigned char* flags) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    if (!valid) p = P.n_particles - 1;
+    // G2P of substep s (registers), then P2G of substep s+1 with the combine policy keyed on the ADVECTED position
+    V3<T> nx, nv; M3<T> nC;
+    g2p_core<T>(P, load_x(frame_at(frames, slot_in.get(), n_pad), p), grid_out, nx, nv, nC);
+    FramePtr<T> fmid = frame_at(frames, slot_mid.get(), n_pad);
+    if (valid) store_xvC(fmid, p, nx, nv, nC);
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) b[d] = (int)(nx[d] * P.inv_dx - T(0.5));
+    WarpCombineScatter<T> sc;
+    sc.tile = tile; sc.lane = lane;
+    sc.setup(valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1);
+    M3<T> F = load_F(fmid, p);
+    T mu, lam, ys;
+    load_material(P, mat, p, mu, lam, ys);
+    M3<T> new_F;
+    p2g_core<T, WarpCombineScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
+    if (valid) {
+        store_F(frame_at(frames, slot_out.get(), n_pad), p, new_F);
+        if (flags) mark_blocks<T>(P, nx, flags);
+    }
+    warp_tile_flush_groups<T, Vec4<T>>(tile, lane, valid && sc.writer, b, P.n_grid, grid_in);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_comb(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
+                                                                           T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    if (!valid) p = P.n_particles - 1;
+    FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
+    V3<T> x = load_x(fin, p);
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    WarpCombineScatter<T> sc;
+    sc.tile = tile; sc.lane = lane;
+    sc.setup(valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1);
+    V3<T> gxn, gvn; M3<T> gCn;
+    load_xvC(frame_at(adj_next, 0, n_pad), p, gxn, gvn, gCn);
+    V3<T> gx = g2p_bwd_core<T, WarpCombineScatter<T>>(P, x, gxn, gvn, gCn, grid_out, sc);
+    if (valid) frame_at(adj_cur, 0, n_pad).A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
+    warp_tile_flush_groups<T, Vec4<T>>(tile, lane, valid && sc.writer, b, P.n_grid, g_out);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_p2g_bwd_g2p_bwd_comb(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
+                                                                                   SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
+                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < P.n_particles;
+    if (!valid) p = P.n_particles - 1;
+    FramePtr<T> fs = frame_at(frames, slot_s.get(), n_pad), fprev = frame_at(frames, slot_prev.get(), n_pad);
+    FramePtr<T> next = frame_at(adj_next, 0, n_pad), cur = frame_at(adj_cur, 0, n_pad);
+    V3<T> x, v; M3<T> C;
+    load_xvC(fs, p, x, v, C);
+    M3<T> F = load_F(fs, p);
+    T mu, lam, ys;
+    load_material(P, mat, p, mu, lam, ys);
+    Vec4<T> part = cur.A0[p];
+    V3<T> gx, gv; M3<T> gC, gF;
+    p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
+    if (valid) store_F(cur, p, gF);
+    V3<T> xp = load_x(fprev, p);
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) b[d] = (int)(xp[d] * P.inv_dx - T(0.5));
+    WarpCombineScatter<T> sc;
+    sc.tile = tile; sc.lane = lane;
+    sc.setup(valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1);
+    V3<T> gxp = g2p_bwd_core<T, WarpCombineScatter<T>>(P, xp, gx, gv, gC, grid_out, sc);
+    if (valid) next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
+    warp_tile_flush_groups<T, Vec4<T>>(tile, lane, valid && sc.writer, b, P.n_grid, g_out);
 }
 
 template <class T>
