@@ -11,6 +11,9 @@
 // grid_out = (velocity xyz, 0) and likewise for their adjoints, linear index (i * n + j) * n + k.
 #pragma once
 #include "plb_grid.cuh"
+#if defined(PLB_WARP_EMUL) && !defined(__CUDACC__)
+#include <mutex>          // host warp emulation (tests/host/warp_emul.cpp): 32 threads per warp scatter concurrently
+#endif
 
 namespace plb {
 
@@ -78,6 +81,13 @@ PLB_D void scatter_add4(Vec4<double>* addr, Vec4<double> v) {
 }
 PLB_D void scatter_add1(float* addr, float v) { atomicAdd(addr, v); }
 PLB_D void scatter_add1(double* addr, double v) { atomicAdd(addr, v); }
+#elif defined(PLB_WARP_EMUL)
+inline std::mutex& emul_scatter_mutex() { static std::mutex m; return m; }
+template <class T> inline void scatter_add4(Vec4<T>* addr, Vec4<T> v) {
+    std::lock_guard<std::mutex> lock(emul_scatter_mutex());
+    addr->x += v.x; addr->y += v.y; addr->z += v.z; addr->w += v.w;
+}
+template <class T> inline void scatter_add1(T* addr, T v) { std::lock_guard<std::mutex> lock(emul_scatter_mutex()); *addr += v; }
 #else
 template <class T> inline void scatter_add4(Vec4<T>* addr, Vec4<T> v) { addr->x += v.x; addr->y += v.y; addr->z += v.z; addr->w += v.w; }
 template <class T> inline void scatter_add1(T* addr, T v) { *addr += v; }
@@ -210,45 +220,39 @@ PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const F
     store_xvC(out, p, nx, nv, nC);
 }
 
-// fused forward kernel body: G2P of substep s (frame `in` -> frame `mid`), then P2G of substep s+1 straight from registers
-// (F[s+1] was written by the previous P2G; F[s+2] goes to frame `out`).  Saves one pass over x,v,C and one launch.
-template <class T, class Sc>
-PLB_HD void g2p_p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& mid, const FramePtr<T>& out, bool store,
-                         const Material<T>& mat, const Vec4<T>* grid_out, const Sc& sc) {
-    V3<T> nx, nv; M3<T> nC;
-    g2p_core<T>(P, load_x(in, p), grid_out, nx, nv, nC);
-    if (store) store_xvC(mid, p, nx, nv, nC);
-    M3<T> F = load_F(mid, p);
-    T mu, lam, ys;
-    load_material(P, mat, p, mu, lam, ys);
-    M3<T> new_F;
-    p2g_core<T, Sc>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
-    if (store) store_F(out, p, new_F);
-}
-
 // ================================================================================================
 // backward substep (after P2G + grid_fwd were recomputed for frame f)
 // ================================================================================================
 // g2p.grad: reads adjoint of (x,v,C)[f+1], scatters the adjoint of grid_out, writes the partial x-adjoint of frame f
 // into adj_cur.A0 (xyz lanes; the w lane is finished by p2g_bwd_body).
-template <class T, class Sc>
-PLB_HD V3<T> g2p_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> gxn, V3<T> gvn, const M3<T>& gCn, const Vec4<T>* grid_out, const Sc& sc) {
+// kStoredNext: (xn, nv) = the position / velocity G2P stored for the next frame.  nv IS the gather sum (g2p stores it
+// unchanged) and the clamp masks of the advection can be read off the stored position (0 < x' < x_hi <=> both clamps pass),
+// so the first 27-node gather is skipped.  Otherwise (no forward result at hand) the sum is recomputed from grid_out.
+template <class T, class Sc, bool kStoredNext = false>
+PLB_HD V3<T> g2p_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> gxn, V3<T> gvn, const M3<T>& gCn, const Vec4<T>* grid_out, const Sc& sc,
+                          V3<T> xn = V3<T>(), V3<T> nv_stored = V3<T>()) {
     Stencil<T> st = make_stencil(x, P.inv_dx);
-    // recompute new_v = sum w g (clamp masks of the advection; it is also the sum the dpos adjoint needs)
-    V3<T> nv = zero3<T>();
+    V3<T> nv, gy;
+    if (kStoredNext) {
+        nv = nv_stored;
+        gy = advect_backward_stored(P, xn, gxn);
+    } else {
+        // recompute new_v = sum w g (clamp masks of the advection; it is also the sum the dpos adjoint needs)
+        nv = zero3<T>();
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+        for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            V3<T> t0 = zero3<T>();
+            for (int j = 0; j < 3; j++) {
+                V3<T> t0 = zero3<T>();
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                Vec4<T> g4 = grid_out[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
-                t0 += st.w[k][2] * mk3<T>(g4.x, g4.y, g4.z);
+                for (int k = 0; k < 3; k++) {
+                    Vec4<T> g4 = grid_out[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
+                    t0 += st.w[k][2] * mk3<T>(g4.x, g4.y, g4.z);
+                }
+                nv += (st.w[i][0] * st.w[j][1]) * t0;
             }
-            nv += (st.w[i][0] * st.w[j][1]) * t0;
-        }
-    V3<T> gy = advect_backward(P, x, nv, gxn);
+        gy = advect_backward(P, x, nv, gxn);
+    }
     V3<T> gx = gy;
     V3<T> gv = gvn + P.dt * gy;
     T gw[3][3];
@@ -285,24 +289,32 @@ PLB_HD V3<T> g2p_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> gxn, V3<T> gvn, c
             gw[i][0] += tij * st.w[j][1];
             gw[j][1] += tij * st.w[i][0];
         }
+        sc.end_plane(i);
     }
     gfx = (-c4) * mTv(gCn, nv);
     gx += stencil_backward(st, gw, gfx, P.inv_dx);
     return gx;
 }
+// fnext: the frame G2P produced from `in` (null: not available, recompute the gather sum)
 template <class T, class Sc>
 PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
-                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, const Sc& sc) {
+                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, const Sc& sc, const FramePtr<T>* fnext = nullptr) {
     V3<T> gxn, gvn; M3<T> gCn;
     load_xvC(adj_next, p, gxn, gvn, gCn);
-    V3<T> gx = g2p_bwd_core<T, Sc>(P, load_x(in, p), gxn, gvn, gCn, grid_out, sc);
+    V3<T> gx;
+    if (fnext) {
+        Vec4<T> q0 = fnext->A0[p], q1 = fnext->A1[p];
+        gx = g2p_bwd_core<T, Sc, true>(P, load_x(in, p), gxn, gvn, gCn, grid_out, sc, mk3<T>(q0.x, q0.y, q0.z), mk3<T>(q0.w, q1.x, q1.y));
+    } else {
+        gx = g2p_bwd_core<T, Sc, false>(P, load_x(in, p), gxn, gvn, gCn, grid_out, sc);
+    }
     adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
 }
 template <class T>
 PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
-                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+                         const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, const FramePtr<T>* fnext = nullptr) {
     DirectScatter<T> sc{g_out, P.n_grid};
-    g2p_bwd_body<T, DirectScatter<T>>(p, P, in, adj_next, adj_cur, grid_out, sc);
+    g2p_bwd_body<T, DirectScatter<T>>(p, P, in, adj_next, adj_cur, grid_out, sc, fnext);
 }
 
 // grid_op.grad for one node.  Reads grid_in (forward values) and g_out (adjoint of grid_out); writes g_in (adjoint of
@@ -398,27 +410,6 @@ PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
     p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(adj_next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
     store_xvC(adj_cur, p, gx, gv, gC);
     store_F(adj_cur, p, gF);
-}
-
-// fused backward kernel body: p2g.grad of substep s (frame `in_s`), then g2p.grad of substep s-1 (frame `in_prev`) with the
-// adjoint of (x,v,C)[s] kept in registers.  Buffers: `next` holds dF[s+1] in its F planes, `cur.A0` holds the partial
-// x-adjoint of frame s; written: `cur` F planes <- dF[s], `next.A0` <- partial x-adjoint of frame s-1 (after the caller's
-// ping-pong swap these are exactly what the following fused / final p2g_bwd_body call reads).
-template <class T, class Sc>
-PLB_HD void p2g_bwd_g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in_s, const FramePtr<T>& in_prev, const FramePtr<T>& next,
-                                 const FramePtr<T>& cur, bool store, const Material<T>& mat, const Vec4<T>* g_in, const Vec4<T>* grid_out,
-                                 const Sc& sc) {
-    V3<T> x, v; M3<T> C;
-    load_xvC(in_s, p, x, v, C);
-    M3<T> F = load_F(in_s, p);
-    T mu, lam, ys;
-    load_material(P, mat, p, mu, lam, ys);
-    Vec4<T> part = cur.A0[p];
-    V3<T> gx, gv; M3<T> gC, gF;
-    p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
-    if (store) store_F(cur, p, gF);
-    V3<T> gxp = g2p_bwd_core<T, Sc>(P, load_x(in_prev, p), gx, gv, gC, grid_out, sc);
-    if (store) next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
 }
 
 // ================================================================================================

@@ -124,6 +124,10 @@ struct plb_engine {
     long long launches = 0;
 };
 
+// __launch_bounds__ min-blocks instantiated for the fused particle kernels (float: two register caps each; double: one)
+template <class T> struct OccSel { static constexpr int fwd_lo = 1, fwd_hi = 1, bwd_lo = 1, bwd_hi = 1; };
+template <> struct OccSel<float> { static constexpr int fwd_lo = 5, fwd_hi = 6, bwd_lo = 3, bwd_hi = 4; };
+
 template <class T>
 struct Engine : plb_engine {
     plb_config cfg{};
@@ -171,12 +175,24 @@ struct Engine : plb_engine {
                   char* inbox[2] = {nullptr, nullptr}; char* peer[2] = {nullptr, nullptr}; HaloGeom geom[2]; size_t inbox_bytes = 0;
                   int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; bool peer_ready = false; } slab;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
-    size_t tile_smem = 0;
-    bool combine = false;           // pair/quad pre-combining tile policy (PLB_TILE_COMBINE=1)
     bool fuse = true;               // fused G2P+P2G / P2G.grad+G2P.grad particle kernels inside env-step graphs (PLB_FUSE=0 disables)
-    bool plane_tile = false;        // one-plane (9-node) tile for P2G: 1/3 shared memory, PLB_P2G_PLANE=1
-    size_t plane_smem = 0;
-    int flush_variant = 0;      // 0 = per-cell groups (measured faster), 1 = chunked runs (PLB_FLUSH overrides)
+    bool fwd_plane = false;         // plane (9-node) tile in the forward scatter kernels: 1/3 shared memory (PLB_FWD_PLANE)
+    bool bwd_plane = false;         // same for the backward scatter kernels (PLB_BWD_PLANE)
+    int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
+    int fwd_minb = 5, bwd_minb = 3; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 / PLB_BWD_MINB=4 select the tighter cap)
+    bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
+                                    // particle kernel and grid adjoint of substep s (needs the second grid set; PLB_BWD_OVERLAP=0 disables)
+    // grid set: forward grid (momentum+mass), grid operator output, active-block list.  Set 0 is the working set of the
+    // forward pass; the backward pass alternates between the two sets by substep parity when bwd_overlap is on.
+    struct GridSet { Vec4<T>* in; Vec4<T>* out; int* list; int* count; };
+    GridSet sets[2] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    cudaStream_t side_stream = nullptr;
+    std::vector<cudaEvent_t> cap_events; size_t cap_ev_used = 0;
+    cudaEvent_t next_event() {
+        if (cap_ev_used == cap_events.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); cap_events.push_back(e); }
+        return cap_events[cap_ev_used++];
+    }
+    std::vector<char> fwd_ok;       // host view: slot s+1 holds the frame the forward substep produced from slot s
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
     int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
     int* d_vals = nullptr; int* d_vals2 = nullptr; void* d_cub = nullptr; size_t cub_bytes = 0; T* frame_tmp = nullptr;
@@ -199,10 +215,14 @@ struct Engine : plb_engine {
         cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_cub); cudaFree(frame_tmp);
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt); cudaFree(store.overflow); cudaFree(d_cursor);
+        cudaFree(sets[1].in); cudaFree(sets[1].out); cudaFree(sets[1].list); cudaFree(sets[1].count);
+        for (cudaEvent_t e : cap_events) cudaEventDestroy(e);
+        if (side_stream) cudaStreamDestroy(side_stream);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 
     int blocks(long long n, int b = kBlock) const { return (int)((n + b - 1) / b); }
+    static size_t tile_smem_bytes(bool plane, int threads) { return (size_t)(threads / 32) * (plane ? kPlaneVec4 : kTileVec4) * sizeof(Vec4<T>); }
     Material<T> material() const { Material<T> m; m.mu = mat_mu; m.lam = mat_lam; m.ys = mat_ys; return m; }
     T* frame_base(int slot) const { return frames + (long long)slot * 24 * n_pad; }
 
@@ -257,21 +277,21 @@ struct Engine : plb_engine {
         PLB_REQUIRE(c.n_grid % 4 == 0, "n_grid must be a multiple of 4");
         sparse = c.kernel_variant != 1;
         tile_scatter = c.kernel_variant == 0;
-        if (const char* fv = getenv("PLB_FLUSH")) flush_variant = atoi(fv);
-        if (const char* pv = getenv("PLB_P2G_PLANE")) plane_tile = atoi(pv) != 0;
-        plane_smem = (size_t)(kBlock / 32) * kPlaneVec4 * sizeof(Vec4<T>);
-        tile_smem = (size_t)(kBlock / 32) * kTileVec4 * sizeof(Vec4<T>);
+        if (const char* v = getenv("PLB_FWD_PLANE")) fwd_plane = atoi(v) != 0;
+        if (const char* v = getenv("PLB_BWD_PLANE")) bwd_plane = atoi(v) != 0;
+        if (const char* v = getenv("PLB_CTA")) cta = atoi(v) == 64 ? 64 : kBlock;
+        if (const char* v = getenv("PLB_FWD_MINB")) fwd_minb = atoi(v);
+        if (const char* v = getenv("PLB_BWD_MINB")) bwd_minb = atoi(v);
+        if (const char* v = getenv("PLB_BWD_OVERLAP")) bwd_overlap = atoi(v) != 0;
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
-        if (const char* cv = getenv("PLB_TILE_COMBINE")) combine = atoi(cv) != 0;
         if (tile_scatter) {
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_comb<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_comb<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_comb<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_comb<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+            const int full = (int)tile_smem_bytes(false, kBlock);
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_warp<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
         }
         n_blocks = (c.n_grid / 4) * (c.n_grid / 4) * (c.n_grid / 4);
         PLB_CUDA(cudaMalloc(&d_flags, n_blocks));
@@ -282,11 +302,23 @@ struct Engine : plb_engine {
         // a blocking (non-legacy) stream: graph capture is not allowed on the legacy default stream, and a blocking
         // stream still orders with work the caller issues on the default stream (torch events, copies)
         PLB_CUDA(cudaStreamCreate(&own_stream));
+        PLB_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
         stream = own_stream; prof_stream = own_stream;
+        sets[0] = GridSet{grid_in, grid_out, d_list, d_nactive};
+        if (bwd_overlap && tile_scatter && sparse) {
+            PLB_CUDA(cudaMalloc(&sets[1].in, gbytes));  PLB_CUDA(cudaMemset(sets[1].in, 0, gbytes));
+            PLB_CUDA(cudaMalloc(&sets[1].out, gbytes)); PLB_CUDA(cudaMemset(sets[1].out, 0, gbytes));
+            PLB_CUDA(cudaMalloc(&sets[1].list, n_blocks * sizeof(int)));
+            PLB_CUDA(cudaMalloc(&sets[1].count, sizeof(int)));
+            PLB_CUDA(cudaMemset(sets[1].count, 0, sizeof(int)));
+        } else {
+            bwd_overlap = false;
+        }
         use_graphs = c.kernel_variant == 0 && !getenv("PLB_NO_GRAPHS");
         PLB_CUDA(cudaMalloc(&d_cursor, 4 * sizeof(int)));
         PLB_CUDA(cudaMemset(d_cursor, 0, 4 * sizeof(int)));
         stored.assign(c.max_frames, 0);
+        fwd_ok.assign(c.max_frames, 0);
         PLB_CUDA(cudaMalloc(&store.overflow, sizeof(int)));
         PLB_CUDA(cudaMemset(store.overflow, 0, sizeof(int)));
         PLB_CUDA(cudaMalloc(&d_perm, n_pad * sizeof(int)));
@@ -307,6 +339,8 @@ struct Engine : plb_engine {
     }
     int synchronize() override { PLB_CUDA(cudaStreamSynchronize(stream)); return PLB_OK; }
 
+    // frame `s` was overwritten from outside a forward substep: its stored grid and the "successor frame" links are stale
+    void slot_written(int s) { stored[s] = 0; fwd_ok[s] = 0; if (s > 0) fwd_ok[s - 1] = 0; }
     int check_slot(int s) { PLB_REQUIRE(s >= 0 && s < cfg.max_frames, "frame slot out of range"); return PLB_OK; }
     int check_pf(int pf, int extra = 0) { PLB_REQUIRE(pf >= 0 && pf + extra < cfg.max_prim_frames, "primitive frame out of range"); return PLB_OK; }
 
@@ -350,7 +384,7 @@ struct Engine : plb_engine {
 
     int set_frame(int slot, const double* x, const double* v, const double* F, const double* C) override {
         if (int r = check_slot(slot)) return r;
-        stored[slot] = 0;
+        slot_written(slot);
         double *dx, *dv, *dF, *dC;
         if (int r = upload_aos(x, v, F, C, &dx, &dv, &dF, &dC)) return r;
         k_pack_frame<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, n_pad, frame_base(slot), d_perm, dx, dv, dF, dC);
@@ -366,7 +400,7 @@ struct Engine : plb_engine {
         if (int r = check_slot(src)) return r;
         if (int r = check_slot(dst)) return r;
         if (src == dst) return PLB_OK;
-        stored[dst] = 0;
+        slot_written(dst);
         PLB_CUDA(cudaMemcpyAsync(frame_base(dst), frame_base(src), (size_t)24 * n_pad * sizeof(T), cudaMemcpyDeviceToDevice, stream));
         return PLB_OK;
     }
@@ -399,6 +433,7 @@ struct Engine : plb_engine {
         launches += 3;
         PLB_CUDA(cudaGetLastError());
         std::fill(stored.begin(), stored.end(), 0);
+        std::fill(fwd_ok.begin(), fwd_ok.end(), 0);
         // size the forward-grid store from the active-block count of this frame (2x margin + 256 blocks)
         if (sparse && cfg.kernel_variant == 0) {
             k_mark_only<T><<<blocks(n), kBlock, 0, stream>>>(P, frame_base(slot), n_pad, d_flags);
@@ -545,14 +580,13 @@ struct Engine : plb_engine {
         launch_p2g(mk(this, 0, 0), mk(this, 1, 0), 1);
         prof_end();
         enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0));
+        const int nbc = blocks(cfg.n_particles, cta);
+        const size_t sm = tile_smem_bytes(fwd_plane, cta);
         for (int i = 1; i < n; i++) {
             prof_begin(K_P2G);
-            if (combine)
-                k_g2p_p2g_comb<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(),
-                                                                     grid_out, grid_in, fl);
-            else
-                k_g2p_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(),
-                                                                     grid_out, grid_in, fl, flush_variant);
+            auto kern = fwd_plane ? (fwd_minb >= 6 ? k_g2p_p2g_warp<T, true, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, true, OccSel<T>::fwd_lo>)
+                                  : (fwd_minb >= 6 ? k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>);
+            kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), grid_out, grid_in, fl);
             prof_end();
             enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i));
             launches++;
@@ -562,27 +596,26 @@ struct Engine : plb_engine {
         prof_end();
         launches += 2;
     }
-    // backward stages of one substep
-    void enqueue_bwd_grid_pre(SlotRef si, SlotRef pf, bool restore) {       // forward grid of the substep + grid_out
-        const int nb = blocks(cfg.n_particles), ng = blocks(n_nodes);
+    // backward stages of one substep, on grid set `gs`, enqueued on stream `st`
+    void enqueue_bwd_grid_pre(SlotRef si, SlotRef pf, bool restore, const GridSet& gs, cudaStream_t st) {   // forward grid of the substep + grid_out
+        const int ng = blocks(n_nodes);
         GridStore<T> nostore{nullptr, nullptr, nullptr, nullptr, 0};
         prof_begin(K_P2G_RECOMPUTE);
         if (restore) {
-            k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid_in, d_list, d_nactive, store, si);
+            k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, st>>>(cfg.n_grid, gs.in, gs.list, gs.count, store, si);
         } else {
-            launch_p2g(si, si, 0);
+            launch_p2g(si, si, 0);                      // (set 0 on the main stream: the non-stored path is never overlapped)
             if (sparse) compact_blocks();
         }
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
         if (sparse)
-            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, d_list, d_nactive, nostore, si);
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, gs.list, gs.count, nostore, si);
         else
-            k_grid_fwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 0, n_nodes);
+            k_grid_fwd<T><<<ng, kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, n_nodes);
         prof_end();
         launches += 2;
-        (void)nb;
     }
-    void enqueue_bwd_grid_adj(SlotRef pf) {                                  // (halo of g_out) + grid_op.grad
+    void enqueue_bwd_grid_adj(SlotRef pf, const GridSet& gs) {               // (halo of g_out) + grid_op.grad
         const int ng = blocks(n_nodes);
         prof_begin(K_GRID_BWD);
         if (slab.peer_ready) {
@@ -592,21 +625,22 @@ struct Engine : plb_engine {
             launches += 6;
         }
         if (sparse)
-            k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive, own_lo(), own_hi());
+            k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());
         else
-            k_grid_bwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, g_out, g_in, 1, d_prim_grad, n_nodes);
+            k_grid_bwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, n_nodes);
         prof_end();
         launches++;
     }
-    void launch_g2p_bwd(SlotRef si, T* a_next, T* a_cur) {
-        const int nb = blocks(cfg.n_particles);
+    void launch_g2p_bwd(SlotRef si, T* a_next, T* a_cur, const GridSet& gs, bool next_ok) {
         prof_begin(K_G2P_BWD);
-        if (tile_scatter && combine)
-            k_g2p_bwd_comb<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
-        else if (tile_scatter)
-            k_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out, flush_variant);
-        else
-            k_g2p_bwd<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, grid_out, g_out);
+        if (tile_scatter) {
+            const int nbc = blocks(cfg.n_particles, cta);
+            const size_t sm = tile_smem_bytes(bwd_plane, cta);
+            if (bwd_plane) k_g2p_bwd_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out);
+            else k_g2p_bwd_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out);
+        } else {
+            k_g2p_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, gs.out, g_out);
+        }
         prof_end();
         launches++;
     }
@@ -616,32 +650,69 @@ struct Engine : plb_engine {
         prof_end();
         launches++;
     }
-    // One backward substep; `restore` = the forward grid of this slot is in the store.
-    void enqueue_bwd(SlotRef si, SlotRef pf, bool restore, T* a_next, T* a_cur) {
-        enqueue_bwd_grid_pre(si, pf, restore);
-        launch_g2p_bwd(si, a_next, a_cur);
-        enqueue_bwd_grid_adj(pf);
+    void launch_bwd_fused(SlotRef s_cur, SlotRef s_prev, T* a_next, T* a_cur, const GridSet& gs) {
+        const int nbc = blocks(cfg.n_particles, cta);
+        const size_t sm = tile_smem_bytes(bwd_plane, cta);
+        prof_begin(K_P2G_BWD);
+        auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo>)
+                              : (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo>);
+        kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out);
+        prof_end();
+        launches++;
+    }
+    // One backward substep; `restore` = the forward grid of this slot is in the store; next_ok = slot si+1 holds G2P's output.
+    void enqueue_bwd(SlotRef si, SlotRef pf, bool restore, bool next_ok, T* a_next, T* a_cur) {
+        enqueue_bwd_grid_pre(si, pf, restore, sets[0], stream);
+        launch_g2p_bwd(si, a_next, a_cur, sets[0], next_ok);
+        enqueue_bwd_grid_adj(pf, sets[0]);
         launch_p2g_bwd(si, a_next, a_cur);
     }
-    // n >= 2 backward substeps (i = n-1 .. 0) with p2g.grad(i) and g2p.grad(i-1) fused; c = adjoint ping-pong parity at entry
-    void enqueue_bwd_fused(int n, bool restore, int c, SlotRef (*mk)(const Engine*, int, int)) {
-        const int nb = blocks(cfg.n_particles);
-        enqueue_bwd_grid_pre(mk(this, 0, n - 1), mk(this, 2, n - 1), restore);
-        launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1]);
-        enqueue_bwd_grid_adj(mk(this, 2, n - 1));
+    // n >= 2 backward substeps (i = n-1 .. 0) with p2g.grad(i) and g2p.grad(i-1) fused; c = adjoint ping-pong parity at entry.
+    // Inside a graph every frame i+1 was produced by the forward graph, so the fused kernel takes clamp masks / gather sums from
+    // the stored frames; `next_ok` covers the leading unfused g2p.grad of substep n-1.
+    // overlap (stream capture only): the grid pre-stage (restore + grid operator) of substep i-1 is captured on a forked branch
+    // and runs beside the particle kernel and grid adjoint of substep i; the two grid sets alternate by substep parity:
+    //   Pre(j) -> K(j) = [p2g.grad(j+1) +] g2p.grad(j) -> A(j) = grid adjoint(j) -> K(j-1);   Pre(j-2) waits for A(j) (same set).
+    void enqueue_bwd_fused(int n, bool restore, bool next_ok, int c, SlotRef (*mk)(const Engine*, int, int), bool overlap) {
+        if (!overlap) {
+            enqueue_bwd_grid_pre(mk(this, 0, n - 1), mk(this, 2, n - 1), restore, sets[0], stream);
+            launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[0], next_ok);
+            enqueue_bwd_grid_adj(mk(this, 2, n - 1), sets[0]);
+            for (int i = n - 1; i >= 1; i--) {
+                enqueue_bwd_grid_pre(mk(this, 0, i - 1), mk(this, 2, i - 1), restore, sets[0], stream);
+                launch_bwd_fused(mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1], sets[0]);
+                c ^= 1;
+                enqueue_bwd_grid_adj(mk(this, 2, i - 1), sets[0]);
+            }
+            launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1]);
+            return;
+        }
+        cap_ev_used = 0;
+        cudaEvent_t ev_fork = next_event();
+        cudaEventRecord(ev_fork, stream);
+        cudaStreamWaitEvent(side_stream, ev_fork, 0);
+        // Pre(n-1) on the main stream, Pre(n-2) on the branch (the other set, free at graph entry)
+        enqueue_bwd_grid_pre(mk(this, 0, n - 1), mk(this, 2, n - 1), true, sets[(n - 1) & 1], stream);
+        cudaEvent_t ev_pre = next_event();
+        enqueue_bwd_grid_pre(mk(this, 0, n - 2), mk(this, 2, n - 2), true, sets[(n - 2) & 1], side_stream);
+        cudaEventRecord(ev_pre, side_stream);
+        launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[(n - 1) & 1], next_ok);
+        enqueue_bwd_grid_adj(mk(this, 2, n - 1), sets[(n - 1) & 1]);
+        cudaEvent_t ev_adj = next_event();              // A(i) done, for the i of the coming iteration
+        cudaEventRecord(ev_adj, stream);
         for (int i = n - 1; i >= 1; i--) {
-            enqueue_bwd_grid_pre(mk(this, 0, i - 1), mk(this, 2, i - 1), restore);
-            prof_begin(K_P2G_BWD);
-            if (combine)
-                k_p2g_bwd_g2p_bwd_comb<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1],
-                                                                             material(), g_in, grid_out, g_out);
-            else
-                k_p2g_bwd_g2p_bwd_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1],
-                                                                             material(), g_in, grid_out, g_out, flush_variant);
-            prof_end();
-            launches++;
+            cudaStreamWaitEvent(stream, ev_pre, 0);     // Pre(i-1) done
+            if (i - 2 >= 0) {                           // Pre(i-2) re-uses the set of substep i: wait for A(i)
+                cudaStreamWaitEvent(side_stream, ev_adj, 0);
+                enqueue_bwd_grid_pre(mk(this, 0, i - 2), mk(this, 2, i - 2), true, sets[(i - 2) & 1], side_stream);
+                ev_pre = next_event();
+                cudaEventRecord(ev_pre, side_stream);
+            }
+            launch_bwd_fused(mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1], sets[(i - 1) & 1]);
             c ^= 1;
-            enqueue_bwd_grid_adj(mk(this, 2, i - 1));
+            enqueue_bwd_grid_adj(mk(this, 2, i - 1), sets[(i - 1) & 1]);
+            ev_adj = next_event();
+            cudaEventRecord(ev_adj, stream);
         }
         launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1]);
     }
@@ -661,16 +732,15 @@ struct Engine : plb_engine {
     int own_lo() const { return slab.on ? slab.own_lo : 0; }
     int own_hi() const { return slab.on ? slab.own_hi : cfg.n_grid; }
     void launch_p2g(SlotRef si, SlotRef so, int store_F) {
-        const int nb = blocks(cfg.n_particles);
         unsigned char* fl = sparse ? d_flags : nullptr;
-        if (tile_scatter && combine)
-            k_p2g_comb<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
-        else if (tile_scatter && plane_tile)
-            k_p2g_plane<T><<<nb, kBlock, plane_smem, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
-        else if (tile_scatter)
-            k_p2g_tile<T><<<nb, kBlock, tile_smem, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_variant);
-        else
-            k_p2g<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+        if (tile_scatter) {
+            const int nbc = blocks(cfg.n_particles, cta);
+            const size_t sm = tile_smem_bytes(fwd_plane, cta);
+            if (fwd_plane) k_p2g_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+            else k_p2g_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+        } else {
+            k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+        }
     }
     // (which: 0 slot_in base, 1 slot_out base, 2 pose frame base; rel) -> cursor-relative reference
     static SlotRef mk_cursor(const Engine* e, int which, int rel) { SlotRef r; r.cur = e->d_cursor; r.idx = which; r.rel = rel; return r; }
@@ -683,15 +753,16 @@ struct Engine : plb_engine {
         if (int r = check_pf(pf, 1)) return r;
         PLB_REQUIRE(si != so, "in-place substep");
         enqueue_fwd(abs_ref(si), abs_ref(so), abs_ref(pf));
+        slot_written(so);
         stored[si] = store.vals != nullptr;
-        stored[so] = 0;
+        fwd_ok[si] = (so == si + 1);
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
     }
     int substep_bwd(int si, int pf) override {
         if (int r = check_slot(si)) return r;
         if (int r = check_pf(pf, 1)) return r;
-        enqueue_bwd(abs_ref(si), abs_ref(pf), stored[si] && store.vals, adj[cur], adj[cur ^ 1]);
+        enqueue_bwd(abs_ref(si), abs_ref(pf), stored[si] && store.vals, fwd_ok[si] != 0, adj[cur], adj[cur ^ 1]);
         cur ^= 1;
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
@@ -704,14 +775,15 @@ struct Engine : plb_engine {
             cudaGraph_t g = nullptr;
             long long l0 = launches;
             PLB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            const bool fused = fuse && tile_scatter && sparse && !plane_tile && key.n >= 2;
+            const bool fused = fuse && tile_scatter && sparse && key.n >= 2;
+            const bool restore = (key.stored & 1) != 0, next_ok = (key.stored & 2) != 0;
             if (key.dir == 0) {
                 if (fused) enqueue_fwd_fused(key.n, &Engine::mk_cursor);
                 else for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
             } else {
                 int c = key.parity;
-                if (fused) enqueue_bwd_fused(key.n, key.stored != 0, c, &Engine::mk_cursor);
-                else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), key.stored != 0, adj[c], adj[c ^ 1]); c ^= 1; }
+                if (fused) enqueue_bwd_fused(key.n, restore, next_ok, c, &Engine::mk_cursor, bwd_overlap && restore && !slab.on);
+                else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), restore, next_ok, adj[c], adj[c ^ 1]); c ^= 1; }
             }
             cudaError_t ce = cudaStreamEndCapture(stream, &g);
             graph_nodes[key] = launches - l0;
@@ -739,22 +811,23 @@ struct Engine : plb_engine {
         }
         GraphKey key{0, n, 0, store.vals != nullptr};
         if (int r = launch_graph(key, slot0, pf0)) return r;
-        for (int i = 0; i < n; i++) stored[slot0 + i] = store.vals != nullptr;
-        stored[slot0 + n] = 0;
+        for (int i = 0; i < n; i++) { stored[slot0 + i] = store.vals != nullptr; fwd_ok[slot0 + i] = 1; }
+        stored[slot0 + n] = 0; fwd_ok[slot0 + n] = 0;
         return PLB_OK;
     }
     int step_bwd(int slot0, int pf0, int n) override {
         if (n <= 0) return PLB_OK;
         if (int r = check_slot(slot0 + n - 1)) return r;
         if (int r = check_pf(pf0, n)) return r;
-        int n_stored = 0;
-        for (int i = 0; i < n; i++) n_stored += stored[slot0 + i] ? 1 : 0;
-        bool uniform = (n_stored == 0 || n_stored == n);
+        int n_stored = 0, n_ok = 0;
+        for (int i = 0; i < n; i++) { n_stored += stored[slot0 + i] ? 1 : 0; n_ok += fwd_ok[slot0 + i] ? 1 : 0; }
+        // the graphs take clamp masks / gather sums from the successor frames: every substep must have been run forward
+        bool uniform = (n_stored == 0 || n_stored == n) && n_ok == n;
         if (!use_graphs || prof_on || !sparse || !uniform) {
             for (int i = n - 1; i >= 0; i--) if (int r = substep_bwd(slot0 + i, pf0 + i)) return r;
             return PLB_OK;
         }
-        GraphKey key{1, n, cur, (n_stored == n && store.vals) ? 1 : 0};
+        GraphKey key{1, n, cur, ((n_stored == n && store.vals) ? 1 : 0) | 2};
         if (int r = launch_graph(key, slot0, pf0)) return r;
         cur ^= (n & 1);
         return PLB_OK;
@@ -830,7 +903,8 @@ struct Engine : plb_engine {
         k_g2p<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(si), abs_ref(so), grid_out);
         prof_end();
         launches += 2;
-        stored[si] = 1; stored[so] = 0;
+        slot_written(so);
+        stored[si] = 1; fwd_ok[si] = (so == si + 1);
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
     }
@@ -843,10 +917,9 @@ struct Engine : plb_engine {
         k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid_in, d_list, d_nactive, store, abs_ref(si));
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
         k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 0, d_list, d_nactive, nostore, abs_ref(si));
-        prof_end(); prof_begin(K_G2P_BWD);
-        k_g2p_bwd_tile<T><<<blocks(cfg.n_particles), kBlock, tile_smem, stream>>>(P, frames, n_pad, abs_ref(si), adj[cur], adj[cur ^ 1], grid_out, g_out, flush_variant);
         prof_end();
-        launches += 3;
+        launch_g2p_bwd(abs_ref(si), adj[cur], adj[cur ^ 1], sets[0], fwd_ok[si] != 0);
+        launches += 2;
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
     }
@@ -868,7 +941,7 @@ struct Engine : plb_engine {
         PLB_REQUIRE(slab.on && has_target, "slab loss needs slab mode and a target");
         k_loss_init<<<1, 32, 0, stream>>>(d_acc, lw.soft);
         PLB_CUDA(cudaMemsetAsync(grid_mass, 0, n_nodes * sizeof(T), stream));
-        k_loss_mass_tile<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass, flush_variant);
+        k_loss_mass_tile<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
         launches += 2;
         return PLB_OK;
     }
@@ -1101,7 +1174,7 @@ struct Engine : plb_engine {
         int nb = blocks(cfg.n_particles);
         k_loss_init<<<1, 32, 0, stream>>>(d_acc, lw.soft);
         PLB_CUDA(cudaMemsetAsync(grid_mass, 0, n_nodes * sizeof(T), stream));
-        if (tile_scatter) k_loss_mass_tile<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass, flush_variant);
+        if (tile_scatter) k_loss_mass_tile<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
         else k_loss_mass<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, slot, grid_mass);
         int rb = (int)std::min<long long>((n_nodes + 255) / 256, 148 * 8);
         k_loss_reduce<T><<<rb, 256, 0, stream>>>(grid_mass, target, target_sdf, n_nodes, d_acc);

@@ -2,14 +2,14 @@
 // reductions (primitive pose gradients, loss terms) that need warp/block cooperation.
 #pragma once
 #include <cuda_runtime.h>
-#include "plb_bodies.cuh"
+#include "plb_warp.cuh"
 
 namespace plb {
 
 constexpr int kBlock = 128;
 // minimum resident blocks per SM requested from ptxas for the register-heavy adjoint kernels (float only)
-template <class T> struct Occ { static constexpr int p2g_bwd = 1, g2p_bwd = 1; };
-template <> struct Occ<float> { static constexpr int p2g_bwd = 3, g2p_bwd = 3; };   // measured best of {1,3,4} x {1,3,4}
+template <class T> struct Occ { static constexpr int p2g_bwd = 1, g2p_bwd = 1, g2p_p2g = 1; };
+template <> struct Occ<float> { static constexpr int p2g_bwd = 3, g2p_bwd = 3, g2p_p2g = 1; };   // bwd: measured best of {1,3,4} x {1,3,4}
 
 // A frame index given either absolutely (cur == nullptr) or relative to a device-resident cursor.  The cursor form
 // lets one captured CUDA graph of an env step (S substeps) be replayed for every env step: only the 3-int cursor
@@ -70,23 +70,6 @@ __device__ __forceinline__ int block_id(int nbx, int i, int j, int k) {
 }
 
 template <class T>
-__device__ __forceinline__ void mark_blocks(const SimConst<T>& P, V3<T> x, unsigned char* flags) {
-    const int nbx = P.n_grid >> kBlkShift;
-    int b[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int c = 0; c < 2; c++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                int id = block_id(nbx, b[0] + 2 * a, b[1] + 2 * c, b[2] + 2 * e);
-                if (!flags[id]) flags[id] = 1;
-            }
-}
-
-template <class T>
 __global__ void k_mark_only(SimConst<T> P, T* frame, long long n_pad, unsigned char* flags) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < P.n_particles) mark_blocks<T>(P, load_x(frame_at(frame, 0, n_pad), p), flags);
@@ -106,222 +89,6 @@ __device__ __forceinline__ long long block_node(int n_grid, int blk, int local) 
     int bk = blk % nbx, bj = (blk / nbx) % nbx, bi = blk / (nbx * nbx);
     int i = (bi << kBlkShift) + (local >> 4), j = (bj << kBlkShift) + ((local >> 2) & 3), k = (bk << kBlkShift) + (local & 3);
     return ((long long)i * n_grid + j) * n_grid + k;
-}
-
-// ------------------------------------------------------------------------------------------------ warp scatter
-// Warp-level pre-reduction of the 27-node scatters (P2G and the G2P adjoint).
-// After the spatial sort the 32 particles of a warp sit in a handful of cells, so their 27-node stencils coincide and
-// per-particle atomics serialise at the L2 atomic unit (measured: 1M particles, p2g 230 us unsorted -> 439 us sorted).
-// Here every lane parks its 27 Vec4 contributions in a per-warp shared tile [27 nodes][33 lanes] (row padded by one
-// Vec4: the transposed read then walks 4-bank groups conflict-free).  Lanes are grouped by base cell; for each group
-// (uniform loop over distinct cells) lane q < 27 sums node q over the group's lanes and issues ONE vector RED.
-// Cost per warp: 27 STS.128 + 32 LDS.128 per lane, independent of the number of groups; atomics drop from
-// 27 x 32 to 27 x (#cells in the warp).
-constexpr int kTileStride = 33;
-constexpr int kTileVec4 = 27 * kTileStride;
-
-template <class T> struct WarpTileScatter {
-    Vec4<T>* tile;     // this warp's tile
-    int lane;
-    __device__ __forceinline__ void add(int slot, int, int, int, Vec4<T> v) const { tile[slot * kTileStride + lane] = v; }
-    __device__ __forceinline__ void end_plane(int) const {}
-};
-
-// 3-pass variant: the tile holds ONE stencil plane (9 nodes); after each plane the warp flushes it.  A third of the shared
-// memory per warp (4.75 KB instead of 14.25 KB), so the scatter kernel is no longer shared-memory-limited in occupancy.
-// Flush: lanes 0..26 = (node q = lane % 9, part r = lane / 9); part r sums the group members sitting in lanes
-// [11 r, 11 r + 11); the three partial sums meet in lanes 0..8 through two shuffles; one vector RED per node and group.
-constexpr int kPlaneVec4 = 9 * kTileStride;
-template <class T> struct WarpPlaneScatter {
-    Vec4<T>* tile; Vec4<T>* grid;
-    int lane, key, n_grid;          // key < 0: this lane carries no particle
-    __device__ __forceinline__ void add(int slot, int, int, int, Vec4<T> v) const { tile[(slot % 9) * kTileStride + lane] = v; }
-    __device__ __forceinline__ void end_plane(int plane) const {
-        const unsigned full = 0xffffffffu;
-        __syncwarp();
-        unsigned remaining = __ballot_sync(full, key >= 0);
-        const int q = lane % 9, r = lane / 9;
-        const unsigned part_mask = r == 0 ? 0x000007ffu : (r == 1 ? 0x003ff800u : (r == 2 ? 0xffc00000u : 0u));
-        const Vec4<T>* row = tile + q * kTileStride;
-        while (remaining) {
-            const int leader = __ffs(remaining) - 1;
-            const int lkey = __shfl_sync(full, key, leader);
-            const unsigned group = __ballot_sync(full, key == lkey);
-            remaining &= ~group;
-            Vec4<T> acc = mk4<T>(T(0), T(0), T(0), T(0));
-            unsigned g = group & part_mask;
-            while (g) {
-                const int j = __ffs(g) - 1;
-                g &= g - 1;
-                const Vec4<T> v = row[j];
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            acc.x += __shfl_down_sync(full, acc.x, 9) + __shfl_down_sync(full, acc.x, 18);
-            acc.y += __shfl_down_sync(full, acc.y, 9) + __shfl_down_sync(full, acc.y, 18);
-            acc.z += __shfl_down_sync(full, acc.z, 9) + __shfl_down_sync(full, acc.z, 18);
-            acc.w += __shfl_down_sync(full, acc.w, 9) + __shfl_down_sync(full, acc.w, 18);
-            if (lane < 9) {
-                const int bk = lkey % n_grid, bj = (lkey / n_grid) % n_grid, bi = lkey / (n_grid * n_grid);
-                scatter_add4(grid + node_index(n_grid, bi + plane, bj + q / 3, bk + q % 3), acc);
-            }
-        }
-        __syncwarp();
-    }
-};
-// Pre-combining policy: before a contribution is parked in the tile, lanes that sit in the same cell as their xor-1
-// partner (and, second level, as their whole quad) add their values with shuffles; only the first lane of such a pair / quad
-// writes a column and takes part in the flush.  The flush -- a serial LDS -> FADD walk over the member columns, >50 % of the
-// stall samples of k_p2g_tile in the ncu source view -- then visits a half / a quarter of the columns.  All 32 lanes must
-// call add() (the shuffles are warp-collective), so the kernels run the particle math on every lane (lanes past the end
-// redo the last particle with key = -1).
-template <class T> struct WarpCombineScatter {
-    Vec4<T>* tile;
-    int lane;
-    bool comb1, comb2, writer;
-    __device__ __forceinline__ void setup(int key) {
-        const unsigned full = 0xffffffffu;
-        const int k1 = __shfl_xor_sync(full, key, 1);
-        comb1 = key >= 0 && k1 == key;
-        const bool pair_ok = comb1;
-        const bool other_pair_ok = __shfl_xor_sync(full, (int)pair_ok, 2) != 0;
-        const int k2 = __shfl_xor_sync(full, key, 2);
-        comb2 = pair_ok && other_pair_ok && k2 == key;
-        writer = comb2 ? (lane & 3) == 0 : (comb1 ? (lane & 1) == 0 : true);
-    }
-    __device__ __forceinline__ void add(int slot, int, int, int, Vec4<T> v) const {
-        const unsigned full = 0xffffffffu;
-        Vec4<T> o;
-        o.x = __shfl_xor_sync(full, v.x, 1); o.y = __shfl_xor_sync(full, v.y, 1); o.z = __shfl_xor_sync(full, v.z, 1); o.w = __shfl_xor_sync(full, v.w, 1);
-        if (comb1) { v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-        o.x = __shfl_xor_sync(full, v.x, 2); o.y = __shfl_xor_sync(full, v.y, 2); o.z = __shfl_xor_sync(full, v.z, 2); o.w = __shfl_xor_sync(full, v.w, 2);
-        if (comb2) { v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-        if (writer) tile[slot * kTileStride + lane] = v;
-    }
-    __device__ __forceinline__ void end_plane(int) const {}
-};
-
-// payload helpers: the tile carries Vec4 (momentum+mass, velocity adjoint) or a scalar (loss mass)
-template <class T> __device__ __forceinline__ void pay_zero(Vec4<T>& a) { a = mk4<T>(T(0), T(0), T(0), T(0)); }
-template <class T> __device__ __forceinline__ void pay_acc(Vec4<T>& a, const Vec4<T>& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
-template <class T> __device__ __forceinline__ void pay_red(Vec4<T>* dst, const Vec4<T>& a) { scatter_add4(dst, a); }
-__device__ __forceinline__ void pay_zero(float& a) { a = 0.f; }
-__device__ __forceinline__ void pay_zero(double& a) { a = 0.0; }
-__device__ __forceinline__ void pay_acc(float& a, const float& v) { a += v; }
-__device__ __forceinline__ void pay_acc(double& a, const double& v) { a += v; }
-__device__ __forceinline__ void pay_red(float* dst, const float& a) { atomicAdd(dst, a); }
-__device__ __forceinline__ void pay_red(double* dst, const double& a) { atomicAdd(dst, a); }
-
-// valid: lane holds a particle; b: its base cell.  All 32 lanes must call.
-// Groups are maximal RUNS of consecutive lanes with the same base cell (after the spatial sort a warp is a few runs;
-// for arbitrary order the result is still correct, the runs just get short).  One pass over the 32 tile columns:
-// lane q < 27 accumulates node q and, at the end of each run, adds the run's sum to the grid with one vector RED.
-// Variant A ("groups"): loop over the distinct cells of the warp, gather the lanes of each cell.
-template <class T, class Pay>
-__device__ __forceinline__ void warp_tile_flush_groups(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid) {
-    __syncwarp();
-    const unsigned full = 0xffffffffu;
-    int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
-    unsigned remaining = __ballot_sync(full, valid);
-    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
-    while (remaining) {
-        int leader = __ffs(remaining) - 1;
-        int lkey = __shfl_sync(full, key, leader);
-        unsigned group = __ballot_sync(full, key == lkey);
-        remaining &= ~group;
-        if (lane < 27) {
-            Pay acc;
-            pay_zero(acc);
-            const Pay* row = tile + lane * kTileStride;
-            unsigned g = group;
-            while (g) {
-                int j = __ffs(g) - 1;
-                g &= g - 1;
-                pay_acc(acc, row[j]);
-            }
-            int bk = lkey % n_grid, bj = (lkey / n_grid) % n_grid, bi = lkey / (n_grid * n_grid);
-            pay_red(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
-        }
-    }
-    __syncwarp();
-}
-
-// Variant B ("runs"): groups are maximal RUNS of consecutive lanes with the same base cell (after the spatial sort a warp
-// is a few runs; for arbitrary order the result is still correct, the runs just get short).  One pass over the 32 tile
-// columns in chunks of 8 (8 independent LDS in flight), lane q < 27 accumulates node q and adds the sum of each run to
-// the grid with one vector RED at the run's last column.  Invalid lanes must have zero-filled their column.
-template <class T, class Pay>
-__device__ __forceinline__ void warp_tile_flush_runs(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid) {
-    __syncwarp();
-    const unsigned full = 0xffffffffu;
-    const int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
-    const int next = __shfl_down_sync(full, key, 1);
-    const unsigned run_end = __ballot_sync(full, lane == 31 || next != key);
-    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;       // node offset owned by this lane (lane < 27)
-    const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
-    Pay acc;
-    pay_zero(acc);
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        Pay v[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = row[c * 8 + j];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            pay_acc(acc, v[j]);
-            if ((run_end >> (c * 8 + j)) & 1u) {                       // warp-uniform
-                const int rkey = __shfl_sync(full, key, c * 8 + j);
-                if (lane < 27 && rkey >= 0) {
-                    int bk = rkey % n_grid, bj = (rkey / n_grid) % n_grid, bi = rkey / (n_grid * n_grid);
-                    pay_red(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
-                }
-                pay_zero(acc);
-            }
-        }
-    }
-    __syncwarp();
-}
-
-// Variant C ("run loops"): runs of consecutive equal cells like B, but with runtime loops: per run a plain counted loop
-// over its columns (LDS + adds + 3 loop instructions per column instead of the find-first-set walk of variant A).
-template <class T, class Pay>
-__device__ __forceinline__ void warp_tile_flush_runloops(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid) {
-    __syncwarp();
-    const unsigned full = 0xffffffffu;
-    const int key = valid ? (b[0] * n_grid + b[1]) * n_grid + b[2] : -1;
-    const int next = __shfl_down_sync(full, key, 1);
-    unsigned run_end = __ballot_sync(full, lane == 31 || next != key);
-    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
-    const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
-    int start = 0;
-    while (run_end) {
-        const int end = __ffs(run_end);                 // one past the last column of this run
-        run_end &= run_end - 1;
-        const int rkey = __shfl_sync(full, key, end - 1);
-        if (rkey >= 0 && lane < 27) {
-            Pay acc;
-            pay_zero(acc);
-            for (int j = start; j < end; j++) pay_acc(acc, row[j]);
-            int bk = rkey % n_grid, bj = (rkey / n_grid) % n_grid, bi = rkey / (n_grid * n_grid);
-            pay_red(grid + node_index(n_grid, bi + oi, bj + oj, bk + ok), acc);
-        }
-        start = end;
-    }
-    __syncwarp();
-}
-
-template <class T, class Pay>
-__device__ __forceinline__ void warp_tile_flush(const Pay* tile, int lane, bool valid, const int b[3], int n_grid, Pay* grid, int variant) {
-    if (variant == 0) warp_tile_flush_groups<T, Pay>(tile, lane, valid, b, n_grid, grid);
-    else if (variant == 1) warp_tile_flush_runs<T, Pay>(tile, lane, valid, b, n_grid, grid);
-    else warp_tile_flush_runloops<T, Pay>(tile, lane, valid, b, n_grid, grid);
-}
-
-// zero this lane's tile column (lanes without a particle, so that the run-based flush can read every column)
-template <class Pay> __device__ __forceinline__ void tile_zero_column(Pay* tile, int lane) {
-    Pay z;
-    pay_zero(z);
-#pragma unroll
-    for (int q = 0; q < 27; q++) tile[q * kTileStride + lane] = z;
 }
 
 // ------------------------------------------------------------------------------------------------ slab halo
@@ -485,165 +252,55 @@ __global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long l
     if (flags) mark_blocks<T>(P, load_x(fin, p), flags);
 }
 
-// same, with the warp-tile scatter (dynamic shared memory: kBlock/32 tiles)
-template <class T>
-__global__ void __launch_bounds__(kBlock) k_p2g_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
-                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags,
-                                                     int flush_variant) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    int b[3] = {0, 0, 0};
-    if (valid) {
-        FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
-        WarpTileScatter<T> sc{tile, lane};
-        p2g_body<T, WarpTileScatter<T>>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, sc);
-        V3<T> x = load_x(fin, p);
-#pragma unroll
-        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
-        if (flags) mark_blocks<T>(P, x, flags);
-    } else {
-        tile_zero_column(tile, lane);
-    }
-    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, grid_in, flush_variant);
+// ---- scatter kernels with the warp tile (plb_warp.cuh); dynamic shared memory = (blockDim / 32) tiles.
+// kPlane: plane tile (4.75 KB / warp) instead of the full tile (14.25 KB / warp).  kCta = threads per CTA (64 or 128): at
+// small particle counts the 64-thread CTAs let one wave hold every warp of the launch.
+template <class T, bool kPlane> __device__ __forceinline__ Vec4<T>* warp_tile_ptr(unsigned char* smem_raw) {
+    return reinterpret_cast<Vec4<T>*>(smem_raw) + (threadIdx.x >> 5) * (kPlane ? kPlaneVec4 : kTileVec4);
 }
 
-// P2G with the one-plane tile (dynamic shared memory: kBlock/32 plane tiles).  Every lane runs the particle math (lanes
-// past the end re-do the last particle with key = -1 and no stores) because the per-plane flush is warp-collective.
-template <class T>
-__global__ void __launch_bounds__(kBlock) k_p2g_plane(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
-                                                      int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    if (!valid) p = P.n_particles - 1;
-    FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
-    V3<T> x = load_x(fin, p);
-    int b[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
-    WarpPlaneScatter<T> sc;
-    sc.tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kPlaneVec4;
-    sc.grid = grid_in; sc.lane = lane; sc.n_grid = P.n_grid;
-    sc.key = valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1;
-    p2g_body<T, WarpPlaneScatter<T>>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0 && valid, mat, sc);
-    if (flags && valid) mark_blocks<T>(P, x, flags);
-}
-
-// P2G / fused kernels with the pre-combining tile policy
-template <class T>
-__global__ void __launch_bounds__(kBlock) k_p2g_comb(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
+template <class T, bool kPlane>
+__global__ void __launch_bounds__(kBlock) k_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
                                                      int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    if (!valid) p = P.n_particles - 1;
-    FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
-    V3<T> x = load_x(fin, p);
-    int b[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
-    WarpCombineScatter<T> sc;
-    sc.tile = tile; sc.lane = lane;
-    sc.setup(valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1);
-    p2g_body<T, WarpCombineScatter<T>>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0 && valid, mat, sc);
-    if (flags && valid) mark_blocks<T>(P, x, flags);
-    warp_tile_flush_groups<T, Vec4<T>>(tile, lane, valid && sc.writer, b, P.n_grid, grid_in);
+    t_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+                     frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in, flags);
 }
 
-template <class T>
-__global__ void __launch_bounds__(kBlock) k_g2p_p2g_comb(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_mid,
-                                                         SlotRef slot_out, Material<T> mat, const Vec4<T>* grid_out, Vec4<T>* grid_in,
-                                                         unsigned char* flags) {
+// G2P of substep s + P2G of substep s+1 in one pass over the particles (inside env-step graphs)
+// kMinB: resident CTAs per SM requested from ptxas (register cap 65536 / (128 kMinB)): 5 -> 96 registers (what ptxas picks
+// unprompted), 6 -> 80 registers (24 resident warps with the plane tile)
+template <class T, bool kPlane, int kMinB>
+__global__ void __launch_bounds__(kBlock, kMinB) k_g2p_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in,
+                                                                           SlotRef slot_mid, SlotRef slot_out, Material<T> mat,
+                                                                           const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    if (!valid) p = P.n_particles - 1;
-    // G2P of substep s (registers), then P2G of substep s+1 with the combine policy keyed on the ADVECTED position
-    V3<T> nx, nv; M3<T> nC;
-    g2p_core<T>(P, load_x(frame_at(frames, slot_in.get(), n_pad), p), grid_out, nx, nv, nC);
-    FramePtr<T> fmid = frame_at(frames, slot_mid.get(), n_pad);
-    if (valid) store_xvC(fmid, p, nx, nv, nC);
-    int b[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) b[d] = (int)(nx[d] * P.inv_dx - T(0.5));
-    WarpCombineScatter<T> sc;
-    sc.tile = tile; sc.lane = lane;
-    sc.setup(valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1);
-    M3<T> F = load_F(fmid, p);
-    T mu, lam, ys;
-    load_material(P, mat, p, mu, lam, ys);
-    M3<T> new_F;
-    p2g_core<T, WarpCombineScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
-    if (valid) {
-        store_F(frame_at(frames, slot_out.get(), n_pad), p, new_F);
-        if (flags) mark_blocks<T>(P, nx, flags);
-    }
-    warp_tile_flush_groups<T, Vec4<T>>(tile, lane, valid && sc.writer, b, P.n_grid, grid_in);
+    t_g2p_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+                         frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_mid.get(), n_pad),
+                         frame_at(frames, slot_out.get(), n_pad), mat, grid_out, grid_in, flags);
 }
 
-template <class T>
-__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_comb(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
-                                                                           T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+// g2p.grad; next_ok: slot_in + 1 holds the frame G2P produced from slot_in (clamp masks and gather sum are read from it)
+template <class T, bool kPlane>
+__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, int next_ok,
+                                                                           T* adj_next, T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    if (!valid) p = P.n_particles - 1;
-    FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
-    V3<T> x = load_x(fin, p);
-    int b[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
-    WarpCombineScatter<T> sc;
-    sc.tile = tile; sc.lane = lane;
-    sc.setup(valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1);
-    V3<T> gxn, gvn; M3<T> gCn;
-    load_xvC(frame_at(adj_next, 0, n_pad), p, gxn, gvn, gCn);
-    V3<T> gx = g2p_bwd_core<T, WarpCombineScatter<T>>(P, x, gxn, gvn, gCn, grid_out, sc);
-    if (valid) frame_at(adj_cur, 0, n_pad).A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
-    warp_tile_flush_groups<T, Vec4<T>>(tile, lane, valid && sc.writer, b, P.n_grid, g_out);
+    const int si = slot_in.get();
+    FramePtr<T> fnext = frame_at(frames, si + 1, n_pad);
+    t_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+                         frame_at(frames, si, n_pad), next_ok ? &fnext : nullptr, frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad),
+                         grid_out, g_out);
 }
 
-template <class T>
-__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_p2g_bwd_g2p_bwd_comb(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
+// p2g.grad of substep s + g2p.grad of substep s-1 (inside env-step graphs; frame s was produced by G2P(s-1) there)
+template <class T, bool kPlane, int kMinB>
+__global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
                                                                                    SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
                                                                                    const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    if (!valid) p = P.n_particles - 1;
-    FramePtr<T> fs = frame_at(frames, slot_s.get(), n_pad), fprev = frame_at(frames, slot_prev.get(), n_pad);
-    FramePtr<T> next = frame_at(adj_next, 0, n_pad), cur = frame_at(adj_cur, 0, n_pad);
-    V3<T> x, v; M3<T> C;
-    load_xvC(fs, p, x, v, C);
-    M3<T> F = load_F(fs, p);
-    T mu, lam, ys;
-    load_material(P, mat, p, mu, lam, ys);
-    Vec4<T> part = cur.A0[p];
-    V3<T> gx, gv; M3<T> gC, gF;
-    p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
-    if (valid) store_F(cur, p, gF);
-    V3<T> xp = load_x(fprev, p);
-    int b[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) b[d] = (int)(xp[d] * P.inv_dx - T(0.5));
-    WarpCombineScatter<T> sc;
-    sc.tile = tile; sc.lane = lane;
-    sc.setup(valid ? (b[0] * P.n_grid + b[1]) * P.n_grid + b[2] : -1);
-    V3<T> gxp = g2p_bwd_core<T, WarpCombineScatter<T>>(P, xp, gx, gv, gC, grid_out, sc);
-    if (valid) next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
-    warp_tile_flush_groups<T, Vec4<T>>(tile, lane, valid && sc.writer, b, P.n_grid, g_out);
+    t_p2g_bwd_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+                                 frame_at(frames, slot_s.get(), n_pad), frame_at(frames, slot_prev.get(), n_pad), frame_at(adj_next, 0, n_pad),
+                                 frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out);
 }
 
 template <class T>
@@ -752,81 +409,6 @@ __global__ void __launch_bounds__(kBlock) k_g2p_bwd(SimConst<T> P, T* frames, lo
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
-                                                         T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_variant) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    int b[3] = {0, 0, 0};
-    if (valid) {
-        FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
-        WarpTileScatter<T> sc{tile, lane};
-        g2p_bwd_body<T, WarpTileScatter<T>>(p, P, fin, frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad), grid_out, sc);
-        V3<T> x = load_x(fin, p);
-#pragma unroll
-        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
-    } else {
-        tile_zero_column(tile, lane);
-    }
-    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, g_out, flush_variant);
-}
-
-// ---- fused particle kernels (see g2p_p2g_body / p2g_bwd_g2p_bwd_body) -------------------------------------------------------
-// Every lane runs the math (lanes past the end redo the last particle, store nothing, and zero their tile column) because
-// the tile flush is warp-collective.
-template <class T>
-__global__ void __launch_bounds__(kBlock) k_g2p_p2g_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_mid,
-                                                         SlotRef slot_out, Material<T> mat, const Vec4<T>* grid_out, Vec4<T>* grid_in,
-                                                         unsigned char* flags, int flush_variant) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    int b[3] = {0, 0, 0};
-    if (valid) {
-        FramePtr<T> fmid = frame_at(frames, slot_mid.get(), n_pad);
-        WarpTileScatter<T> sc{tile, lane};
-        g2p_p2g_body<T, WarpTileScatter<T>>(p, P, frame_at(frames, slot_in.get(), n_pad), fmid, frame_at(frames, slot_out.get(), n_pad), true,
-                                            mat, grid_out, sc);
-        V3<T> x = load_x(fmid, p);                       // the advected position this thread just stored
-#pragma unroll
-        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
-        if (flags) mark_blocks<T>(P, x, flags);
-    } else {
-        tile_zero_column(tile, lane);
-    }
-    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, grid_in, flush_variant);
-}
-
-template <class T>
-__global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_p2g_bwd_g2p_bwd_tile(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
-                                                                                   SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
-                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out,
-                                                                                   int flush_variant) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Vec4<T>* tile = reinterpret_cast<Vec4<T>*>(smem_raw) + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    int b[3] = {0, 0, 0};
-    if (valid) {
-        FramePtr<T> fprev = frame_at(frames, slot_prev.get(), n_pad);
-        WarpTileScatter<T> sc{tile, lane};
-        p2g_bwd_g2p_bwd_body<T, WarpTileScatter<T>>(p, P, frame_at(frames, slot_s.get(), n_pad), fprev, frame_at(adj_next, 0, n_pad),
-                                                    frame_at(adj_cur, 0, n_pad), true, mat, g_in, grid_out, sc);
-        V3<T> x = load_x(fprev, p);
-#pragma unroll
-        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
-    } else {
-        tile_zero_column(tile, lane);
-    }
-    warp_tile_flush<T, Vec4<T>>(tile, lane, valid, b, P.n_grid, g_out, flush_variant);
-}
-
-template <class T>
 __global__ void __launch_bounds__(kBlock) k_grid_bwd(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pfr,
                                                      Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, int clear,
                                                      double* prim_grad, long long n_nodes) {
@@ -869,29 +451,10 @@ __global__ void __launch_bounds__(kBlock) k_loss_mass(SimConst<T> P, T* frames, 
 }
 
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_loss_mass_tile(SimConst<T> P, T* frames, long long n_pad, int slot, T* grid_mass, int flush_variant) {
+__global__ void __launch_bounds__(kBlock) k_loss_mass_tile(SimConst<T> P, T* frames, long long n_pad, int slot, T* grid_mass) {
     __shared__ T tiles[(kBlock / 32) * kTileVec4];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T* tile = tiles + warp * kTileVec4;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < P.n_particles;
-    int b[3] = {0, 0, 0};
-    if (valid) {
-        V3<T> x = load_x(frame_at(frames, slot, n_pad), p);
-        Stencil<T> st = make_stencil(x, P.inv_dx);
-#pragma unroll
-        for (int d = 0; d < 3; d++) b[d] = st.b[d];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    tile[((i * 3 + j) * 3 + k) * kTileStride + lane] = st.w[i][0] * st.w[j][1] * st.w[k][2] * P.p_mass;
-    } else {
-        tile_zero_column(tile, lane);
-    }
-    warp_tile_flush<T, T>(tile, lane, valid, b, P.n_grid, grid_mass, flush_variant);
+    t_loss_mass<T>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, tiles + (threadIdx.x >> 5) * kTileVec4, P,
+                   frame_at(frames, slot, n_pad), grid_mass);
 }
 
 __global__ void k_loss_init(double* acc, int soft) {

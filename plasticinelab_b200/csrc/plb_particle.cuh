@@ -197,4 +197,12 @@ template <class T> PLB_HD V3<T> advect_backward(const SimConst<T>& P, V3<T> x, V
     return r;
 }
 
+// same, from the position G2P stored: x' = max(min(y, hi), 0) lies strictly inside (0, hi) iff both clamps passed y through
+template <class T> PLB_HD V3<T> advect_backward_stored(const SimConst<T>& P, V3<T> x_next, V3<T> gx_next) {
+    V3<T> r;
+#pragma unroll
+    for (int d = 0; d < 3; d++) r[d] = (T(0) < x_next[d] && x_next[d] < P.x_hi) ? gx_next[d] : T(0);
+    return r;
+}
+
 }  // namespace plb

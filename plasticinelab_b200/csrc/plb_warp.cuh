@@ -1,0 +1,346 @@
+// Warp-level pre-reduction of the 27-node scatters (P2G and the G2P adjoint).
+//
+// After the spatial sort the 32 particles of a warp sit in a handful of cells, so their 27-node stencils coincide and
+// per-particle atomics serialise at the L2 atomic unit (measured: 1M particles, p2g 230 us unsorted -> 439 us sorted).
+// Every lane parks its contributions in a per-warp shared tile [nodes][33 columns]; lanes are grouped by base cell and
+// for each group one lane per node sums the group's columns and issues ONE vector RED: atomics drop from
+// 27 x 32 per warp to 27 x (#cells in the warp).
+//
+// Two tile shapes:
+//   * full tile  [27][33] Vec4 (14.25 KB / warp): one flush per particle, lane q < 27 owns node q;
+//   * plane tile [ 9][33] Vec4 ( 4.75 KB / warp): the stencil is produced plane by plane (i = 0,1,2) and flushed after
+//     each plane; lanes 0..26 = (node q = lane % 9, part r = lane / 9), part r sums the group members sitting in lanes
+//     [11 r, 11 r + 11), the three partial sums meet in lanes 0..8 through two shuffles.  A third of the shared memory,
+//     so the scatter kernels are limited by registers, not by shared memory, in resident warps per SM.
+// Column 32 of every row (the padding that makes the transposed read conflict-free) is kept at zero and serves as the
+// "no member" column: the member walk is unrolled by four with independent LDS.
+//
+// The code below uses only the small intrinsic layer (warp_ballot / warp_shfl / warp_shfl_down / warp_sync / ctz32), so
+// that tests/host/warp_emul.hpp can run it on the CPU with 32 lock-stepped threads per warp (there is no GPU on the
+// build box); on the device these are the CUDA warp intrinsics.
+#pragma once
+#include "plb_bodies.cuh"
+
+namespace plb {
+
+#if defined(__CUDACC__)
+PLB_D unsigned warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+PLB_D int warp_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PLB_D float warp_shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+PLB_D double warp_shfl_down(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+PLB_D void warp_sync() { __syncwarp(); }
+PLB_D int ctz32(unsigned g) { return __clz(__brev(g)); }          // 32 for g == 0
+#endif
+// (host: tests/host/warp_emul.hpp defines the same six functions before this header is included)
+
+constexpr int kTileStride = 33;
+constexpr int kNullCol = 32;
+constexpr int kTileVec4 = 27 * kTileStride;
+constexpr int kPlaneVec4 = 9 * kTileStride;
+
+// base cell packed into one int, 10 bits per axis (n_grid <= 1024); negative = the lane carries no particle
+PLB_HD int pack_cell(int i, int j, int k) { return (i << 20) | (j << 10) | k; }
+template <class T> PLB_HD int cell_key(V3<T> x, T inv_dx) {
+    return pack_cell((int)(x.x * inv_dx - T(0.5)), (int)(x.y * inv_dx - T(0.5)), (int)(x.z * inv_dx - T(0.5)));
+}
+
+// payload helpers: the tile carries Vec4 (momentum+mass, velocity adjoint) or a scalar (loss mass)
+template <class T> PLB_HD void pay_zero(Vec4<T>& a) { a = mk4<T>(T(0), T(0), T(0), T(0)); }
+template <class T> PLB_HD void pay_acc(Vec4<T>& a, const Vec4<T>& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+template <class T> PLB_D void pay_red(Vec4<T>* dst, const Vec4<T>& a) { scatter_add4(dst, a); }
+PLB_HD void pay_zero(float& a) { a = 0.f; }
+PLB_HD void pay_zero(double& a) { a = 0.0; }
+PLB_HD void pay_acc(float& a, const float& v) { a += v; }
+PLB_HD void pay_acc(double& a, const double& v) { a += v; }
+PLB_D void pay_red(float* dst, const float& a) { scatter_add1(dst, a); }
+PLB_D void pay_red(double* dst, const double& a) { scatter_add1(dst, a); }
+
+// sum of the columns named by the bits of `g` of one tile row (row[kNullCol] must be zero)
+template <class Pay> PLB_D Pay tile_row_sum(const Pay* row, unsigned g) {
+    Pay a0, a1;
+    pay_zero(a0); pay_zero(a1);
+    while (g) {
+        const int j0 = ctz32(g); g &= g - 1;
+        const int j1 = ctz32(g); g &= g - 1;
+        const int j2 = ctz32(g); g &= g - 1;
+        const int j3 = ctz32(g); g &= g - 1;
+        const Pay v0 = row[j0], v1 = row[j1], v2 = row[j2], v3 = row[j3];
+        pay_acc(a0, v0); pay_acc(a1, v1); pay_acc(a0, v2); pay_acc(a1, v3);
+    }
+    pay_acc(a0, a1);
+    return a0;
+}
+
+// ------------------------------------------------------------------------------------------------ full tile
+template <class T> struct WarpTileScatter {
+    Vec4<T>* tile;     // this warp's tile
+    int lane;
+    PLB_D void add(int slot, int, int, int, Vec4<T> v) const { tile[slot * kTileStride + lane] = v; }
+    PLB_D void end_plane(int) const {}
+};
+
+// lane q < 27 zeroes the padding column of row q (the only lane that ever reads that row)
+template <class Pay> PLB_D void tile_init(Pay* tile, int lane) {
+    if (lane < 27) pay_zero(tile[lane * kTileStride + kNullCol]);
+}
+
+// key: packed base cell of this lane's particle (< 0: none).  All 32 lanes must call.  Loop over the distinct cells of
+// the warp; lane q < 27 sums node q over the lanes of the cell and adds it to the grid with one (vector) RED.
+template <class Pay>
+PLB_D void warp_tile_flush(const Pay* tile, int lane, int key, int n_grid, Pay* grid) {
+    warp_sync();
+    unsigned remaining = warp_ballot(key >= 0);
+    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;       // node offset owned by this lane (lane < 27)
+    const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
+    while (remaining) {
+        const int leader = ctz32(remaining);
+        const int lkey = warp_shfl(key, leader);
+        const unsigned group = warp_ballot(key == lkey);
+        remaining &= ~group;
+        if (lane < 27) {
+            const Pay acc = tile_row_sum(row, group);
+            pay_red(grid + node_index(n_grid, (lkey >> 20) + oi, ((lkey >> 10) & 1023) + oj, (lkey & 1023) + ok), acc);
+        }
+    }
+    warp_sync();
+}
+
+// ------------------------------------------------------------------------------------------------ plane tile
+template <class T> struct WarpPlaneScatter {
+    Vec4<T>* tile; Vec4<T>* grid;
+    int lane, key, n_grid;          // key < 0: this lane carries no particle
+    PLB_D void init() const {       // zero the padding column; the first end_plane() synchronises before any read
+        if (lane < 9) pay_zero(tile[lane * kTileStride + kNullCol]);
+    }
+    PLB_D void add(int slot, int, int, int, Vec4<T> v) const { tile[(slot % 9) * kTileStride + lane] = v; }
+    PLB_D void end_plane(int plane) const {
+        warp_sync();
+        unsigned remaining = warp_ballot(key >= 0);
+        const int q = lane % 9, r = lane / 9;
+        const unsigned part_mask = r == 0 ? 0x000007ffu : (r == 1 ? 0x003ff800u : (r == 2 ? 0xffc00000u : 0u));
+        const Vec4<T>* row = tile + q * kTileStride;
+        while (remaining) {
+            const int leader = ctz32(remaining);
+            const int lkey = warp_shfl(key, leader);
+            const unsigned group = warp_ballot(key == lkey);
+            remaining &= ~group;
+            Vec4<T> acc = tile_row_sum(row, group & part_mask);
+            acc.x += warp_shfl_down(acc.x, 9) + warp_shfl_down(acc.x, 18);
+            acc.y += warp_shfl_down(acc.y, 9) + warp_shfl_down(acc.y, 18);
+            acc.z += warp_shfl_down(acc.z, 9) + warp_shfl_down(acc.z, 18);
+            acc.w += warp_shfl_down(acc.w, 9) + warp_shfl_down(acc.w, 18);
+            if (lane < 9)
+                scatter_add4(grid + node_index(n_grid, (lkey >> 20) + plane, ((lkey >> 10) & 1023) + q / 3, (lkey & 1023) + q % 3), acc);
+        }
+        warp_sync();                // the next plane overwrites the columns
+    }
+};
+
+
+// ================================================================================================
+// Thread-level scatter kernels: what ONE thread of a scatter kernel does, given its particle index, its lane and its warp's
+// tile.  The __global__ wrappers in plb_kernels.cuh only derive (p, lane, tile) from the launch geometry; the host warp
+// emulation (tests/host) calls the same functions.  kPlane selects the plane tile; with it every lane runs the particle
+// math (lanes past the end redo the last particle with key = -1 and store nothing) because the per-plane flush is
+// warp-collective.  With the full tile, lanes past the end skip the math and only take part in the flush.
+// ================================================================================================
+namespace detail {
+constexpr int kBlkShiftW = 2;          // 4 nodes per active-block edge (same constant as plb_kernels.cuh)
+}
+
+// flags[] of the (up to 8) 4^3 blocks touched by the stencil of a particle at x
+template <class T>
+PLB_HD void mark_blocks(const SimConst<T>& P, V3<T> x, unsigned char* flags) {
+    const int nbx = P.n_grid >> detail::kBlkShiftW;
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                int id = (((b[0] + 2 * a) >> detail::kBlkShiftW) * nbx + ((b[1] + 2 * c) >> detail::kBlkShiftW)) * nbx +
+                         ((b[2] + 2 * e) >> detail::kBlkShiftW);
+                if (!flags[id]) flags[id] = 1;
+            }
+}
+
+// P2G of one substep
+template <class T, bool kPlane>
+PLB_D void t_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>& fout, bool store_F,
+                 const Material<T>& mat, Vec4<T>* grid_in, unsigned char* flags) {
+    const bool valid = p < P.n_particles;
+    if (kPlane) {
+        if (!valid) p = P.n_particles - 1;
+        V3<T> x = load_x(fin, p);
+        WarpPlaneScatter<T> sc{tile, grid_in, lane, valid ? cell_key(x, P.inv_dx) : -1, P.n_grid};
+        sc.init();
+        p2g_body<T, WarpPlaneScatter<T>>(p, P, fin, fout, store_F && valid, mat, sc);
+        if (flags && valid) mark_blocks<T>(P, x, flags);
+    } else {
+        tile_init(tile, lane);
+        int key = -1;
+        if (valid) {
+            WarpTileScatter<T> sc{tile, lane};
+            p2g_body<T, WarpTileScatter<T>>(p, P, fin, fout, store_F, mat, sc);
+            V3<T> x = load_x(fin, p);
+            key = cell_key(x, P.inv_dx);
+            if (flags) mark_blocks<T>(P, x, flags);
+        }
+        warp_tile_flush(tile, lane, key, P.n_grid, grid_in);
+    }
+}
+
+// G2P of substep s (frame fin -> fmid) + P2G of substep s+1 (F from fmid, F' to fout), keyed on the ADVECTED position
+template <class T, bool kPlane>
+PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>& fmid,
+                     const FramePtr<T>& fout, const Material<T>& mat, const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags) {
+    const bool valid = p < P.n_particles;
+    if (kPlane) {
+        if (!valid) p = P.n_particles - 1;
+        V3<T> nx, nv; M3<T> nC;
+        g2p_core<T>(P, load_x(fin, p), grid_out, nx, nv, nC);
+        if (valid) store_xvC(fmid, p, nx, nv, nC);
+        WarpPlaneScatter<T> sc{tile, grid_in, lane, valid ? cell_key(nx, P.inv_dx) : -1, P.n_grid};
+        sc.init();
+        M3<T> F = load_F(fmid, p);
+        T mu, lam, ys;
+        load_material(P, mat, p, mu, lam, ys);
+        M3<T> new_F;
+        p2g_core<T, WarpPlaneScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
+        if (valid) {
+            store_F(fout, p, new_F);
+            if (flags) mark_blocks<T>(P, nx, flags);
+        }
+    } else {
+        tile_init(tile, lane);
+        int key = -1;
+        if (valid) {
+            V3<T> nx, nv; M3<T> nC;
+            g2p_core<T>(P, load_x(fin, p), grid_out, nx, nv, nC);
+            store_xvC(fmid, p, nx, nv, nC);
+            M3<T> F = load_F(fmid, p);
+            T mu, lam, ys;
+            load_material(P, mat, p, mu, lam, ys);
+            M3<T> new_F;
+            WarpTileScatter<T> sc{tile, lane};
+            p2g_core<T, WarpTileScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
+            store_F(fout, p, new_F);
+            key = cell_key(nx, P.inv_dx);
+            if (flags) mark_blocks<T>(P, nx, flags);
+        }
+        warp_tile_flush(tile, lane, key, P.n_grid, grid_in);
+    }
+}
+
+// g2p.grad of one substep (state frame fin; fnext = the frame G2P produced, or null pointers => recompute the gather sum)
+template <class T, bool kPlane>
+PLB_D void t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>* fnext,
+                     const FramePtr<T>& adj_next, const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+    const bool valid = p < P.n_particles;
+    if (kPlane) {
+        if (!valid) p = P.n_particles - 1;
+        V3<T> x = load_x(fin, p);
+        WarpPlaneScatter<T> sc{tile, g_out, lane, valid ? cell_key(x, P.inv_dx) : -1, P.n_grid};
+        sc.init();
+        V3<T> gxn, gvn; M3<T> gCn;
+        load_xvC(adj_next, p, gxn, gvn, gCn);
+        V3<T> gx;
+        if (fnext) {
+            Vec4<T> q0 = fnext->A0[p], q1 = fnext->A1[p];
+            gx = g2p_bwd_core<T, WarpPlaneScatter<T>, true>(P, x, gxn, gvn, gCn, grid_out, sc, mk3<T>(q0.x, q0.y, q0.z), mk3<T>(q0.w, q1.x, q1.y));
+        } else {
+            gx = g2p_bwd_core<T, WarpPlaneScatter<T>, false>(P, x, gxn, gvn, gCn, grid_out, sc, zero3<T>(), zero3<T>());
+        }
+        if (valid) adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
+    } else {
+        tile_init(tile, lane);
+        int key = -1;
+        if (valid) {
+            V3<T> x = load_x(fin, p);
+            WarpTileScatter<T> sc{tile, lane};
+            V3<T> gxn, gvn; M3<T> gCn;
+            load_xvC(adj_next, p, gxn, gvn, gCn);
+            V3<T> gx;
+            if (fnext) {
+                Vec4<T> q0 = fnext->A0[p], q1 = fnext->A1[p];
+                gx = g2p_bwd_core<T, WarpTileScatter<T>, true>(P, x, gxn, gvn, gCn, grid_out, sc, mk3<T>(q0.x, q0.y, q0.z), mk3<T>(q0.w, q1.x, q1.y));
+            } else {
+                gx = g2p_bwd_core<T, WarpTileScatter<T>, false>(P, x, gxn, gvn, gCn, grid_out, sc, zero3<T>(), zero3<T>());
+            }
+            adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
+            key = cell_key(x, P.inv_dx);
+        }
+        warp_tile_flush(tile, lane, key, P.n_grid, g_out);
+    }
+}
+
+// p2g.grad of substep s (frame fs) + g2p.grad of substep s-1 (frame fprev); the adjoint of (x,v,C)[s] stays in registers and
+// the state (x,v)[s] this thread loaded anyway is what G2P(s-1) produced (clamp masks + gather sum come from it)
+template <class T, bool kPlane>
+PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fs, const FramePtr<T>& fprev,
+                             const FramePtr<T>& next, const FramePtr<T>& cur, const Material<T>& mat, const Vec4<T>* g_in,
+                             const Vec4<T>* grid_out, Vec4<T>* g_out) {
+    const bool valid = p < P.n_particles;
+    if (kPlane) {
+        if (!valid) p = P.n_particles - 1;
+        V3<T> x, v; M3<T> C;
+        load_xvC(fs, p, x, v, C);
+        M3<T> F = load_F(fs, p);
+        T mu, lam, ys;
+        load_material(P, mat, p, mu, lam, ys);
+        Vec4<T> part = cur.A0[p];
+        V3<T> gx, gv; M3<T> gC, gF;
+        p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
+        if (valid) store_F(cur, p, gF);
+        V3<T> xp = load_x(fprev, p);
+        WarpPlaneScatter<T> sc{tile, g_out, lane, valid ? cell_key(xp, P.inv_dx) : -1, P.n_grid};
+        sc.init();
+        V3<T> gxp = g2p_bwd_core<T, WarpPlaneScatter<T>, true>(P, xp, gx, gv, gC, grid_out, sc, x, v);
+        if (valid) next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
+    } else {
+        tile_init(tile, lane);
+        int key = -1;
+        if (valid) {
+            V3<T> x, v; M3<T> C;
+            load_xvC(fs, p, x, v, C);
+            M3<T> F = load_F(fs, p);
+            T mu, lam, ys;
+            load_material(P, mat, p, mu, lam, ys);
+            Vec4<T> part = cur.A0[p];
+            V3<T> gx, gv; M3<T> gC, gF;
+            p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
+            store_F(cur, p, gF);
+            V3<T> xp = load_x(fprev, p);
+            WarpTileScatter<T> sc{tile, lane};
+            V3<T> gxp = g2p_bwd_core<T, WarpTileScatter<T>, true>(P, xp, gx, gv, gC, grid_out, sc, x, v);
+            next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
+            key = cell_key(xp, P.inv_dx);
+        }
+        warp_tile_flush(tile, lane, key, P.n_grid, g_out);
+    }
+}
+
+// mass-only scatter of the loss (scalar payload, full tile of scalars)
+template <class T>
+PLB_D void t_loss_mass(int p, int lane, T* tile, const SimConst<T>& P, const FramePtr<T>& fin, T* grid_mass) {
+    tile_init(tile, lane);
+    int key = -1;
+    if (p < P.n_particles) {
+        V3<T> x = load_x(fin, p);
+        Stencil<T> st = make_stencil(x, P.inv_dx);
+        key = pack_cell(st.b[0], st.b[1], st.b[2]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    tile[((i * 3 + j) * 3 + k) * kTileStride + lane] = st.w[i][0] * st.w[j][1] * st.w[k][2] * P.p_mass;
+    }
+    warp_tile_flush(tile, lane, key, P.n_grid, grid_mass);
+}
+
+}  // namespace plb
