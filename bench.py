@@ -496,6 +496,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+    eng.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -180,6 +180,7 @@ struct Engine : plb_engine {
     bool bwd_plane = false;         // same for the backward scatter kernels (PLB_BWD_PLANE)
     int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
     int fwd_minb = 5, bwd_minb = 3; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 / PLB_BWD_MINB=4 select the tighter cap)
+    bool grid_scan = false;         // forward grid stage as one kernel (flag scan + store + grid operator), PLB_GRID_SCAN=1
     bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
                                     // particle kernel and grid adjoint of substep s (needs the second grid set; PLB_BWD_OVERLAP=0 disables)
     // grid set: forward grid (momentum+mass), grid operator output, active-block list.  Set 0 is the working set of the
@@ -283,6 +284,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_FWD_MINB")) fwd_minb = atoi(v);
         if (const char* v = getenv("PLB_BWD_MINB")) bwd_minb = atoi(v);
         if (const char* v = getenv("PLB_BWD_OVERLAP")) bwd_overlap = atoi(v) != 0;
+        if (const char* v = getenv("PLB_GRID_SCAN")) grid_scan = atoi(v) != 0;
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
         if (tile_scatter) {
             const int full = (int)tile_smem_bytes(false, kBlock);
@@ -529,6 +531,11 @@ struct Engine : plb_engine {
 
     // ---------------------------------------------------------------- substeps
     int sparse_ctas() const { return std::min(std::max(n_blocks / 2, 1), 148 * 8); }
+    int scan_ctas() const { return std::min(std::max((n_blocks + kBlock - 1) / kBlock, 1), 148 * 8); }
+    // forward grid stage as one kernel (k_grid_fwd_scan): single GPU, forward-grid store present, per-CTA list capacity suffices
+    bool scan_mode() const {
+        return grid_scan && sparse && tile_scatter && store.vals && !slab.on && (long long)scan_ctas() * kScanCap >= n_blocks;
+    }
     void compact_blocks() {
         cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
         k_compact<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags, d_list, d_nactive);
@@ -551,6 +558,12 @@ struct Engine : plb_engine {
                                                               slab.listed_stamp, d_list, d_nactive);
                 halo_add_inbox(grid_in);
                 launches += 8;
+            } else if (scan_mode()) {
+                // one kernel: flag scan + store + grid operator (the slot's store counter was zeroed by the caller)
+                k_grid_fwd_scan<T><<<scan_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, d_flags, n_blocks, store, si);
+                prof_end();
+                launches++;
+                return;
             } else {
                 compact_blocks();
             }
@@ -752,6 +765,7 @@ struct Engine : plb_engine {
         if (int r = check_slot(so)) return r;
         if (int r = check_pf(pf, 1)) return r;
         PLB_REQUIRE(si != so, "in-place substep");
+        if (scan_mode()) PLB_CUDA(cudaMemsetAsync(store.cnt + si, 0, sizeof(int), stream));
         enqueue_fwd(abs_ref(si), abs_ref(so), abs_ref(pf));
         slot_written(so);
         stored[si] = store.vals != nullptr;
@@ -794,7 +808,8 @@ struct Engine : plb_engine {
             cudaGraphDestroy(g);
             it = graphs.emplace(key, ge).first;
         }
-        k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
+        if (key.dir == 0 && scan_mode()) k_set_cursor_zero<<<1, 256, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0, store.cnt, key.n);
+        else k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
         PLB_CUDA(cudaGraphLaunch(it->second, stream));
         // kernels + memset nodes inside the replayed graph (the capture counted them once into graph_nodes[key])
         launches += graph_nodes[key] + 1;
@@ -809,7 +824,7 @@ struct Engine : plb_engine {
             for (int i = 0; i < n; i++) if (int r = substep_fwd(slot0 + i, slot0 + i + 1, pf0 + i)) return r;
             return PLB_OK;
         }
-        GraphKey key{0, n, 0, store.vals != nullptr};
+        GraphKey key{0, n, 0, (store.vals != nullptr ? 1 : 0) | (scan_mode() ? 2 : 0)};
         if (int r = launch_graph(key, slot0, pf0)) return r;
         for (int i = 0; i < n; i++) { stored[slot0 + i] = store.vals != nullptr; fwd_ok[slot0 + i] = 1; }
         stored[slot0 + n] = 0; fwd_ok[slot0 + n] = 0;

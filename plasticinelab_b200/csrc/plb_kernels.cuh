@@ -333,11 +333,61 @@ __global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimS
     }
 }
 
+// Forward grid stage in ONE kernel (single-GPU path with the forward-grid store): no separate compaction.  CTA c owns the
+// block ids c, c + G, c + 2G, ... ; it collects its flagged blocks in shared memory (clearing the flags), reserves store
+// entries for them with one atomic on the slot's counter (zeroed beforehand by k_set_cursor_zero / a memset), and runs the
+// grid operator on them.  The active-block list of the substep then exists only in the store (ids), which is all the backward
+// pass reads.  Replaces memset + k_compact + k_grid_fwd_sparse (3 graph nodes per forward substep) by one.
+constexpr int kScanCap = 2048;                  // flagged blocks one CTA can hold
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_grid_fwd_scan(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pf,
+                                                          Vec4<T>* grid_in, Vec4<T>* grid_out, unsigned char* flags, int n_blocks,
+                                                          GridStore<T> store, SlotRef slot) {
+    __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
+    __shared__ int s_blk[kScanCap];
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    load_poses_smem<T>(traj, pf.get(), P.n_prim, s0, s1);          // (ends with __syncthreads)
+    for (int b = blockIdx.x + threadIdx.x * gridDim.x; b < n_blocks; b += gridDim.x * blockDim.x)
+        if (flags[b]) {
+            flags[b] = 0;
+            s_blk[atomicAdd(&s_n, 1)] = b;
+        }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    const long long sl = slot.get();
+    if (threadIdx.x == 0) {
+        s_base = atomicAdd(store.cnt + sl, n);
+        if (s_base + n > store.cap) *store.overflow = 1;
+    }
+    __syncthreads();
+    const int base = s_base;
+    Vec4<T>* svals = store.vals + sl * store.cap * kBlkNodes;
+    int* sids = store.ids + sl * store.cap;
+    const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1);
+    for (int e = threadIdx.x / kBlkNodes; e < n; e += per_cta) {
+        const int blk = s_blk[e];
+        const long long node = block_node(P.n_grid, blk, local);
+        const int idx = base + e;
+        if (idx < store.cap) {
+            svals[(long long)idx * kBlkNodes + local] = grid_in[node];
+            if (local == 0) sids[idx] = blk;
+        }
+        grid_fwd_body<T>(node, P, prims, s0, s1, grid_in, grid_out, true);
+    }
+}
+// cursor + zeroed store counters of the n slots the coming forward graph fills
+__global__ void k_set_cursor_zero(int* cur, int a, int b, int c, int* cnt, int n) {
+    if (threadIdx.x == 0) { cur[0] = a; cur[1] = b; cur[2] = c; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cnt[a + i] = 0;
+}
+
 // backward: re-install the stored forward grid of `slot` (values + active list) instead of recomputing P2G
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_restore_blocks(int n_grid, Vec4<T>* grid_in, int* list, int* count, GridStore<T> store, SlotRef slot) {
     const long long sl = slot.get();
-    const int n = store.cnt[sl];
+    const int n = min(store.cnt[sl], store.cap);          // (-1 or > cap: overflow, flagged by the forward kernel)
     const Vec4<T>* svals = store.vals + sl * store.cap * kBlkNodes;
     const int* sids = store.ids + sl * store.cap;
     const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1);

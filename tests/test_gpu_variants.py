@@ -1,0 +1,66 @@
+"""GPU test: every selectable kernel variant of the engine produces the same episode (loss, action gradient, final state).
+
+The variants are chosen with environment switches read at plb_create (plb_engine.cu): tile shape of the scatter kernels
+(full 27-node tile / 9-node plane tile), register caps of the fused particle kernels, CTA size, the one-kernel forward grid
+stage and the forked grid pre-stage of the backward graphs.  The conservative configuration (everything serial, full tiles)
+is compared against the float64 oracle by tests/test_gpu_parity.py; here all other variants are compared with it on the
+same episode, in one process.  Tolerances: float64 1e-10 on the loss, 1e-7 on the gradient (summation order only), float32 1e-4 on the loss,
+2e-2 on the gradient (float32 summation-order noise through 27 substeps of contact dynamics).
+"""
+import numpy as np
+import pytest
+
+import plb_test_helpers as H
+from test_gpu_parity import _episode_cfg, _target32
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE"]
+VARIANTS = {
+    "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3),
+    "defaults": {},
+    "overlap": dict(PLB_BWD_OVERLAP=1),
+    "scan": dict(PLB_GRID_SCAN=1),
+    "plane": dict(PLB_FWD_PLANE=1, PLB_BWD_PLANE=1),
+    "tight": dict(PLB_FWD_MINB=6, PLB_BWD_MINB=4),
+    "cta64": dict(PLB_CTA=64),
+    "everything": dict(PLB_BWD_OVERLAP=1, PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6, PLB_BWD_PLANE=1, PLB_BWD_MINB=4, PLB_CTA=64),
+    "unfused": dict(PLB_FUSE=0),
+}
+
+
+def _run(monkeypatch, env_vars, dtype):
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.optimizer.solver import Solver
+    for k in KEYS:
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env_vars.items():
+        monkeypatch.setenv(k, str(v))
+    cfg = _episode_cfg()
+    env = TaichiEnv(cfg, dtype=dtype)
+    env.initialize()
+    env.loss.load_target_density(grids=_target32(env))
+    env.loss.set_weights(10, 10, 1, False)
+    actions = np.random.RandomState(1).uniform(-1, 1, (3, 6))
+    solver = Solver(env, None, None, n_iters=1, softness=666., horizon=3)
+    solver.total_steps = 0
+    loss, grad = solver.forward(env.get_state()['state'], actions)
+    x = env.simulator.get_state(env.simulator.cur)[0]
+    env.engine.close()
+    return loss, grad, x
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+def test_kernel_variants_agree(monkeypatch, dtype):
+    ref = _run(monkeypatch, VARIANTS["conservative"], dtype)
+    ltol, gtol, xtol = (1e-10, 1e-7, 1e-10) if dtype == 'float64' else (1e-4, 2e-2, 1e-5)
+    bad = []
+    for name, env_vars in VARIANTS.items():
+        if name == "conservative":
+            continue
+        loss, grad, x = _run(monkeypatch, env_vars, dtype)
+        dl, dg, dx = abs(loss - ref[0]) / abs(ref[0]), H.relerr(grad, ref[1]), float(np.abs(x - ref[2]).max())
+        print(f"[variants {dtype}] {name:12s} loss {dl:.2e} grad {dg:.2e} x {dx:.2e}")
+        if not (dl < ltol and dg < gtol and dx < xtol):
+            bad.append((name, dl, dg, dx))
+    assert not bad, bad
