@@ -180,6 +180,7 @@ struct Engine : plb_engine {
     bool bwd_plane = false;         // same for the backward scatter kernels (PLB_BWD_PLANE)
     int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
     int fwd_minb = 5, bwd_minb = 3; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 / PLB_BWD_MINB=4 select the tighter cap)
+    int flush_mode = 0;             // full-tile flush: 0 = per-cell groups, 1 = runs of consecutive lanes (PLB_FLUSH_RUNS=1)
     bool grid_scan = false;         // forward grid stage as one kernel (flag scan + store + grid operator), PLB_GRID_SCAN=1
     bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
                                     // particle kernel and grid adjoint of substep s (needs the second grid set; PLB_BWD_OVERLAP=0 disables)
@@ -285,6 +286,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_BWD_MINB")) bwd_minb = atoi(v);
         if (const char* v = getenv("PLB_BWD_OVERLAP")) bwd_overlap = atoi(v) != 0;
         if (const char* v = getenv("PLB_GRID_SCAN")) grid_scan = atoi(v) != 0;
+        if (const char* v = getenv("PLB_FLUSH_RUNS")) flush_mode = atoi(v) != 0 ? 1 : 0;
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
         if (tile_scatter) {
             const int full = (int)tile_smem_bytes(false, kBlock);
@@ -599,7 +601,7 @@ struct Engine : plb_engine {
             prof_begin(K_P2G);
             auto kern = fwd_plane ? (fwd_minb >= 6 ? k_g2p_p2g_warp<T, true, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, true, OccSel<T>::fwd_lo>)
                                   : (fwd_minb >= 6 ? k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>);
-            kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), grid_out, grid_in, fl);
+            kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), grid_out, grid_in, fl, flush_mode);
             prof_end();
             enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i));
             launches++;
@@ -649,8 +651,8 @@ struct Engine : plb_engine {
         if (tile_scatter) {
             const int nbc = blocks(cfg.n_particles, cta);
             const size_t sm = tile_smem_bytes(bwd_plane, cta);
-            if (bwd_plane) k_g2p_bwd_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out);
-            else k_g2p_bwd_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out);
+            if (bwd_plane) k_g2p_bwd_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode);
+            else k_g2p_bwd_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode);
         } else {
             k_g2p_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, gs.out, g_out);
         }
@@ -669,7 +671,7 @@ struct Engine : plb_engine {
         prof_begin(K_P2G_BWD);
         auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo>)
                               : (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo>);
-        kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out);
+        kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode);
         prof_end();
         launches++;
     }
@@ -749,8 +751,8 @@ struct Engine : plb_engine {
         if (tile_scatter) {
             const int nbc = blocks(cfg.n_particles, cta);
             const size_t sm = tile_smem_bytes(fwd_plane, cta);
-            if (fwd_plane) k_p2g_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
-            else k_p2g_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+            if (fwd_plane) k_p2g_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode);
+            else k_p2g_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode);
         } else {
             k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
         }

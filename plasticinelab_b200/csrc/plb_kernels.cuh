@@ -261,10 +261,10 @@ template <class T, bool kPlane> __device__ __forceinline__ Vec4<T>* warp_tile_pt
 
 template <class T, bool kPlane>
 __global__ void __launch_bounds__(kBlock) k_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
-                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
+                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     t_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
-                     frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in, flags);
+                     frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in, flags, flush_mode);
 }
 
 // G2P of substep s + P2G of substep s+1 in one pass over the particles (inside env-step graphs)
@@ -273,34 +273,34 @@ __global__ void __launch_bounds__(kBlock) k_p2g_warp(SimConst<T> P, T* frames, l
 template <class T, bool kPlane, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB) k_g2p_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in,
                                                                            SlotRef slot_mid, SlotRef slot_out, Material<T> mat,
-                                                                           const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags) {
+                                                                           const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags, int flush_mode) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     t_g2p_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                          frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_mid.get(), n_pad),
-                         frame_at(frames, slot_out.get(), n_pad), mat, grid_out, grid_in, flags);
+                         frame_at(frames, slot_out.get(), n_pad), mat, grid_out, grid_in, flags, flush_mode);
 }
 
 // g2p.grad; next_ok: slot_in + 1 holds the frame G2P produced from slot_in (clamp masks and gather sum are read from it)
 template <class T, bool kPlane>
 __global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, int next_ok,
-                                                                           T* adj_next, T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+                                                                           T* adj_next, T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int si = slot_in.get();
     FramePtr<T> fnext = frame_at(frames, si + 1, n_pad);
     t_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                          frame_at(frames, si, n_pad), next_ok ? &fnext : nullptr, frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad),
-                         grid_out, g_out);
+                         grid_out, g_out, flush_mode);
 }
 
 // p2g.grad of substep s + g2p.grad of substep s-1 (inside env-step graphs; frame s was produced by G2P(s-1) there)
 template <class T, bool kPlane, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
                                                                                    SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
-                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     t_p2g_bwd_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                                  frame_at(frames, slot_s.get(), n_pad), frame_at(frames, slot_prev.get(), n_pad), frame_at(adj_next, 0, n_pad),
-                                 frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out);
+                                 frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out, flush_mode);
 }
 
 template <class T>

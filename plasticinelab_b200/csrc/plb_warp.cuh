@@ -105,6 +105,55 @@ PLB_D void warp_tile_flush(const Pay* tile, int lane, int key, int n_grid, Pay* 
     warp_sync();
 }
 
+// Run-based flush: one pass over the 32 columns in lane order; a run = maximal stretch of consecutive lanes with the same
+// cell (after the spatial sort a warp is a few runs; for arbitrary order the result is still correct, the runs just get
+// short).  Lane q < 27 accumulates node q and adds the run's sum to the grid at the run's last column.  No per-cell
+// gather loop: ~7 instructions per column + ~15 per run.  Every column must be defined (lanes without a particle zero theirs).
+template <class Pay>
+PLB_D void warp_tile_flush_runs(const Pay* tile, int lane, int key, int n_grid, Pay* grid) {
+    warp_sync();
+    const int next = warp_shfl(key, (lane + 1) & 31);
+    const unsigned run_end = warp_ballot(lane == 31 || next != key);
+    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
+    const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
+    Pay acc;
+    pay_zero(acc);
+#pragma unroll 2
+    for (int c = 0; c < 32; c += 4) {
+        Pay v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = row[c + j];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            pay_acc(acc, v[j]);
+            if ((run_end >> (c + j)) & 1u) {                          // warp-uniform
+                const int rkey = warp_shfl(key, c + j);
+                if (lane < 27 && rkey >= 0)
+                    pay_red(grid + node_index(n_grid, (rkey >> 20) + oi, ((rkey >> 10) & 1023) + oj, (rkey & 1023) + ok), acc);
+                pay_zero(acc);
+            }
+        }
+    }
+    warp_sync();
+}
+// zero this lane's column (lanes without a particle, for the run-based flush)
+template <class Pay> PLB_D void tile_zero_column(Pay* tile, int lane) {
+    Pay z;
+    pay_zero(z);
+#pragma unroll
+    for (int q = 0; q < 27; q++) tile[q * kTileStride + lane] = z;
+}
+// mode 0: per-cell groups, mode 1: runs
+template <class Pay>
+PLB_D void warp_tile_flush_sel(Pay* tile, int lane, int key, int n_grid, Pay* grid, int mode) {
+    if (mode == 1) {
+        if (key < 0) tile_zero_column(tile, lane);
+        warp_tile_flush_runs(tile, lane, key, n_grid, grid);
+    } else {
+        warp_tile_flush(tile, lane, key, n_grid, grid);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ plane tile
 template <class T> struct WarpPlaneScatter {
     Vec4<T>* tile; Vec4<T>* grid;
@@ -148,29 +197,34 @@ namespace detail {
 constexpr int kBlkShiftW = 2;          // 4 nodes per active-block edge (same constant as plb_kernels.cuh)
 }
 
-// flags[] of the (up to 8) 4^3 blocks touched by the stencil of a particle at x
+// flags[] of the (up to 8) 4^3 blocks touched by the stencil of a particle at x.  Plain byte stores, no test-before-set: a
+// load of the flag would sit on the critical path (L2 latency, and the compiler cannot hoist it over the previous store); the
+// stores of a warp to one flag coalesce.  Along an axis the stencil (base .. base+2) stays in one block unless base % 4 >= 2.
 template <class T>
 PLB_HD void mark_blocks(const SimConst<T>& P, V3<T> x, unsigned char* flags) {
     const int nbx = P.n_grid >> detail::kBlkShiftW;
-    int b[3];
+    int lo[3], hi[3];
 #pragma unroll
-    for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    for (int d = 0; d < 3; d++) {
+        const int b = (int)(x[d] * P.inv_dx - T(0.5));
+        lo[d] = b >> detail::kBlkShiftW;
+        hi[d] = (b + 2) >> detail::kBlkShiftW;
+    }
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int c = 0; c < 2; c++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                int id = (((b[0] + 2 * a) >> detail::kBlkShiftW) * nbx + ((b[1] + 2 * c) >> detail::kBlkShiftW)) * nbx +
-                         ((b[2] + 2 * e) >> detail::kBlkShiftW);
-                if (!flags[id]) flags[id] = 1;
+                if ((a && hi[0] == lo[0]) || (c && hi[1] == lo[1]) || (e && hi[2] == lo[2])) continue;      // same block as a = 0 / c = 0 / e = 0
+                flags[((a ? hi[0] : lo[0]) * nbx + (c ? hi[1] : lo[1])) * nbx + (e ? hi[2] : lo[2])] = 1;
             }
 }
 
 // P2G of one substep
 template <class T, bool kPlane>
 PLB_D void t_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>& fout, bool store_F,
-                 const Material<T>& mat, Vec4<T>* grid_in, unsigned char* flags) {
+                 const Material<T>& mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode = 0) {
     const bool valid = p < P.n_particles;
     if (kPlane) {
         if (!valid) p = P.n_particles - 1;
@@ -189,25 +243,26 @@ PLB_D void t_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const Fra
             key = cell_key(x, P.inv_dx);
             if (flags) mark_blocks<T>(P, x, flags);
         }
-        warp_tile_flush(tile, lane, key, P.n_grid, grid_in);
+        warp_tile_flush_sel(tile, lane, key, P.n_grid, grid_in, flush_mode);
     }
 }
 
 // G2P of substep s (frame fin -> fmid) + P2G of substep s+1 (F from fmid, F' to fout), keyed on the ADVECTED position
 template <class T, bool kPlane>
 PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>& fmid,
-                     const FramePtr<T>& fout, const Material<T>& mat, const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags) {
+                     const FramePtr<T>& fout, const Material<T>& mat, const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags,
+                     int flush_mode = 0) {
     const bool valid = p < P.n_particles;
     if (kPlane) {
         if (!valid) p = P.n_particles - 1;
+        M3<T> F = load_F(fmid, p);                 // issued before the gather: the stores below may alias for the compiler
+        T mu, lam, ys;
+        load_material(P, mat, p, mu, lam, ys);
         V3<T> nx, nv; M3<T> nC;
         g2p_core<T>(P, load_x(fin, p), grid_out, nx, nv, nC);
         if (valid) store_xvC(fmid, p, nx, nv, nC);
         WarpPlaneScatter<T> sc{tile, grid_in, lane, valid ? cell_key(nx, P.inv_dx) : -1, P.n_grid};
         sc.init();
-        M3<T> F = load_F(fmid, p);
-        T mu, lam, ys;
-        load_material(P, mat, p, mu, lam, ys);
         M3<T> new_F;
         p2g_core<T, WarpPlaneScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
         if (valid) {
@@ -218,12 +273,12 @@ PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
         tile_init(tile, lane);
         int key = -1;
         if (valid) {
+            M3<T> F = load_F(fmid, p);             // issued before the gather: the stores below may alias for the compiler
+            T mu, lam, ys;
+            load_material(P, mat, p, mu, lam, ys);
             V3<T> nx, nv; M3<T> nC;
             g2p_core<T>(P, load_x(fin, p), grid_out, nx, nv, nC);
             store_xvC(fmid, p, nx, nv, nC);
-            M3<T> F = load_F(fmid, p);
-            T mu, lam, ys;
-            load_material(P, mat, p, mu, lam, ys);
             M3<T> new_F;
             WarpTileScatter<T> sc{tile, lane};
             p2g_core<T, WarpTileScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
@@ -231,14 +286,14 @@ PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
             key = cell_key(nx, P.inv_dx);
             if (flags) mark_blocks<T>(P, nx, flags);
         }
-        warp_tile_flush(tile, lane, key, P.n_grid, grid_in);
+        warp_tile_flush_sel(tile, lane, key, P.n_grid, grid_in, flush_mode);
     }
 }
 
 // g2p.grad of one substep (state frame fin; fnext = the frame G2P produced, or null pointers => recompute the gather sum)
 template <class T, bool kPlane>
 PLB_D void t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>* fnext,
-                     const FramePtr<T>& adj_next, const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out) {
+                     const FramePtr<T>& adj_next, const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0) {
     const bool valid = p < P.n_particles;
     if (kPlane) {
         if (!valid) p = P.n_particles - 1;
@@ -273,7 +328,7 @@ PLB_D void t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
             adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
             key = cell_key(x, P.inv_dx);
         }
-        warp_tile_flush(tile, lane, key, P.n_grid, g_out);
+        warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode);
     }
 }
 
@@ -282,7 +337,7 @@ PLB_D void t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
 template <class T, bool kPlane>
 PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fs, const FramePtr<T>& fprev,
                              const FramePtr<T>& next, const FramePtr<T>& cur, const Material<T>& mat, const Vec4<T>* g_in,
-                             const Vec4<T>* grid_out, Vec4<T>* g_out) {
+                             const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0) {
     const bool valid = p < P.n_particles;
     if (kPlane) {
         if (!valid) p = P.n_particles - 1;
@@ -319,7 +374,7 @@ PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& 
             next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
             key = cell_key(xp, P.inv_dx);
         }
-        warp_tile_flush(tile, lane, key, P.n_grid, g_out);
+        warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode);
     }
 }
 

@@ -81,7 +81,7 @@ template <class T> struct World {
 template <class T, bool kPlane>
 int check(const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x, const double* v, const double* F,
           const double* C, const double* pose0, const double* pose1, const double* gx, const double* gv, const double* gF,
-          const double* gC, int stored_next, double* out) {
+          const double* gC, int stored_next, int flush_mode, double* out) {
     World<T> R(*c, pd, softness, pose0, pose1), W(*c, pd, softness, pose0, pose1);
     const int n = c->n_particles;
     const int tile_elems = kPlane ? kPlaneVec4 : kTileVec4;
@@ -119,7 +119,7 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     W.pack(W.f[0], x, v, F, C);
     // (1) P2G of substep 0
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), true, W.mat, W.grid_in.data(), W.flags.data());
+        t_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), true, W.mat, W.grid_in.data(), W.flags.data(), flush_mode);
     });
     out[o++] = rel_dev(W.grid_in, ref_in0);
     {   // flags: exactly the blocks touched by a particle stencil
@@ -130,7 +130,7 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     W.grid_op(W.grid_out[0]);
     // (2) fused G2P(0) + P2G(1)
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_g2p_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), W.fr(2), W.mat, W.grid_out[0].data(), W.grid_in.data(), nullptr);
+        t_g2p_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), W.fr(2), W.mat, W.grid_out[0].data(), W.grid_in.data(), nullptr, flush_mode);
     });
     out[o++] = rel_dev(W.grid_in, ref_in1);
     out[o++] = rel_dev(W.f[1].data(), R.f[1].data(), W.f[1].size());
@@ -145,14 +145,14 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     W.pack(W.adj[2], gx, gv, gF, gC);
     FramePtr<T> wf2 = W.fr(2);
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_g2p_bwd<T, kPlane>(p, lane, tile, W.P, W.fr(1), stored_next ? &wf2 : nullptr, W.ad(2), W.ad(1), W.grid_out[1].data(), W.g_out.data());
+        t_g2p_bwd<T, kPlane>(p, lane, tile, W.P, W.fr(1), stored_next ? &wf2 : nullptr, W.ad(2), W.ad(1), W.grid_out[1].data(), W.g_out.data(), flush_mode);
     });
     out[o++] = rel_dev(W.g_out, ref_gout1);
     out[o++] = rel_dev(W.adj[1].data(), ref_adj1_partial.data(), W.adj[1].size());
     W.grid_adj(ref_in1);
     // (4) fused p2g.grad(1) + g2p.grad(0)
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_p2g_bwd_g2p_bwd<T, kPlane>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data());
+        t_p2g_bwd_g2p_bwd<T, kPlane>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode);
     });
     out[o++] = rel_dev(W.g_out, ref_gout0);
     {   // dF[1] (F planes of adj 1) and the partial x-adjoint of frame 0 (written into adj 2's A0 plane)
@@ -182,10 +182,10 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
 
 extern "C" int wemul_check(int dtype, int plane, const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x,
                            const double* v, const double* F, const double* C, const double* pose0, const double* pose1, const double* gx,
-                           const double* gv, const double* gF, const double* gC, int stored_next, double* out) {
+                           const double* gv, const double* gF, const double* gC, int stored_next, int flush_mode, double* out) {
     if (dtype == PLB_F32)
-        return plane ? check<float, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, out)
-                     : check<float, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, out);
-    return plane ? check<double, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, out)
-                 : check<double, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, out);
+        return plane ? check<float, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out)
+                     : check<float, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out);
+    return plane ? check<double, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out)
+                 : check<double, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out);
 }

@@ -15,7 +15,7 @@ from test_gpu_parity import _episode_cfg, _target32
 
 pytestmark = pytest.mark.gpu
 
-KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE"]
+KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS"]
 VARIANTS = {
     "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3),
     "defaults": {},
@@ -26,6 +26,8 @@ VARIANTS = {
     "cta64": dict(PLB_CTA=64),
     "everything": dict(PLB_BWD_OVERLAP=1, PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6, PLB_BWD_PLANE=1, PLB_BWD_MINB=4, PLB_CTA=64),
     "unfused": dict(PLB_FUSE=0),
+    "runs": dict(PLB_FLUSH_RUNS=1),
+    "runs_unfused_cta64": dict(PLB_FLUSH_RUNS=1, PLB_FUSE=0, PLB_CTA=64),
 }
 
 

@@ -13,21 +13,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA"]
+KEYS = ["PLB_FLUSH_RUNS", "PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA"]
 VARIANTS = [
-    ("base100k", "move100k", dict(PLB_BWD_OVERLAP=0)),
-    ("ovl100k", "move100k", dict()),
-    ("scan100k", "move100k", dict(PLB_GRID_SCAN=1)),
-    ("plane6", "move100k", dict(PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6)),
-    ("plane5", "move100k", dict(PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=5)),
-    ("plane6c64", "move100k", dict(PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6, PLB_CTA=64)),
-    ("bwdplane4", "move100k", dict(PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6, PLB_BWD_PLANE=1, PLB_BWD_MINB=4)),
-    ("base1m", "move1m", dict(PLB_BWD_OVERLAP=0)),
-    ("new1m", "move1m", dict(PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6)),
-    ("new1m_b4", "move1m", dict(PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6, PLB_BWD_PLANE=1, PLB_BWD_MINB=4)),
-    ("full6", "move100k", dict(PLB_GRID_SCAN=1, PLB_FWD_MINB=6)),
-    ("bwdplane3", "move100k", dict(PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6, PLB_BWD_PLANE=1, PLB_BWD_MINB=3)),
-    ("full_c64", "move100k", dict(PLB_GRID_SCAN=1, PLB_CTA=64)),
+    ("def100k", "move100k", dict()),
+    ("runs100k", "move100k", dict(PLB_FLUSH_RUNS=1)),
+    ("runs6", "move100k", dict(PLB_FLUSH_RUNS=1, PLB_FWD_MINB=6)),
+    ("def6", "move100k", dict(PLB_FWD_MINB=6)),
+    ("noovl", "move100k", dict(PLB_BWD_OVERLAP=0)),
+    ("def1m", "move1m", dict()),
+    ("runs1m", "move1m", dict(PLB_FLUSH_RUNS=1)),
+    ("runs1m6", "move1m", dict(PLB_FLUSH_RUNS=1, PLB_FWD_MINB=6)),
+    ("runs_c64", "move100k", dict(PLB_FLUSH_RUNS=1, PLB_CTA=64)),
+    ("scan_runs", "move100k", dict(PLB_FLUSH_RUNS=1, PLB_GRID_SCAN=1)),
 ]
 
 

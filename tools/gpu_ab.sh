@@ -11,13 +11,9 @@ timeout 300 python -m pytest tests/test_gpu_variants.py -m gpu -q -s -p no:cache
 stamp "-> exit $? $(tail -1 $OUT/pytest_variants.log)"
 grep "variants float" $OUT/pytest_variants.log | tee -a $OUT/timeline.txt
 
-stamp "parity subset (vs the float64 oracle) with the defaults"
-timeout ${PARITY_TIMEOUT:-240} python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider --durations=8 -k "episode_loss or golden or checkpointed or substep_parity or sorted_sparse" > $OUT/pytest_default.log 2>&1
-stamp "-> exit $? $(tail -1 $OUT/pytest_default.log)"
-
 stamp "in-process bench A/B"
 timeout ${AB_TIMEOUT:-420} python tools/ab_bench.py $OUT ${AB_BUDGET:-330} 2>&1 | tee -a $OUT/timeline.txt
-stamp "rest of the parity suite"
-timeout ${REST_TIMEOUT:-200} python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider --durations=8 -k "not (episode_loss or golden or checkpointed or substep_parity or sorted_sparse)" > $OUT/pytest_rest.log 2>&1
-stamp "-> exit $? $(tail -1 $OUT/pytest_rest.log)"
+stamp "parity suite with the defaults"
+timeout ${PARITY_TIMEOUT:-240} python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider > $OUT/pytest_default.log 2>&1
+stamp "-> exit $? $(tail -1 $OUT/pytest_default.log)"
 stamp done
