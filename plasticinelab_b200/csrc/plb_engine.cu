@@ -296,6 +296,15 @@ struct Engine : plb_engine {
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
             PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
             PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            // the full tiles want the whole shared-memory carve-out (4 x 57 KB per SM); the driver's default choice left the
+            // backward kernel at 3 CTAs per SM by shared memory (ncu launch__occupancy_limit_shared_mem)
+            const int carve = cudaSharedmemCarveoutMaxShared;
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_warp<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         }
         n_blocks = (c.n_grid / 4) * (c.n_grid / 4) * (c.n_grid / 4);
         PLB_CUDA(cudaMalloc(&d_flags, n_blocks));

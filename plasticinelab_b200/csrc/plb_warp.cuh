@@ -33,6 +33,20 @@ PLB_D int ctz32(unsigned g) { return __clz(__brev(g)); }          // 32 for g ==
 #endif
 // (host: tests/host/warp_emul.hpp defines the same six functions before this header is included)
 
+// L2 prefetch of the line holding *p (no-op on the host).  The backward particle kernel of substep s uses it on the frame of
+// substep s-1, which the NEXT kernel reads from HBM first thing (12 % of the fused backward kernel's stall samples sat on
+// those first loads, profiles/r1b_move100k_ncu_stall_hotspots.txt).
+#if defined(__CUDACC__)
+PLB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+inline void prefetch_l2(const void*) {}
+#endif
+// every plane of frame f at particle p except A0 (the fused backward kernel reads A0 of that frame itself)
+template <class T> PLB_D void prefetch_frame_rest(const FramePtr<T>& f, int p) {
+    prefetch_l2(f.A1 + p); prefetch_l2(f.A2 + p); prefetch_l2(f.a3 + p); prefetch_l2(f.a4 + p); prefetch_l2(f.a5 + p);
+    prefetch_l2(f.B0 + p); prefetch_l2(f.B1 + p); prefetch_l2(f.b2 + p);
+}
+
 constexpr int kTileStride = 33;
 constexpr int kNullCol = 32;
 constexpr int kTileVec4 = 27 * kTileStride;
@@ -339,6 +353,7 @@ PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& 
                              const FramePtr<T>& next, const FramePtr<T>& cur, const Material<T>& mat, const Vec4<T>* g_in,
                              const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0) {
     const bool valid = p < P.n_particles;
+    if (valid) prefetch_frame_rest(fprev, p);          // for the next backward kernel (p2g.grad of substep s-1)
     if (kPlane) {
         if (!valid) p = P.n_particles - 1;
         V3<T> x, v; M3<T> C;

@@ -16,15 +16,12 @@ import bench  # noqa: E402
 KEYS = ["PLB_FLUSH_RUNS", "PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA"]
 VARIANTS = [
     ("def100k", "move100k", dict()),
-    ("runs100k", "move100k", dict(PLB_FLUSH_RUNS=1)),
-    ("runs6", "move100k", dict(PLB_FLUSH_RUNS=1, PLB_FWD_MINB=6)),
-    ("def6", "move100k", dict(PLB_FWD_MINB=6)),
-    ("noovl", "move100k", dict(PLB_BWD_OVERLAP=0)),
+    ("bwd4", "move100k", dict(PLB_BWD_MINB=4)),
     ("def1m", "move1m", dict()),
-    ("runs1m", "move1m", dict(PLB_FLUSH_RUNS=1)),
-    ("runs1m6", "move1m", dict(PLB_FLUSH_RUNS=1, PLB_FWD_MINB=6)),
-    ("runs_c64", "move100k", dict(PLB_FLUSH_RUNS=1, PLB_CTA=64)),
-    ("scan_runs", "move100k", dict(PLB_FLUSH_RUNS=1, PLB_GRID_SCAN=1)),
+    ("bwd4_1m", "move1m", dict(PLB_BWD_MINB=4)),
+    ("fwd6_bwd4", "move100k", dict(PLB_FWD_MINB=6, PLB_BWD_MINB=4)),
+    ("c64", "move100k", dict(PLB_CTA=64)),
+    ("c64_1m", "move1m", dict(PLB_CTA=64)),
 ]
 
 

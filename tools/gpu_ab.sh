@@ -13,7 +13,4 @@ grep "variants float" $OUT/pytest_variants.log | tee -a $OUT/timeline.txt
 
 stamp "in-process bench A/B"
 timeout ${AB_TIMEOUT:-420} python tools/ab_bench.py $OUT ${AB_BUDGET:-330} 2>&1 | tee -a $OUT/timeline.txt
-stamp "parity suite with the defaults"
-timeout ${PARITY_TIMEOUT:-240} python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider > $OUT/pytest_default.log 2>&1
-stamp "-> exit $? $(tail -1 $OUT/pytest_default.log)"
 stamp done
