@@ -490,6 +490,7 @@ def main():
                             f"; loss scalars / pose gradients all-reduced over NCCL; bounds {senv.bounds}") if slab
                            else f"{world} independent replicas (one env per GPU)"),
                        "n_particles_global": N_global, "scaling_reference": n1_reference,
+                       "kernel_switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("PLB_")} or "defaults",
                        "l2": "inputs larger than L2: every substep reads a different trajectory frame "
                              f"({(H * S + 1) * 96 * N / 1e9:.1f} GB trajectory per episode)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
