@@ -181,6 +181,7 @@ struct Engine : plb_engine {
     int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
     int fwd_minb = 5, bwd_minb = 3; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 / PLB_BWD_MINB=4 select the tighter cap)
     int flush_mode = 0;             // full-tile flush: 0 = per-cell groups, 1 = runs of consecutive lanes (PLB_FLUSH_RUNS=1)
+    bool grid_bwd_v2 = false;       // grid adjoint with register-resident pose gradients (k_grid_bwd_sparse_v2), PLB_GRID_BWD_V2=1
     bool grid_scan = false;         // forward grid stage as one kernel (flag scan + store + grid operator), PLB_GRID_SCAN=1
     bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
                                     // particle kernel and grid adjoint of substep s (needs the second grid set; PLB_BWD_OVERLAP=0 disables)
@@ -287,6 +288,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_BWD_OVERLAP")) bwd_overlap = atoi(v) != 0;
         if (const char* v = getenv("PLB_GRID_SCAN")) grid_scan = atoi(v) != 0;
         if (const char* v = getenv("PLB_FLUSH_RUNS")) flush_mode = atoi(v) != 0 ? 1 : 0;
+        if (const char* v = getenv("PLB_GRID_BWD_V2")) grid_bwd_v2 = atoi(v) != 0;
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
         if (tile_scatter) {
             const int full = (int)tile_smem_bytes(false, kBlock);
@@ -648,7 +650,9 @@ struct Engine : plb_engine {
             halo_add_inbox(g_out);
             launches += 6;
         }
-        if (sparse)
+        if (sparse && grid_bwd_v2)
+            k_grid_bwd_sparse_v2<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());
+        else if (sparse)
             k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());
         else
             k_grid_bwd<T><<<ng, kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, n_nodes);

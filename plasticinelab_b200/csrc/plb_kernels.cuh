@@ -431,6 +431,32 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse(SimConst<T> P, PrimS
     }
 }
 
+// same operator, pose gradients of one primitive at a time in registers (t_grid_bwd_node, plb_warp.cuh): no per-thread
+// PoseGrad arrays in local memory, float warp reduction, one pass
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse_v2(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pfr,
+                                                               Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, int clear,
+                                                               double* prim_grad, const int* __restrict__ list,
+                                                               const int* __restrict__ count, int own_lo, int own_hi) {
+    __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
+    const int pf = pfr.get();
+    load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
+    const int per_cta = kBlock / kBlkNodes, n = *count;
+    const int rounds = (n + gridDim.x * per_cta - 1) / (gridDim.x * per_cta);
+    for (int r = 0; r < rounds; r++) {              // uniform trip count: warp collectives inside
+        const int e = (r * gridDim.x + blockIdx.x) * per_cta + threadIdx.x / kBlkNodes;
+        const bool act = e < n;
+        long long node = 0;
+        bool owned = false;
+        if (act) {
+            node = block_node(P.n_grid, list[e], threadIdx.x & (kBlkNodes - 1));
+            const int plane = (int)(node / ((long long)P.n_grid * P.n_grid));
+            owned = plane >= own_lo && plane < own_hi;
+        }
+        t_grid_bwd_node<T>(act, owned, node, threadIdx.x & 31, P, prims, s0, s1, grid_in, g_out, g_in, clear != 0, prim_grad, pf);
+    }
+}
+
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_grid_fwd(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pf,
                                                      Vec4<T>* grid_in, Vec4<T>* grid_out, int clear_in, long long n_nodes) {

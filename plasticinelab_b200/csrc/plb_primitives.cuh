@@ -104,7 +104,7 @@ template <class T> PLB_HD V3<T> capsule_p2(T h, V3<T> q, T& dy) {
     return mk3<T>(q.x, y0 - cl, q.z);
 }
 
-template <class T> PLB_HD T local_sdf(const PrimStatic<T>& ps, T gap, V3<T> q) {
+template <class T> PLB_HD_NOINLINE T local_sdf(PrimStatic<T> ps, T gap, V3<T> q) {
     switch (ps.type) {
     case PRIM_CAPSULE: case PRIM_ROLLINGPIN: {
         T dy; V3<T> p2 = capsule_p2(ps.p[0], q, dy);
@@ -138,7 +138,7 @@ template <class T> PLB_HD T local_sdf(const PrimStatic<T>& ps, T gap, V3<T> q) {
 template <class T> PLB_HD T sgn0(T x) { return x > T(0) ? T(1) : (x < T(0) ? T(-1) : T(0)); }
 
 // gradient of local_sdf wrt q, scaled by g; also d/d gap (chopsticks)
-template <class T> PLB_HD V3<T> local_sdf_vjp(const PrimStatic<T>& ps, T gap, V3<T> q, T g, T& ggap) {
+template <class T> PLB_HD_NOINLINE V3<T> local_sdf_vjp(PrimStatic<T> ps, T gap, V3<T> q, T g, T& ggap) {
     switch (ps.type) {
     case PRIM_CAPSULE: case PRIM_ROLLINGPIN: {
         T dy; V3<T> p2 = capsule_p2(ps.p[0], q, dy);
@@ -199,7 +199,7 @@ template <class T> PLB_HD V3<T> local_sdf_vjp(const PrimStatic<T>& ps, T gap, V3
     }
 }
 
-template <class T> PLB_HD V3<T> local_normal(const PrimStatic<T>& ps, T gap, V3<T> q) {
+template <class T> PLB_HD_NOINLINE V3<T> local_normal(PrimStatic<T> ps, T gap, V3<T> q) {
     switch (ps.type) {
     case PRIM_CAPSULE: case PRIM_ROLLINGPIN: {
         T dy; V3<T> p2 = capsule_p2(ps.p[0], q, dy);
@@ -248,7 +248,7 @@ template <class T> PLB_HD V3<T> local_normal(const PrimStatic<T>& ps, T gap, V3<
 }
 
 // adjoint of local_normal wrt q (and gap)
-template <class T> PLB_HD V3<T> local_normal_vjp(const PrimStatic<T>& ps, T gap, V3<T> q, V3<T> gn, T& ggap) {
+template <class T> PLB_HD_NOINLINE V3<T> local_normal_vjp(PrimStatic<T> ps, T gap, V3<T> q, V3<T> gn, T& ggap) {
     switch (ps.type) {
     case PRIM_CAPSULE: case PRIM_ROLLINGPIN: {
         T dy; V3<T> p2 = capsule_p2(ps.p[0], q, dy);

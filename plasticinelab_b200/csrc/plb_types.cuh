@@ -13,9 +13,13 @@
 #if defined(__CUDACC__)
 #define PLB_HD __host__ __device__ __forceinline__
 #define PLB_D __device__ __forceinline__
+// out-of-line on the device: the shape switches of the non-spherical primitives, so that the grid kernels (a handful of
+// resident warps, instruction-fetch bound) keep a compact hot path instead of ~25 inlined copies of every shape
+#define PLB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define PLB_HD inline
 #define PLB_D inline
+#define PLB_HD_NOINLINE inline
 #endif
 
 namespace plb {

@@ -28,10 +28,13 @@ PLB_D unsigned warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 PLB_D int warp_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 PLB_D float warp_shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 PLB_D double warp_shfl_down(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+PLB_D float warp_shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+PLB_D double warp_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 PLB_D void warp_sync() { __syncwarp(); }
 PLB_D int ctz32(unsigned g) { return __clz(__brev(g)); }          // 32 for g == 0
+PLB_D void atomic_add_f64(double* dst, double v) { atomicAdd(dst, v); }
 #endif
-// (host: tests/host/warp_emul.hpp defines the same six functions before this header is included)
+// (host: tests/host/warp_emul.hpp defines the same functions before this header is included)
 
 // L2 prefetch of the line holding *p (no-op on the host).  The backward particle kernel of substep s uses it on the frame of
 // substep s-1, which the NEXT kernel reads from HBM first thing (12 % of the fused backward kernel's stall samples sat on
@@ -411,6 +414,74 @@ PLB_D void t_loss_mass(int p, int lane, T* tile, const SimConst<T>& P, const Fra
                     tile[((i * 3 + j) * 3 + k) * kTileStride + lane] = st.w[i][0] * st.w[j][1] * st.w[k][2] * P.p_mass;
     }
     warp_tile_flush(tile, lane, key, P.n_grid, grid_mass);
+}
+
+// ================================================================================================
+// grid_op.grad for one node per thread with the pose gradients of ONE primitive at a time in registers
+// (k_grid_bwd_sparse_v2).  The array form (grid_bwd_body: PoseGrad g0[8], g1[8] per thread, reduced after the node) keeps
+// 128 floats per thread in local memory; here each primitive's pair is warp-reduced right after its collide adjoint and
+// added to the global pose gradient with double atomics from lane 0.  All 32 lanes must call (warp collectives inside the
+// uniform loop over primitives); `act` = this thread has a node, `owned` = its pose gradients count on this rank (slab).
+// ================================================================================================
+template <class T>
+PLB_D void reduce_pose_grad_T(const PoseGrad<T>& g, int lane, double* dst) {
+    T vals[8] = {g.pos.x, g.pos.y, g.pos.z, g.rot.w, g.rot.x, g.rot.y, g.rot.z, g.gap};
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        T s = vals[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += warp_shfl_xor(s, o);
+        if (lane == 0 && s != T(0)) atomic_add_f64(dst + c, (double)s);
+    }
+}
+
+template <class T>
+PLB_D void t_grid_bwd_node(bool act, bool owned, long long node, int lane, const SimConst<T>& P, const PrimSet<T>& prims, const Pose<T>* s0,
+                           const Pose<T>* s1, Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, bool clear, double* prim_grad, int pf) {
+    Vec4<T> in4 = mk4<T>(T(0), T(0), T(0), T(0)), go = in4;
+    int ix = 0, iy = 0, iz = 0;
+    if (act) {
+        in4 = grid_in[node];
+        go = g_out[node];
+        const int n = P.n_grid;
+        iz = (int)(node % n); iy = (int)((node / n) % n); ix = (int)(node / ((long long)n * n));
+    }
+    const bool live = act && (in4.w > T(1e-12));
+    V3<T> vstack[PLB_MAX_PRIM];
+    V3<T> g = zero3<T>(), gpos = zero3<T>(), vin = mk3<T>(in4.x, in4.y, in4.z);
+    T inv_m = T(0);
+    if (live) {
+        inv_m = T(1) / in4.w;
+        V3<T> v = mk3<T>(inv_m * in4.x + P.grav_dv[0], inv_m * in4.y + P.grav_dv[1], inv_m * in4.z + P.grav_dv[2]);
+        gpos = mk3<T>(T(ix) * P.dx, T(iy) * P.dx, T(iz) * P.dx);
+        for (int k = 0; k < P.n_prim; k++) {
+            vstack[k] = v;
+            bool taken;
+            v = prim_collide(prims.s[k], s0[k], s1[k], gpos, v, P.dt, taken);
+        }
+        BoundaryTape<T> tape;
+        boundary_forward<T>(P, ix, iy, iz, v, &tape);
+        g = boundary_backward<T>(P, ix, iy, iz, tape, mk3<T>(go.x, go.y, go.z));
+    }
+    for (int k = P.n_prim - 1; k >= 0; k--) {                 // uniform trip count
+        PoseGrad<T> g0, g1;
+        g0.clear(); g1.clear();
+        bool taken = false;
+        if (live) g = prim_collide_bwd(prims.s[k], s0[k], s1[k], gpos, vstack[k], P.dt, g, g0, g1, taken);
+        const bool contrib = taken && owned;
+        if (warp_ballot(contrib) == 0u) continue;
+        if (!contrib) { g0.clear(); g1.clear(); }
+        reduce_pose_grad_T<T>(g0, lane, prim_grad + ((long long)pf * PLB_MAX_PRIM + k) * PLB_POSE_DIM);
+        reduce_pose_grad_T<T>(g1, lane, prim_grad + ((long long)(pf + 1) * PLB_MAX_PRIM + k) * PLB_POSE_DIM);
+    }
+    if (act) {
+        // v = inv_m * v_in + const ; inv_m = 1 / m
+        g_in[node] = live ? mk4<T>(inv_m * g.x, inv_m * g.y, inv_m * g.z, -dot(g, vin) * inv_m * inv_m) : mk4<T>(T(0), T(0), T(0), T(0));
+        if (clear) {
+            if (in4.x != T(0) || in4.y != T(0) || in4.z != T(0) || in4.w != T(0)) grid_in[node] = mk4<T>(T(0), T(0), T(0), T(0));
+            if (go.x != T(0) || go.y != T(0) || go.z != T(0)) g_out[node] = mk4<T>(T(0), T(0), T(0), T(0));
+        }
+    }
 }
 
 }  // namespace plb

@@ -178,6 +178,59 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     return o;
 }
 
+// grid adjoint: t_grid_bwd_node on emulated warps (32 consecutive nodes per warp) vs the array form grid_bwd_body
+template <class T>
+int check_grid_bwd(const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x, const double* v, const double* F,
+                   const double* C, const double* pose0, const double* pose1, const double* gout4, double* out) {
+    World<T> R(*c, pd, softness, pose0, pose1), W(*c, pd, softness, pose0, pose1);
+    const int n = c->n_particles, np = c->n_primitives;
+    for (World<T>* w : {&R, &W}) {
+        w->pack(w->f[0], x, v, F, C);
+        for (int p = 0; p < n; p++) p2g_body<T>(p, w->P, w->fr(0), w->fr(1), true, w->mat, w->grid_in.data());
+        for (long long i = 0; i < w->n_nodes; i++)
+            w->g_out[i] = mk4<T>((T)gout4[i * 4], (T)gout4[i * 4 + 1], (T)gout4[i * 4 + 2], T(0));
+    }
+    std::vector<double> ref(2 * PLB_MAX_PRIM * 8, 0.0), got(2 * PLB_MAX_PRIM * 8, 0.0);
+    for (long long node = 0; node < R.n_nodes; node++) {
+        PoseGrad<T> g0[PLB_MAX_PRIM], g1[PLB_MAX_PRIM];
+        for (int k = 0; k < np; k++) { g0[k].clear(); g1[k].clear(); }
+        unsigned touched = 0;
+        grid_bwd_body<T>(node, R.P, R.prims, R.s0, R.s1, R.grid_in.data(), R.g_out.data(), R.g_in.data(), true, g0, g1, touched);
+        for (int k = 0; k < np; k++) {
+            if (!((touched >> k) & 1u)) continue;
+            const PoseGrad<T>* gg[2] = {&g0[k], &g1[k]};
+            for (int w = 0; w < 2; w++) {
+                double* d = ref.data() + ((size_t)w * PLB_MAX_PRIM + k) * 8;
+                d[0] += gg[w]->pos.x; d[1] += gg[w]->pos.y; d[2] += gg[w]->pos.z; d[3] += gg[w]->rot.w; d[4] += gg[w]->rot.x;
+                d[5] += gg[w]->rot.y; d[6] += gg[w]->rot.z; d[7] += gg[w]->gap;
+            }
+        }
+    }
+    // only warps that contain an active node are emulated (the rest return zeros by construction: no mass -> no gradient)
+    for (long long w0 = 0; w0 < W.n_nodes; w0 += 32) {
+        bool any = false;
+        for (int l = 0; l < 32 && w0 + l < W.n_nodes; l++) any = any || W.grid_in[w0 + l].w != T(0) || W.g_out[w0 + l].x != T(0) || W.g_out[w0 + l].y != T(0) || W.g_out[w0 + l].z != T(0);
+        if (!any) continue;
+        run_warp([&](int lane) {
+            const long long node = w0 + lane;
+            t_grid_bwd_node<T>(node < W.n_nodes, true, node, lane, W.P, W.prims, W.s0, W.s1, W.grid_in.data(), W.g_out.data(), W.g_in.data(), true,
+                               got.data(), 0);
+        });
+    }
+    int o = 0;
+    out[o++] = rel_dev(W.g_in, R.g_in);
+    out[o++] = rel_dev(got.data(), ref.data(), got.size());
+    {   // both cleared grid_in / g_out
+        double m = 0;
+        for (long long i = 0; i < W.n_nodes; i++) m = std::max({m, std::fabs((double)W.grid_in[i].w), std::fabs((double)W.g_out[i].x), std::fabs((double)W.g_out[i].y), std::fabs((double)W.g_out[i].z)});
+        out[o++] = m;
+    }
+    double nrm = 0;
+    for (double r : ref) nrm = std::max(nrm, std::fabs(r));
+    out[o++] = nrm;                 // (reported so the test can insist that the contact branch actually ran)
+    return o;
+}
+
 }  // namespace
 
 extern "C" int wemul_check(int dtype, int plane, const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x,
@@ -188,4 +241,10 @@ extern "C" int wemul_check(int dtype, int plane, const plb_config* c, const plb_
                      : check<float, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out);
     return plane ? check<double, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out)
                  : check<double, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out);
+}
+
+extern "C" int wemul_check_grid_bwd(int dtype, const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x, const double* v,
+                                    const double* F, const double* C, const double* pose0, const double* pose1, const double* gout4, double* out) {
+    return dtype == PLB_F32 ? check_grid_bwd<float>(c, pd, softness, x, v, F, C, pose0, pose1, gout4, out)
+                            : check_grid_bwd<double>(c, pd, softness, x, v, F, C, pose0, pose1, gout4, out);
 }

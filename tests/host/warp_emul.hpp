@@ -54,6 +54,17 @@ inline double warp_shfl_down(double v, int d) {
     return r;
 }
 inline float warp_shfl_down(float v, int d) { return (float)warp_shfl_down((double)v, d); }
+inline double warp_shfl_xor(double v, int m) {
+    EmulWarp* w = tl_warp;
+    w->dval[tl_lane] = v;
+    w->bar.arrive_and_wait();
+    double r = w->dval[(tl_lane ^ m) & 31];
+    w->bar.arrive_and_wait();
+    return r;
+}
+inline float warp_shfl_xor(float v, int m) { return (float)warp_shfl_xor((double)v, m); }
+inline std::mutex& emul_atomic_mutex() { static std::mutex m; return m; }
+inline void atomic_add_f64(double* dst, double v) { std::lock_guard<std::mutex> lock(emul_atomic_mutex()); *dst += v; }
 inline void warp_sync() { tl_warp->bar.arrive_and_wait(); }
 inline int ctz32(unsigned g) { return g ? __builtin_ctz(g) : 32; }
 

@@ -64,3 +64,26 @@ def test_warp_scatter_kernels_match_direct_bodies(wemul_lib, plane, flush_mode, 
     assert k == len(NAMES)
     for name, dev in zip(NAMES, out[:k]):
         assert dev <= tol, f"{name}: deviation {dev:.3e} (plane={plane}, flush_mode={flush_mode}, {dtype})"
+
+
+@pytest.mark.parametrize('dtype,tol', [('float64', 1e-12), ('float32', 2e-5)])
+@pytest.mark.parametrize('prims', ['spheres', 'capsule', 'box', 'chopsticks'])
+def test_grid_adjoint_register_form_matches_array_form(wemul_lib, dtype, tol, prims):
+    """k_grid_bwd_sparse_v2's per-thread function (pose gradients of one primitive at a time in registers, float warp
+    reduction) against grid_bwd_body (PoseGrad arrays), on the grid a random particle state scatters."""
+    from test_host_emulation import PRIM_SETS, _poses
+    from oracle import plb_oracle as O
+    n = 200
+    cfg = H.small_cfg(PRIM_SETS[prims], n_particles=n, yield_stress=30.0, ground_friction=1.5)
+    conf, parr, _ = H.c_setup(cfg, n, dtype)
+    x, v, Cm, F = (np.ascontiguousarray(a) for a in H.random_state(n, 1, 0.35, 0.65))
+    osim = O.OracleSim(dict(cfg.SIMULATOR), [dict(p) for p in cfg.PRIMITIVES])
+    pose0, pose1 = _poses(osim, 1)
+    gout = np.ascontiguousarray(np.random.RandomState(9).randn(conf.n_grid ** 3, 4))
+    out = np.full(8, np.nan)
+    k = wemul_lib.wemul_check_grid_bwd(conf.dtype, C.byref(conf), parr, C.c_double(666.0), D(x), D(v), D(F), D(Cm), D(pose0), D(pose1), D(gout), D(out))
+    assert k == 4
+    assert out[3] > 0, "no node took the contact branch: the test scene does not exercise the pose gradients"
+    assert out[0] <= tol, f"g_in deviates by {out[0]:.3e}"
+    assert out[1] <= (1e-10 if dtype == 'float64' else 1e-4), f"pose gradients deviate by {out[1]:.3e}"
+    assert out[2] == 0.0, "grid_in / g_out not cleared"

@@ -13,15 +13,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-KEYS = ["PLB_FLUSH_RUNS", "PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA"]
+KEYS = ["PLB_GRID_BWD_V2", "PLB_FLUSH_RUNS", "PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA"]
 VARIANTS = [
+    ("gridv2", "move100k", dict(PLB_GRID_BWD_V2=1)),
     ("def100k", "move100k", dict()),
-    ("bwd4", "move100k", dict(PLB_BWD_MINB=4)),
-    ("def1m", "move1m", dict()),
-    ("bwd4_1m", "move1m", dict(PLB_BWD_MINB=4)),
-    ("fwd6_bwd4", "move100k", dict(PLB_FWD_MINB=6, PLB_BWD_MINB=4)),
-    ("c64", "move100k", dict(PLB_CTA=64)),
-    ("c64_1m", "move1m", dict(PLB_CTA=64)),
+    ("gridv2_1m", "move1m", dict(PLB_GRID_BWD_V2=1)),
 ]
 
 
