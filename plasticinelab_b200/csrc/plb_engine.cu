@@ -181,7 +181,7 @@ struct Engine : plb_engine {
     int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
     int fwd_minb = 5, bwd_minb = 3; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 / PLB_BWD_MINB=4 select the tighter cap)
     int flush_mode = 0;             // full-tile flush: 0 = per-cell groups, 1 = runs of consecutive lanes (PLB_FLUSH_RUNS=1)
-    bool grid_bwd_v2 = false;       // grid adjoint with register-resident pose gradients (k_grid_bwd_sparse_v2), PLB_GRID_BWD_V2=1
+    bool grid_bwd_v2 = true;        // grid adjoint with register-resident pose gradients (k_grid_bwd_sparse_v2); PLB_GRID_BWD_V2=0: array form
     bool grid_scan = false;         // forward grid stage as one kernel (flag scan + store + grid operator), PLB_GRID_SCAN=1
     bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
                                     // particle kernel and grid adjoint of substep s (needs the second grid set; PLB_BWD_OVERLAP=0 disables)
@@ -650,7 +650,7 @@ struct Engine : plb_engine {
             halo_add_inbox(g_out);
             launches += 6;
         }
-        if (sparse && grid_bwd_v2)
+        if (sparse && grid_bwd_v2 && !slab.on)         // (slab runs keep the array form: the register form was validated on one GPU only)
             k_grid_bwd_sparse_v2<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());
         else if (sparse)
             k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());

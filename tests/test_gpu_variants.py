@@ -15,9 +15,10 @@ from test_gpu_parity import _episode_cfg, _target32
 
 pytestmark = pytest.mark.gpu
 
-KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS"]
+KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2"]
 VARIANTS = {
-    "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3),
+    "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3,
+                         PLB_GRID_BWD_V2=0, PLB_FLUSH_RUNS=0),
     "defaults": {},
     "overlap": dict(PLB_BWD_OVERLAP=1),
     "scan": dict(PLB_GRID_SCAN=1),
@@ -26,6 +27,7 @@ VARIANTS = {
     "cta64": dict(PLB_CTA=64),
     "everything": dict(PLB_BWD_OVERLAP=1, PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6, PLB_BWD_PLANE=1, PLB_BWD_MINB=4, PLB_CTA=64),
     "unfused": dict(PLB_FUSE=0),
+    "grid_bwd_arrays": dict(PLB_GRID_BWD_V2=0),
     "runs": dict(PLB_FLUSH_RUNS=1),
     "runs_unfused_cta64": dict(PLB_FLUSH_RUNS=1, PLB_FUSE=0, PLB_CTA=64),
 }
