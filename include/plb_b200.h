@@ -134,6 +134,22 @@ int  plb_get_primitive_grads(plb_engine* e, int pf0, int n, double* out);
    set_velocity.grad; out[n_steps][sum action_dim] */
 int  plb_get_action_grad(plb_engine* e, int n_steps, int n_substeps, double* out);
 
+/* ---- policy path: state-feedback policies differentiated through the simulator ------------------------------
+   (plb/engine/nn/mlp.py:68-134 reads x, v of every (N // 200)-th particle and the primitive poses at frame t*S,
+   writes action_buffer[t]; plb/optimizer/solver_nn.py:33-43 replays it under ti.Tape.)
+   plb_gather_particles : x[n][3], v[n][3] of the listed particles (caller-order indices) of frame `slot`.
+   plb_scatter_adjoint  : adds gx[n][3], gv[n][3] to the CURRENT adjoint frame at the listed (distinct) particles --
+                          the adjoint of that observation, once the backward sweep stands at the observed frame.
+   plb_action_grad_step : like plb_get_action_grad for ONE env step (out[sum action_dim]); must be called for the env
+                          steps in descending order, each after plb_step_bwd of that step; keeps the pose adjoint that
+                          flows into frame step*S from everything after it.
+   plb_add_pose_adjoint : adds g8 = d loss / d (position(3), rotation(4), gap) of primitive k at that frame (the
+                          observation of the primitive state) to the carried adjoint. */
+int  plb_gather_particles(plb_engine* e, int slot, const int* idx, int n, double* x3, double* v3);
+int  plb_scatter_adjoint(plb_engine* e, const int* idx, int n, const double* gx3, const double* gv3);
+int  plb_action_grad_step(plb_engine* e, int step, int n_substeps, double* out);
+int  plb_add_pose_adjoint(plb_engine* e, int k, const double* g8);
+
 /* ---- loss (plb/engine/losses/loss.py) --------------------------------------------------------------------- */
 /* Loss.load_target_density + update_target (loss.py:46-66,81-106).  density: [n_grid^3] float64.
    sdf may be NULL: the engine then builds it on the device with the reference's sweep. */

@@ -793,3 +793,132 @@ class OracleEnv:
         out['adj0'] = adj
         out['prim_grads'] = gfr
         return out
+
+    # ------------------------------------------------------------------ policy path (plb/engine/nn/mlp.py, solver_nn.py:33-43)
+    def policy_obs_index(self, n_observed=200):
+        step = self.n // n_observed
+        return np.arange(self.n // step) * step
+
+    @staticmethod
+    def policy_unpack(params, dims):
+        """flattened W0, b0, W1, b1, ... (+ optional velocity_weight) -> lists of tensors (mlp.py:167-183)"""
+        params = torch.as_tensor(np.asarray(params, dtype=np.float64))
+        Ws, bs, o = [], [], 0
+        for i in range(len(dims) - 1):
+            n = dims[i + 1] * dims[i]
+            Ws.append(params[o:o + n].reshape(dims[i + 1], dims[i])); o += n
+            bs.append(params[o:o + dims[i + 1]]); o += dims[i + 1]
+        vw = float(params[o]) if len(params) - o == 1 else 1.0
+        assert len(params) - o in (0, 1)
+        return Ws, bs, vw
+
+    def rollout_policy(self, params, horizon, hidden=(256, 256), activation='relu', n_observed=200, softness=666.0,
+                       with_grad=True):
+        """Episode driven by the reference's MLP policy: at env step t the observation is x, v * velocity_weight of every
+        (N // n_observed)-th particle and position + rotation of every primitive at frame t*S (mlp.py:63-89); the action is
+        the network output clamped to [-1, 1] (mlp.py:91-103).  Returns dict(loss, grad[len(params)] wrt W/b, actions).
+        Backward = the tape replay: per env step (descending) loss adjoint, S substep adjoints, then the kinematics chain of
+        that step (autograd through `fk`), the clamp, the network, and the observation adjoint into x, v of the observed
+        particles and into the primitive pose of frame t*S."""
+        sim = self.sim
+        sim.set_softness(softness)
+        S = sim.substeps
+        idx = torch.as_tensor(self.policy_obs_index(n_observed))
+        n_obs, P = len(idx), len(sim.prims)
+        A = self.action_dims[-1]
+        dims = (n_obs * 6 + 7 * P,) + tuple(hidden) + (A,)
+        Ws, bs, vw = self.policy_unpack(params, dims)
+
+        def net(obs, Wl, bl):
+            h = obs
+            for i in range(len(Wl)):
+                h = Wl[i] @ h + bl[i]
+                if i != len(Wl) - 1:
+                    # Taichi routes max(z, 0) by the strict comparison 0 < z; torch.relu's subgradient at 0 is 0 as well
+                    h = torch.relu(h) if activation == 'relu' else (torch.tanh(h) if activation == 'tanh' else h)
+            # max(min(h, 1), -1) with strict routing == clamp (its gradient is 1 only strictly inside up to the measure-zero ends)
+            return torch.where((h < 1.0) & (-1.0 < h), h, h.detach().clamp(-1.0, 1.0))
+
+        def step_frames(pose0, a):
+            """frames t*S+1 .. (t+1)*S as a function of the pose at t*S and the (already clamped) action"""
+            out, cur = [], list(pose0)
+            for _ in range(S):
+                nxt = []
+                for k, p in enumerate(sim.prims):
+                    if p.action_dim > 0:
+                        v, w, gv = p.velocities(a[self.action_dims[k]:self.action_dims[k + 1]])
+                        v, w = v / S, w / S
+                        gv = None if gv is None else gv / S
+                    else:
+                        v, w, gv = torch.zeros(3, dtype=DT), torch.zeros(3, dtype=DT), torch.zeros((), dtype=DT)
+                    nxt.append(p.fk(cur[k], v, w, gv))
+                out.append(nxt)
+                cur = nxt
+            return out
+
+        def observation(state, pose):
+            return torch.cat([torch.cat([state[0][idx], state[1][idx] * vw], dim=1).reshape(-1)] + [q[:7] for q in pose])
+
+        # ---------------- forward
+        state = self.initial_state()
+        frames = [[q.detach() for q in self.initial_prims()]]
+        states, actions, total = [state], [], 0.0
+        with torch.no_grad():
+            for t in range(horizon):
+                a = net(observation(state, frames[t * S]), Ws, bs)
+                actions.append(a)
+                frames += [[q.detach() for q in f] for f in step_frames(frames[t * S], a)]
+                for s_ in range(t * S, (t + 1) * S):
+                    state = sim.substep(state, frames[s_], frames[s_ + 1])
+                    states.append(state)
+                if self.loss is not None:
+                    total += self.loss.value(state[0], frames[(t + 1) * S])['loss']
+        out = dict(loss=total, actions=torch.stack(actions).numpy(), final_state=state)
+        if not with_grad:
+            return out
+        # ---------------- backward
+        n = self.n
+        adj = (torch.zeros(n, 3, dtype=DT), torch.zeros(n, 3, dtype=DT), torch.zeros(n, 3, 3, dtype=DT), torch.zeros(n, 3, 3, dtype=DT))
+        gfr = [[torch.zeros_like(q) for q in f] for f in frames]
+        gW = [torch.zeros_like(w) for w in Ws]
+        gb = [torch.zeros_like(b) for b in bs]
+        for t in reversed(range(horizon)):
+            f_end = (t + 1) * S
+            if self.loss is not None:
+                gx, gp = self.loss.vjp(states[f_end][0], frames[f_end])
+                adj = (adj[0] + gx, adj[1], adj[2], adj[3])
+                for k, g in enumerate(gp):
+                    gfr[f_end][k] = gfr[f_end][k] + g
+            for s_ in reversed(range(t * S, f_end)):
+                adj, g0, g1 = sim.substep_vjp(states[s_], frames[s_], frames[s_ + 1], adj)
+                for k in range(P):
+                    gfr[s_][k] = gfr[s_][k] + g0[k]
+                    gfr[s_ + 1][k] = gfr[s_ + 1][k] + g1[k]
+            # kinematics chain of env step t: pose(t*S), action -> frames t*S+1 .. f_end
+            pose0 = [q.clone().requires_grad_(True) for q in frames[t * S]]
+            x_obs = states[t * S][0][idx].clone().requires_grad_(True)
+            v_obs = states[t * S][1][idx].clone().requires_grad_(True)
+            Wl = [w.clone().requires_grad_(True) for w in Ws]
+            bl = [b.clone().requires_grad_(True) for b in bs]
+            obs = torch.cat([torch.cat([x_obs, v_obs * vw], dim=1).reshape(-1)] + [q[:7] for q in pose0])
+            a = net(obs, Wl, bl)
+            fr = step_frames(pose0, a)
+            outs = [q for f in fr for q in f]
+            gouts = [g for f in gfr[t * S + 1: f_end + 1] for g in f]
+            keep = [(o, g) for o, g in zip(outs, gouts) if o.requires_grad]
+            inputs = pose0 + [x_obs, v_obs] + Wl + bl
+            grads = torch.autograd.grad([o for o, _ in keep], inputs, grad_outputs=[g for _, g in keep], allow_unused=True)
+            grads = [torch.zeros_like(i) if g is None else g for g, i in zip(grads, inputs)]
+            for k in range(P):
+                gfr[t * S][k] = gfr[t * S][k] + grads[k]
+            gx_obs, gv_obs = grads[P], grads[P + 1]
+            ax, av = adj[0].clone(), adj[1].clone()
+            ax[idx] += gx_obs
+            av[idx] += gv_obs
+            adj = (ax, av, adj[2], adj[3])
+            for i in range(len(Ws)):
+                gW[i] += grads[P + 2 + i]
+                gb[i] += grads[P + 2 + len(Ws) + i]
+        out['grad'] = np.concatenate([a_.numpy().reshape(-1) for i in range(len(Ws)) for a_ in (gW[i], gb[i])])
+        return out
+

@@ -165,6 +165,10 @@ _SIGNATURES = {
     "plb_get_adjoint": ([C.c_void_p, _D, _D, _D, _D], C.c_int),
     "plb_get_primitive_grads": ([C.c_void_p, C.c_int, C.c_int, _D], C.c_int),
     "plb_get_action_grad": ([C.c_void_p, C.c_int, C.c_int, _D], C.c_int),
+    "plb_action_grad_step": ([C.c_void_p, C.c_int, C.c_int, _D], C.c_int),
+    "plb_add_pose_adjoint": ([C.c_void_p, C.c_int, _D], C.c_int),
+    "plb_gather_particles": ([C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, _D, _D], C.c_int),
+    "plb_scatter_adjoint": ([C.c_void_p, C.POINTER(C.c_int), C.c_int, _D, _D], C.c_int),
     "plb_set_target": ([C.c_void_p, _D, _D], C.c_int),
     "plb_get_target_sdf": ([C.c_void_p, _D], C.c_int),
     "plb_set_loss_weights": ([C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int], C.c_int),

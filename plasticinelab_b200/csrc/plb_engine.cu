@@ -98,6 +98,10 @@ struct plb_engine {
     virtual int get_adjoint(double* gx, double* gv, double* gF, double* gC) = 0;
     virtual int get_prim_grads(int pf0, int n, double* out) = 0;
     virtual int get_action_grad(int n_steps, int S, double* out) = 0;
+    virtual int action_grad_step(int step, int S, double* out) = 0;
+    virtual int add_pose_adjoint(int k, const double* g8) = 0;
+    virtual int gather_particles(int slot, const int* idx, int n, double* x3, double* v3) = 0;
+    virtual int scatter_adjoint(const int* idx, int n, const double* gx3, const double* gv3) = 0;
     virtual int set_target(const double* density, const double* sdf) = 0;
     virtual int get_target_sdf(double* sdf) = 0;
     virtual int set_loss_weights(double sdf, double density, double contact, int soft, int all) = 0;
@@ -218,6 +222,7 @@ struct Engine : plb_engine {
         cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_cub); cudaFree(frame_tmp);
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt); cudaFree(store.overflow); cudaFree(d_cursor);
+        cudaFree(d_inv_perm); cudaFree(d_sel_idx); cudaFree(d_sel_val);
         cudaFree(sets[1].in); cudaFree(sets[1].out); cudaFree(sets[1].list); cudaFree(sets[1].count);
         for (cudaEvent_t e : cap_events) cudaEventDestroy(e);
         if (side_stream) cudaStreamDestroy(side_stream);
@@ -445,6 +450,7 @@ struct Engine : plb_engine {
             PLB_CUDA(cudaMemcpyAsync(mats[i], frame_tmp, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
         }
         std::swap(d_perm, d_perm2);
+        inv_perm_valid = false;
         launches += 3;
         PLB_CUDA(cudaGetLastError());
         std::fill(stored.begin(), stored.end(), 0);
@@ -1075,6 +1081,7 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMemsetAsync(adj[1], 0, (size_t)24 * n_pad * sizeof(T), stream));
         PLB_CUDA(cudaMemsetAsync(d_prim_grad, 0, traj.size() * sizeof(double), stream));
         PLB_CUDA(cudaMemsetAsync(d_acc + kAccN, 0, sizeof(double), stream));
+        scan_carry.reset();
         return PLB_OK;
     }
     int set_adjoint(const double* gx, const double* gv, const double* gF, const double* gC) override {
@@ -1125,22 +1132,82 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMemcpyAsync(g.data(), d_prim_grad, g.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         PLB_CUDA(cudaStreamSynchronize(stream));
         std::fill(out, out + (size_t)n_steps * action_total, 0.0);
-        for (int f = nf - 1; f >= 0; f--) {
-            int step = f / S;
-            for (int k = cfg.n_primitives - 1; k >= 0; k--) {
-                const kin::Desc& d = kdesc[k];
-                const double* vv = velo(f, k);
-                double* gnext = &g[((size_t)(f + 1) * PLB_MAX_PRIM + k) * 8];
-                double* gcur = &g[((size_t)f * PLB_MAX_PRIM + k) * 8];
-                double gvel[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, ggv = 0;
-                kin::fk_backward(d, pose(f, k), vv, vv + 3, vv[6], gnext, gcur, gvel, gw, ggv);
-                if (d.action_dim == 0) continue;
-                double* o = out + (size_t)step * action_total + action_off[k];
-                for (int i = 0; i < 3; i++) o[i] += gvel[i] * d.action_scale[i] / S;
-                if (d.action_dim > 3) for (int i = 0; i < 3; i++) o[3 + i] += gw[i] * d.action_scale[3 + i] / S;
-                if (d.type == PRIM_CHOPSTICKS) o[6] += ggv * d.action_scale[6] / S;
-            }
+        kin::action_grad_scan(kdesc.data(), cfg.n_primitives, PLB_MAX_PRIM, traj.data(), vel.data(), g.data(), 0, 0, nf, S, action_off.data(),
+                              action_total, out, 0);
+        return PLB_OK;
+    }
+
+    // ---------------------------------------------------------------- policy path (plb/engine/nn/mlp.py, plb/optimizer/solver_nn.py)
+    // With a state-feedback policy the action of env step t depends on the particle state and the poses at frame t*S, so its
+    // gradient is needed while the backward sweep stands at that frame: the kinematics reverse scan is run one env step at a
+    // time, carrying the adjoint that flows into the pose of frame t*S from everything after it (`scan_carry`), to which the
+    // caller adds the policy's observation adjoint (plb_add_pose_adjoint) before the next (earlier) step.
+    kin::ScanCarry scan_carry;
+    int action_grad_step(int step, int S, double* out) override {
+        const int f_lo = step * S, f_hi = (step + 1) * S;
+        PLB_REQUIRE(step >= 0 && S > 0 && out != nullptr, "bad step");
+        if (int r = check_pf(f_hi)) return r;
+        if (int r = check_overflow()) return r;
+        const size_t row = (size_t)PLB_MAX_PRIM * 8;
+        std::vector<double> dev((size_t)(S + 1) * row), scratch((size_t)(S + 1) * row);
+        PLB_CUDA(cudaMemcpyAsync(dev.data(), d_prim_grad + (size_t)f_lo * row, dev.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        const bool ok = kin::action_grad_step(kdesc.data(), cfg.n_primitives, traj.data(), vel.data(), dev.data(), step, S, action_off.data(),
+                                              action_total, scan_carry, out, scratch.data());
+        PLB_REQUIRE(ok, "plb_action_grad_step must walk the env steps in descending order");
+        return PLB_OK;
+    }
+    int add_pose_adjoint(int k, const double* g8) override {
+        PLB_REQUIRE(k >= 0 && k < cfg.n_primitives && g8 != nullptr, "primitive index");
+        PLB_REQUIRE(scan_carry.frame >= 0, "plb_add_pose_adjoint needs a preceding plb_action_grad_step");
+        for (int i = 0; i < 8; i++) scan_carry.v[(size_t)k * 8 + i] += g8[i];
+        return PLB_OK;
+    }
+    // caller-order particle indices -> stored positions
+    int* d_inv_perm = nullptr; bool inv_perm_valid = false;
+    int* d_sel_idx = nullptr; double* d_sel_val = nullptr; int sel_cap = 0;
+    int prepare_selection(const int* idx, int n) {
+        PLB_REQUIRE(idx != nullptr && n > 0 && n <= cfg.n_particles, "bad particle selection");
+        for (int i = 0; i < n; i++) PLB_REQUIRE(idx[i] >= 0 && idx[i] < cfg.n_particles, "particle index out of range");
+        if (!d_inv_perm) PLB_CUDA(cudaMalloc(&d_inv_perm, n_pad * sizeof(int)));
+        if (!inv_perm_valid) {
+            k_invert_perm<<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, d_perm, d_inv_perm);
+            launches++;
+            inv_perm_valid = true;
         }
+        if (n > sel_cap) {
+            cudaFree(d_sel_idx); cudaFree(d_sel_val);
+            d_sel_idx = nullptr; d_sel_val = nullptr; sel_cap = 0;
+            PLB_CUDA(cudaMalloc(&d_sel_idx, (size_t)n * sizeof(int)));
+            PLB_CUDA(cudaMalloc(&d_sel_val, (size_t)n * 6 * sizeof(double)));
+            sel_cap = n;
+        }
+        PLB_CUDA(cudaMemcpyAsync(d_sel_idx, idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream));
+        return PLB_OK;
+    }
+    // x, v of the listed particles of frame `slot` (observation of the policy: mlp.py:68-76)
+    int gather_particles(int slot, const int* idx, int n, double* x3, double* v3) override {
+        if (int r = check_slot(slot)) return r;
+        PLB_REQUIRE(x3 != nullptr && v3 != nullptr, "null output");
+        if (int r = prepare_selection(idx, n)) return r;
+        k_gather_xv<T><<<blocks(n), kBlock, 0, stream>>>(n, n_pad, frame_base(slot), d_sel_idx, d_inv_perm, d_sel_val);
+        launches++;
+        std::vector<double> h((size_t)n * 6);
+        PLB_CUDA(cudaMemcpyAsync(h.data(), d_sel_val, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) { x3[i * 3 + c] = h[(size_t)i * 6 + c]; v3[i * 3 + c] = h[(size_t)i * 6 + 3 + c]; }
+        return PLB_OK;
+    }
+    // adds (gx, gv) to the CURRENT adjoint frame at the listed particles (distinct indices): adjoint of the observation
+    int scatter_adjoint(const int* idx, int n, const double* gx3, const double* gv3) override {
+        PLB_REQUIRE(gx3 != nullptr && gv3 != nullptr, "null input");
+        if (int r = prepare_selection(idx, n)) return r;
+        std::vector<double> h((size_t)n * 6);
+        for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) { h[(size_t)i * 6 + c] = gx3[i * 3 + c]; h[(size_t)i * 6 + 3 + c] = gv3[i * 3 + c]; }
+        PLB_CUDA(cudaMemcpyAsync(d_sel_val, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        k_scatter_adj_xv<T><<<blocks(n), kBlock, 0, stream>>>(n, n_pad, adj[cur], d_sel_idx, d_inv_perm, d_sel_val);
+        launches++;
+        PLB_CUDA(cudaStreamSynchronize(stream));      // h goes out of scope
         return PLB_OK;
     }
 
@@ -1328,6 +1395,10 @@ int plb_set_adjoint(plb_engine* e, const double* gx, const double* gv, const dou
 int plb_get_adjoint(plb_engine* e, double* gx, double* gv, double* gF, double* gC) { return e->get_adjoint(gx, gv, gF, gC); }
 int plb_get_primitive_grads(plb_engine* e, int pf0, int n, double* out) { return e->get_prim_grads(pf0, n, out); }
 int plb_get_action_grad(plb_engine* e, int n_steps, int S, double* out) { return e->get_action_grad(n_steps, S, out); }
+int plb_action_grad_step(plb_engine* e, int step, int S, double* out) { return e->action_grad_step(step, S, out); }
+int plb_add_pose_adjoint(plb_engine* e, int k, const double* g8) { return e->add_pose_adjoint(k, g8); }
+int plb_gather_particles(plb_engine* e, int slot, const int* idx, int n, double* x3, double* v3) { return e->gather_particles(slot, idx, n, x3, v3); }
+int plb_scatter_adjoint(plb_engine* e, const int* idx, int n, const double* gx3, const double* gv3) { return e->scatter_adjoint(idx, n, gx3, gv3); }
 int plb_set_target(plb_engine* e, const double* d, const double* s) { return e->set_target(d, s); }
 int plb_get_target_sdf(plb_engine* e, double* s) { return e->get_target_sdf(s); }
 int plb_set_loss_weights(plb_engine* e, double s, double d, double c, int soft, int all) { return e->set_loss_weights(s, d, c, soft, all); }

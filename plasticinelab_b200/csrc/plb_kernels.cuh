@@ -739,6 +739,32 @@ template <class T> __global__ void k_permute_scalar(int n, const T* src, T* dst,
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) dst[j] = src[order[j]];
 }
+// ---- policy path: observation gather / observation-adjoint scatter for a handful of particles (caller-order indices)
+__global__ void k_invert_perm(int n, const int* __restrict__ perm, int* inv) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) inv[perm[p]] = p;
+}
+template <class T>
+__global__ void k_gather_xv(int n_sel, long long n_pad, T* frame, const int* __restrict__ idx, const int* __restrict__ inv, double* out6) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sel) return;
+    const int p = inv[idx[j]];
+    FramePtr<T> f = frame_at(frame, 0, n_pad);
+    Vec4<T> q0 = f.A0[p], q1 = f.A1[p];
+    out6[j * 6 + 0] = q0.x; out6[j * 6 + 1] = q0.y; out6[j * 6 + 2] = q0.z;
+    out6[j * 6 + 3] = q0.w; out6[j * 6 + 4] = q1.x; out6[j * 6 + 5] = q1.y;
+}
+template <class T>
+__global__ void k_scatter_adj_xv(int n_sel, long long n_pad, T* adj, const int* __restrict__ idx, const int* __restrict__ inv, const double* g6) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sel) return;
+    const int p = inv[idx[j]];                  // distinct indices: no two threads touch the same particle
+    FramePtr<T> f = frame_at(adj, 0, n_pad);
+    Vec4<T> q0 = f.A0[p], q1 = f.A1[p];
+    q0.x += (T)g6[j * 6 + 0]; q0.y += (T)g6[j * 6 + 1]; q0.z += (T)g6[j * 6 + 2];
+    q0.w += (T)g6[j * 6 + 3]; q1.x += (T)g6[j * 6 + 4]; q1.y += (T)g6[j * 6 + 5];
+    f.A0[p] = q0; f.A1[p] = q1;
+}
 __global__ void k_iota(int n, int* a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
 
 template <class T> __global__ void k_convert(long long n, const double* src, T* dst) {

@@ -173,5 +173,56 @@ inline void fk_backward(const Desc& d, const double st[8], const double v[3], co
     for (int i = 0; i < 4; i++) gst[3 + i] += gq[i];
 }
 
+// Reverse scan of the pose adjoints through forward_kinematics.grad and set_velocity.grad for the frames f_hi-1 .. f_lo
+// (Primitive.forward_kinematics.grad + set_velocity.grad replayed by the tape, primive_base.py:117-121,184-192).
+//   g      pose adjoints [frame - g_base][max_prim][8]; g[f+1] is consumed, g[f] accumulates (in place)
+//   traj   poses [frame][max_prim][8], vel per-substep velocities [frame][max_prim][8] = v(3) w(3) gap-velocity pad
+//   out    action gradients [step - out_base][action_total], step = f / S; ACCUMULATED into
+// Used for the whole episode at once (plb_get_action_grad) and one env step at a time (plb_action_grad_step, policy path).
+inline void action_grad_scan(const Desc* descs, int n_prim, int max_prim, const double* traj, const double* vel, double* g, int g_base,
+                             int f_lo, int f_hi, int S, const int* action_off, int action_total, double* out, int out_base) {
+    for (int f = f_hi - 1; f >= f_lo; f--) {
+        const int step = f / S;
+        for (int k = n_prim - 1; k >= 0; k--) {
+            const Desc& d = descs[k];
+            const double* vv = vel + ((size_t)f * max_prim + k) * 8;
+            const double* gnext = g + ((size_t)(f + 1 - g_base) * max_prim + k) * 8;
+            double* gcur = g + ((size_t)(f - g_base) * max_prim + k) * 8;
+            double gvel[3] = {0, 0, 0}, gw[3] = {0, 0, 0}, ggv = 0;
+            fk_backward(d, traj + ((size_t)f * max_prim + k) * 8, vv, vv + 3, vv[6], gnext, gcur, gvel, gw, ggv);
+            if (d.action_dim == 0) continue;
+            double* o = out + (size_t)(step - out_base) * action_total + action_off[k];
+            for (int i = 0; i < 3; i++) o[i] += gvel[i] * d.action_scale[i] / S;
+            if (d.action_dim > 3) for (int i = 0; i < 3; i++) o[3 + i] += gw[i] * d.action_scale[3 + i] / S;
+            if (d.type == PRIM_CHOPSTICKS) o[6] += ggv * d.action_scale[6] / S;
+        }
+    }
+}
+
+// One env step of that scan for state-feedback policies (the action of step t depends on the state at frame t*S, so its
+// gradient is needed while the backward sweep stands there).  `carry` holds the adjoint that flows into the pose of frame
+// (step+1)*S from everything after it; `dev` = the accumulated pose adjoints of the frames step*S .. (step+1)*S as the device
+// holds them now ([S+1][PLB_MAX_PRIM][8]; the row of frame step*S is still incomplete, which is why only the part the scan
+// ADDS to it is carried on).  Steps must come in descending order.  out[action_total] is overwritten.
+struct ScanCarry {
+    double v[PLB_MAX_PRIM * 8];
+    int frame;                       // frame the carry belongs to; -1: nothing carried yet
+    ScanCarry() { reset(); }
+    void reset() { std::memset(v, 0, sizeof(v)); frame = -1; }
+};
+inline bool action_grad_step(const Desc* descs, int n_prim, const double* traj, const double* vel, const double* dev, int step, int S,
+                             const int* action_off, int action_total, ScanCarry& carry, double* out, double* scratch /*[(S+1)*PLB_MAX_PRIM*8]*/) {
+    const int f_lo = step * S, f_hi = (step + 1) * S;
+    if (carry.frame >= 0 && carry.frame != f_hi) return false;
+    const size_t row = (size_t)PLB_MAX_PRIM * 8;
+    std::memcpy(scratch, dev, (size_t)(S + 1) * row * sizeof(double));
+    if (carry.frame == f_hi) for (size_t i = 0; i < row; i++) scratch[(size_t)S * row + i] += carry.v[i];
+    for (int i = 0; i < action_total; i++) out[i] = 0.0;
+    action_grad_scan(descs, n_prim, PLB_MAX_PRIM, traj, vel, scratch, f_lo, f_lo, f_hi, S, action_off, action_total, out, step);
+    for (size_t i = 0; i < row; i++) carry.v[i] = scratch[i] - dev[i];
+    carry.frame = f_lo;
+    return true;
+}
+
 }  // namespace kin
 }  // namespace plb

@@ -4,7 +4,8 @@ Public surface = `plb/engine/taichi_env.py:9-106` (constructor arguments, `initi
 `get_state`, `set_state`, `render`, attributes `simulator`, `primitives`, `loss`, `n_particles`, `init_particles`).
 What is different underneath: no Taichi runtime -- a CUDA engine handle is created through the C ABI (no CPU fallback);
 `dtype` picks the float32 production kernels or the float64 parity kernels (the reference only has float64,
-`mpm_simulator.py:8`); `render` and the Taichi MLP policy are out of scope.
+`mpm_simulator.py:8`); `nn=True` attaches the state-feedback MLP policy (`engine/nn/mlp.py`); `render` is out of scope
+(SURVEY.md 2a #7).
 """
 from __future__ import annotations
 
@@ -26,8 +27,6 @@ def _resolve_dtype(requested, sim_cfg):
 
 class TaichiEnv:
     def __init__(self, cfg, nn=False, loss=True, dtype=None, device=0, max_prim_frames=None, particle_index=None):
-        if nn:
-            raise NotImplementedError("the Taichi MLP policy (plb/engine/nn/mlp.py) is out of scope (SURVEY.md 8f #3)")
         sim_cfg = cfg.SIMULATOR
         self.cfg = cfg.ENV
         self._is_copy = True
@@ -49,6 +48,9 @@ class TaichiEnv:
         self.primitives.bind(self.engine)
         self.simulator = MPMSimulator(sim_cfg, self.primitives, self.engine)
         self.simulator._env = self
+        if nn:
+            from .nn.mlp import MLP
+            self.nn = MLP(self.simulator, self.primitives, (256, 256))     # taichi_env.py:35-36
         self.loss = Loss(cfg.ENV.loss, self.simulator) if loss else None
 
     # ------------------------------------------------------------------ lifecycle

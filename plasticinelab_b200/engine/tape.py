@@ -34,6 +34,12 @@ class Tape:
     def record_loss(self, f):
         self.records.append(("loss", int(f)))
 
+    def record_policy(self, policy, step):
+        """`policy.set_action(step, S)` ran (engine/nn/mlp.py): its backward runs when the sweep is back at frame step*S."""
+        if not any(r[0] == "policy" and r[1] is policy for r in self.records):
+            policy.zero_grad_for_tape()
+        self.records.append(("policy", policy, int(step)))
+
     def __exit__(self, exc_type, exc, tb):
         global _ACTIVE
         _ACTIVE = None
@@ -43,6 +49,8 @@ class Tape:
         for rec in reversed(self.records):
             if rec[0] == "loss":
                 eng.call("plb_loss_bwd", rec[1], rec[1])
+            elif rec[0] == "policy":
+                rec[1].backward(rec[2])
             else:
                 eng.call("plb_step_bwd", rec[1], rec[1], rec[2])
         return False

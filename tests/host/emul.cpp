@@ -197,6 +197,39 @@ void emul_fk_bwd(const plb_primitive_desc* d, const double* st, const double* v,
     *ggv = 0;
     kin::fk_backward(make_kindesc(*d), st, v, w, gv, gout, gst, gvel, gw, *ggv);
 }
+// kinematics reverse scan: whole episode at once (chunked = 0) or one env step at a time with the carried adjoint (chunked = 1).
+// traj / vel / g: [n_steps * S + 1][PLB_MAX_PRIM][8]; inject (optional): [n_steps][n_prim][8] added to the carry after each
+// step's scan (policy observation adjoint).  out: [n_steps][action_total].  Returns action_total, or -1 on an order error.
+int emul_action_grad(const plb_primitive_desc* pd, int n_prim, const double* traj, const double* vel, const double* g_dev, int n_steps,
+                     int S, int chunked, const double* inject, double* out) {
+    std::vector<kin::Desc> kd;
+    std::vector<int> off;
+    int total = 0;
+    for (int k = 0; k < n_prim; k++) { kd.push_back(make_kindesc(pd[k])); off.push_back(total); total += pd[k].action_dim; }
+    const size_t row = (size_t)PLB_MAX_PRIM * 8;
+    const int nf = n_steps * S;
+    std::memset(out, 0, sizeof(double) * (size_t)n_steps * total);
+    if (!chunked) {
+        std::vector<double> g(g_dev, g_dev + (size_t)(nf + 1) * row);
+        if (inject)      // the observation adjoint of step t lands on the pose of frame t*S
+            for (int t = 0; t < n_steps; t++)
+                for (int k = 0; k < n_prim; k++)
+                    for (int i = 0; i < 8; i++) g[(size_t)t * S * row + (size_t)k * 8 + i] += inject[((size_t)t * n_prim + k) * 8 + i];
+        kin::action_grad_scan(kd.data(), n_prim, PLB_MAX_PRIM, traj, vel, g.data(), 0, 0, nf, S, off.data(), total, out, 0);
+        return total;
+    }
+    kin::ScanCarry carry;
+    std::vector<double> scratch((size_t)(S + 1) * row);
+    for (int t = n_steps - 1; t >= 0; t--) {
+        if (!kin::action_grad_step(kd.data(), n_prim, traj, vel, g_dev + (size_t)t * S * row, t, S, off.data(), total, carry,
+                                   out + (size_t)t * total, scratch.data()))
+            return -1;
+        if (inject)
+            for (int k = 0; k < n_prim; k++)
+                for (int i = 0; i < 8; i++) carry.v[(size_t)k * 8 + i] += inject[((size_t)t * n_prim + k) * 8 + i];
+    }
+    return total;
+}
 void emul_svd(int dtype, const double* F9, double* U9, double* s3, double* V9) {
     if (dtype == PLB_F32) {
         M3<float> F, U, V; V3<float> s;

@@ -251,3 +251,39 @@ def test_loss_value_and_adjoint(emul_lib, mode):
     for k in range(len(poses)):
         ref = ogp[k].numpy()
         assert np.abs(gp[k, :7] - ref).max() < 1e-9 * max(np.abs(ref).max(), 1e-12) + 1e-13, (k, gp[k], ref)
+
+
+def test_stepwise_action_gradient_scan_equals_whole_episode_scan(emul_lib):
+    """plb_action_grad_step (policy path: one env step at a time, carried pose adjoint, injected observation adjoints) against
+    plb_get_action_grad's whole-episode scan on random pose adjoints.  Exact up to summation order (1e-12)."""
+    rng = np.random.RandomState(4)
+    names = ['spheres', 'capsule', 'chopsticks']
+    prims = [dict(p) for n in names for p in PRIM_SETS[n]]
+    descs = [_capi.primitive_desc(p) for p in prims]
+    parr = (_capi.PrimitiveDesc * len(descs))(*descs)
+    n_steps, S, MAXP = 4, 5, 8
+    nf = n_steps * S
+    traj = np.zeros((nf + 1, MAXP, 8)); vel = np.zeros((nf + 1, MAXP, 8))
+    for k, d in enumerate(descs):
+        st = np.array(list(d.init_state), dtype=np.float64)
+        st[3:7] /= np.linalg.norm(st[3:7])
+        traj[0, k] = st
+        for f in range(nf):
+            vel[f, k, :3] = 2e-3 * rng.randn(3); vel[f, k, 3:6] = 5e-3 * rng.randn(3); vel[f, k, 6] = 1e-3 * rng.rand()
+            out = np.zeros(8)
+            emul_lib.emul_fk(C.byref(d), D(np.ascontiguousarray(traj[f, k])), D(np.ascontiguousarray(vel[f, k, :3])),
+                             D(np.ascontiguousarray(vel[f, k, 3:6])), C.c_double(vel[f, k, 6]), D(out))
+            traj[f + 1, k] = out
+    g = np.zeros((nf + 1, MAXP, 8)); g[:, :len(descs)] = rng.randn(nf + 1, len(descs), 8)
+    inject = np.ascontiguousarray(rng.randn(n_steps, len(descs), 8))
+    emul_lib.emul_action_grad.restype = C.c_int
+    for inj in (None, inject):
+        res = []
+        for chunked in (0, 1):
+            A = sum(d.action_dim for d in descs)
+            out = np.zeros((n_steps, A))
+            r = emul_lib.emul_action_grad(parr, len(descs), D(traj), D(vel), D(g), n_steps, S, chunked, D(inj), D(out))
+            assert r == A
+            res.append(out)
+        assert np.abs(res[0]).max() > 0
+        assert np.abs(res[0] - res[1]).max() < 1e-12 * max(1.0, np.abs(res[0]).max())

@@ -79,6 +79,28 @@ def test_oracle_gradient_matches_finite_differences():
         assert abs(fd - g[i, j]) < 1e-6 * max(abs(fd), 1e-3), (i, j, fd, g[i, j])
 
 
+def test_oracle_policy_gradient_matches_finite_differences():
+    """Policy path (plb/engine/nn/mlp.py + solver_nn.py): the oracle's tape replay with the state-feedback MLP -- kinematics chain
+    per env step, clamp, dense layers, observation adjoint into x, v and the primitive poses -- equals central differences of its
+    own forward with respect to the network parameters (true sub-gradient mode of the contact loss)."""
+    env = _small_env('argmin')
+    rng = np.random.RandomState(0)
+    n_obs, P, A = len(env.policy_obs_index(30)), len(env.sim.prims), env.action_dims[-1]
+    dims = (n_obs * 6 + 7 * P, 8, A)
+    params = 0.3 * rng.randn(sum(dims[i + 1] * dims[i] + dims[i + 1] for i in range(2)))
+    kw = dict(hidden=(8,), n_observed=30)
+    out = env.rollout_policy(params, 2, **kw)
+    g = out['grad']
+    assert np.abs(out['actions']).max() < 1.0 and np.abs(g).max() > 1e-4       # clamp inactive, gradient flows
+    for i in list(np.argsort(-np.abs(g))[:3]) + [3]:
+        e = 1e-6
+        p1, p2 = params.copy(), params.copy()
+        p1[i] += e
+        p2[i] -= e
+        fd = (env.rollout_policy(p1, 2, with_grad=False, **kw)['loss'] - env.rollout_policy(p2, 2, with_grad=False, **kw)['loss']) / (2 * e)
+        assert abs(fd - g[i]) < 2e-6 * max(abs(fd), 1e-3), (i, fd, g[i])
+
+
 def test_taichi_contact_mode_differs_only_through_contact_term():
     a = _small_env('taichi').rollout(np.zeros((1, 9)))
     b = _small_env('argmin').rollout(np.zeros((1, 9)))
