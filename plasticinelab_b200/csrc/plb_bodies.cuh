@@ -116,9 +116,10 @@ template <class T> PLB_HD void load_material(const SimConst<T>& P, const Materia
 // P2G: F_tmp, SVD, return mapping, stress, 27-node scatter.  `out` may alias nothing (F[f+1] store skipped if !store_F_out).
 // register-level core: particle state in, new_F out, 27 contributions through the scatter policy
 template <class T, class Sc>
-PLB_HD void p2g_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys, M3<T>& new_F, const Sc& sc) {
+PLB_HD void p2g_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys, M3<T>& new_F, const Sc& sc,
+                     SvdRec<T>* svd_out = nullptr) {
     M3<T> affine;
-    p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine);
+    p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine, nullptr, svd_out);
     Stencil<T> st = make_stencil(x, P.inv_dx);
     // momentum_o = w_o (p_mass v + affine ((o - fx) dx)) = w_o (m0 + i c0 + j c1 + k c2): the affine part is evaluated
     // incrementally along the three stencil axes (81 + 27 + 9 FMAs instead of 27 mat-vecs)
@@ -143,23 +144,28 @@ PLB_HD void p2g_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, con
         sc.end_plane(i);
     }
 }
+// svd_keep (optional): planes of the SVD store of this frame; written when the frame's F' is (store_F_out)
 template <class T, class Sc>
 PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,
-                     const Material<T>& mat, const Sc& sc) {
+                     const Material<T>& mat, const Sc& sc, const SvdPtr<T>* svd_keep = nullptr) {
     V3<T> x, v; M3<T> C;
     load_xvC(in, p, x, v, C);
     M3<T> F = load_F(in, p);
     T mu, lam, ys;
     load_material(P, mat, p, mu, lam, ys);
     M3<T> new_F;
-    p2g_core<T, Sc>(P, x, v, C, F, mu, lam, ys, new_F, sc);
-    if (store_F_out) store_F(out, p, new_F);
+    SvdRec<T> rec;
+    p2g_core<T, Sc>(P, x, v, C, F, mu, lam, ys, new_F, sc, svd_keep ? &rec : nullptr);
+    if (store_F_out) {
+        store_F(out, p, new_F);
+        if (svd_keep) store_svd(*svd_keep, p, rec);
+    }
 }
 template <class T>
 PLB_HD void p2g_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, bool store_F_out,
-                     const Material<T>& mat, Vec4<T>* grid_in) {
+                     const Material<T>& mat, Vec4<T>* grid_in, const SvdPtr<T>* svd_keep = nullptr) {
     DirectScatter<T> sc{grid_in, P.n_grid};
-    p2g_body<T, DirectScatter<T>>(p, P, in, out, store_F_out, mat, sc);
+    p2g_body<T, DirectScatter<T>>(p, P, in, out, store_F_out, mat, sc, svd_keep);
 }
 
 // grid operator: grid_in -> grid_out; optionally zeroes grid_in for the next scatter
@@ -337,12 +343,14 @@ PLB_HD void grid_bwd_body(long long node, const SimConst<T>& P, const PrimSet<T>
 
 // p2g.grad + svd_grad + compute_F_tmp.grad: gathers g_in at 27 nodes, finishes the adjoint of frame f in adj_cur.
 // register-level core: state of frame f, adjoint of F[f+1], partial x-adjoint -> full adjoint of frame f
-template <class T>
+// kSvdGiven: `svd` holds the forward's decomposition of F_tmp (SVD store) and the Jacobi iteration is not re-run
+template <class T, bool kSvdGiven = false>
 PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys, const Vec4<T>* g_in,
-                         const M3<T>& gF_next, V3<T> gx_partial, V3<T>& gx_out, V3<T>& gv_out, M3<T>& gC, M3<T>& gF) {
+                         const M3<T>& gF_next, V3<T> gx_partial, V3<T>& gx_out, V3<T>& gv_out, M3<T>& gC, M3<T>& gF,
+                         SvdRec<T>* svd = nullptr) {
     M3<T> new_F, affine;
     P2GState<T> keep;
-    p2g_particle<T>(P, C, F, mu, lam, ys, new_F, affine, &keep);
+    p2g_particle<T, kSvdGiven>(P, C, F, mu, lam, ys, new_F, affine, &keep, svd);
     Stencil<T> st = make_stencil(x, P.inv_dx);
     // forward node value: w_o (m_o, p_mass) with m_o = p_mass v + affine (o - fx) dx, evaluated incrementally.
     // With a_o = adjoint of the node momentum: g(weight_o) = a_o . m_o + b_o p_mass;  g(v) = p_mass sum w a;
@@ -397,9 +405,9 @@ PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C,
     gv_out = gv;
     p2g_particle_backward<T>(P, C, F, mu, lam, keep, g_aff, gF_next, gC, gF);
 }
-template <class T>
+template <class T, bool kSvdGiven = false>
 PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
-                         const FramePtr<T>& adj_cur, const Material<T>& mat, const Vec4<T>* g_in) {
+                         const FramePtr<T>& adj_cur, const Material<T>& mat, const Vec4<T>* g_in, const SvdPtr<T>* svd_kept = nullptr) {
     V3<T> x, v; M3<T> C;
     load_xvC(in, p, x, v, C);
     M3<T> F = load_F(in, p);
@@ -407,7 +415,9 @@ PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, con
     load_material(P, mat, p, mu, lam, ys);
     Vec4<T> part = adj_cur.A0[p];                           // partial x-adjoint from g2p_bwd_body
     V3<T> gx, gv; M3<T> gC, gF;
-    p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(adj_next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
+    SvdRec<T> rec;
+    if (kSvdGiven) rec = load_svd(*svd_kept, p);
+    p2g_bwd_core<T, kSvdGiven>(P, x, v, C, F, mu, lam, ys, g_in, load_F(adj_next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF, &rec);
     store_xvC(adj_cur, p, gx, gv, gC);
     store_F(adj_cur, p, gF);
 }

@@ -200,6 +200,10 @@ struct Engine : plb_engine {
         return cap_events[cap_ev_used++];
     }
     std::vector<char> fwd_ok;       // host view: slot s+1 holds the frame the forward substep produced from slot s
+    // SVD store (PLB_SVD_STORE=1): U, sigma, V of F_tmp per particle and frame slot, written by the forward P2G, read by the
+    // backward pass instead of re-running the Jacobi iteration; 84 B (f32) per particle and frame
+    T* svd_store = nullptr; bool svd_enable = false;
+    std::vector<char> svd_ok;       // host view: svd_store[slot] holds the decomposition of the substep that started at slot
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
     int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
     int* d_vals = nullptr; int* d_vals2 = nullptr; void* d_cub = nullptr; size_t cub_bytes = 0; T* frame_tmp = nullptr;
@@ -222,7 +226,7 @@ struct Engine : plb_engine {
         cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_cub); cudaFree(frame_tmp);
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt); cudaFree(store.overflow); cudaFree(d_cursor);
-        cudaFree(d_inv_perm); cudaFree(d_sel_idx); cudaFree(d_sel_val);
+        cudaFree(d_inv_perm); cudaFree(d_sel_idx); cudaFree(d_sel_val); cudaFree(svd_store);
         cudaFree(sets[1].in); cudaFree(sets[1].out); cudaFree(sets[1].list); cudaFree(sets[1].count);
         for (cudaEvent_t e : cap_events) cudaEventDestroy(e);
         if (side_stream) cudaStreamDestroy(side_stream);
@@ -292,6 +296,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_BWD_MINB")) bwd_minb = atoi(v);
         if (const char* v = getenv("PLB_BWD_OVERLAP")) bwd_overlap = atoi(v) != 0;
         if (const char* v = getenv("PLB_GRID_SCAN")) grid_scan = atoi(v) != 0;
+        if (const char* v = getenv("PLB_SVD_STORE")) svd_enable = atoi(v) != 0;
         if (const char* v = getenv("PLB_FLUSH_RUNS")) flush_mode = atoi(v) != 0 ? 1 : 0;
         if (const char* v = getenv("PLB_GRID_BWD_V2")) grid_bwd_v2 = atoi(v) != 0;
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
@@ -301,8 +306,10 @@ struct Engine : plb_engine {
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
             // the full tiles want the whole shared-memory carve-out (4 x 57 KB per SM); the driver's default choice left the
             // backward kernel at 3 CTAs per SM by shared memory (ncu launch__occupancy_limit_shared_mem)
             const int carve = cudaSharedmemCarveoutMaxShared;
@@ -310,8 +317,10 @@ struct Engine : plb_engine {
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         }
         n_blocks = (c.n_grid / 4) * (c.n_grid / 4) * (c.n_grid / 4);
         PLB_CUDA(cudaMalloc(&d_flags, n_blocks));
@@ -339,6 +348,16 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMemset(d_cursor, 0, 4 * sizeof(int)));
         stored.assign(c.max_frames, 0);
         fwd_ok.assign(c.max_frames, 0);
+        svd_ok.assign(c.max_frames, 0);
+        if (svd_enable && tile_scatter && sparse) {
+            const size_t sb = (size_t)c.max_frames * kSvdScalars * n_pad * sizeof(T);
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            if (sb + ((size_t)4 << 30) >= free_b || cudaMalloc(&svd_store, sb) != cudaSuccess) {
+                cudaGetLastError();          // not enough memory: the backward pass keeps recomputing the SVD
+                svd_store = nullptr;
+            }
+        }
         PLB_CUDA(cudaMalloc(&store.overflow, sizeof(int)));
         PLB_CUDA(cudaMemset(store.overflow, 0, sizeof(int)));
         PLB_CUDA(cudaMalloc(&d_perm, n_pad * sizeof(int)));
@@ -360,7 +379,7 @@ struct Engine : plb_engine {
     int synchronize() override { PLB_CUDA(cudaStreamSynchronize(stream)); return PLB_OK; }
 
     // frame `s` was overwritten from outside a forward substep: its stored grid and the "successor frame" links are stale
-    void slot_written(int s) { stored[s] = 0; fwd_ok[s] = 0; if (s > 0) fwd_ok[s - 1] = 0; }
+    void slot_written(int s) { stored[s] = 0; fwd_ok[s] = 0; svd_ok[s] = 0; if (s > 0) fwd_ok[s - 1] = 0; }
     int check_slot(int s) { PLB_REQUIRE(s >= 0 && s < cfg.max_frames, "frame slot out of range"); return PLB_OK; }
     int check_pf(int pf, int extra = 0) { PLB_REQUIRE(pf >= 0 && pf + extra < cfg.max_prim_frames, "primitive frame out of range"); return PLB_OK; }
 
@@ -455,6 +474,7 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaGetLastError());
         std::fill(stored.begin(), stored.end(), 0);
         std::fill(fwd_ok.begin(), fwd_ok.end(), 0);
+        std::fill(svd_ok.begin(), svd_ok.end(), 0);
         // size the forward-grid store from the active-block count of this frame (2x margin + 256 blocks)
         if (sparse && cfg.kernel_variant == 0) {
             k_mark_only<T><<<blocks(n), kBlock, 0, stream>>>(P, frame_base(slot), n_pad, d_flags);
@@ -618,7 +638,7 @@ struct Engine : plb_engine {
             prof_begin(K_P2G);
             auto kern = fwd_plane ? (fwd_minb >= 6 ? k_g2p_p2g_warp<T, true, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, true, OccSel<T>::fwd_lo>)
                                   : (fwd_minb >= 6 ? k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>);
-            kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), grid_out, grid_in, fl, flush_mode);
+            kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), grid_out, grid_in, fl, flush_mode, svd_store);
             prof_end();
             enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i));
             launches++;
@@ -678,28 +698,31 @@ struct Engine : plb_engine {
         prof_end();
         launches++;
     }
-    void launch_p2g_bwd(SlotRef si, T* a_next, T* a_cur) {
+    void launch_p2g_bwd(SlotRef si, T* a_next, T* a_cur, bool svd) {
         prof_begin(K_P2G_BWD);
-        k_p2g_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in);
+        if (svd) k_p2g_bwd<T, true><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in, svd_store);
+        else k_p2g_bwd<T, false><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in, (T*)nullptr);
         prof_end();
         launches++;
     }
-    void launch_bwd_fused(SlotRef s_cur, SlotRef s_prev, T* a_next, T* a_cur, const GridSet& gs) {
+    void launch_bwd_fused(SlotRef s_cur, SlotRef s_prev, T* a_next, T* a_cur, const GridSet& gs, bool svd) {
         const int nbc = blocks(cfg.n_particles, cta);
         const size_t sm = tile_smem_bytes(bwd_plane, cta);
         prof_begin(K_P2G_BWD);
-        auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo>)
-                              : (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo>);
-        kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode);
+        // (the plane-tile variants are instantiated without the SVD-store form: they lost at every size measured)
+        auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo, false>)
+                    : svd     ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>)
+                              : (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, false>);
+        kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode, svd_store);
         prof_end();
         launches++;
     }
     // One backward substep; `restore` = the forward grid of this slot is in the store; next_ok = slot si+1 holds G2P's output.
-    void enqueue_bwd(SlotRef si, SlotRef pf, bool restore, bool next_ok, T* a_next, T* a_cur) {
+    void enqueue_bwd(SlotRef si, SlotRef pf, bool restore, bool next_ok, bool svd, T* a_next, T* a_cur) {
         enqueue_bwd_grid_pre(si, pf, restore, sets[0], stream);
         launch_g2p_bwd(si, a_next, a_cur, sets[0], next_ok);
         enqueue_bwd_grid_adj(pf, sets[0]);
-        launch_p2g_bwd(si, a_next, a_cur);
+        launch_p2g_bwd(si, a_next, a_cur, svd);
     }
     // n >= 2 backward substeps (i = n-1 .. 0) with p2g.grad(i) and g2p.grad(i-1) fused; c = adjoint ping-pong parity at entry.
     // Inside a graph every frame i+1 was produced by the forward graph, so the fused kernel takes clamp masks / gather sums from
@@ -707,18 +730,19 @@ struct Engine : plb_engine {
     // overlap (stream capture only): the grid pre-stage (restore + grid operator) of substep i-1 is captured on a forked branch
     // and runs beside the particle kernel and grid adjoint of substep i; the two grid sets alternate by substep parity:
     //   Pre(j) -> K(j) = [p2g.grad(j+1) +] g2p.grad(j) -> A(j) = grid adjoint(j) -> K(j-1);   Pre(j-2) waits for A(j) (same set).
-    void enqueue_bwd_fused(int n, bool restore, bool next_ok, int c, SlotRef (*mk)(const Engine*, int, int), bool overlap) {
+    void enqueue_bwd_fused(int n, bool restore, bool next_ok, bool svd, int c, SlotRef (*mk)(const Engine*, int, int), bool overlap) {
+        svd = svd && !bwd_plane;
         if (!overlap) {
             enqueue_bwd_grid_pre(mk(this, 0, n - 1), mk(this, 2, n - 1), restore, sets[0], stream);
             launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[0], next_ok);
             enqueue_bwd_grid_adj(mk(this, 2, n - 1), sets[0]);
             for (int i = n - 1; i >= 1; i--) {
                 enqueue_bwd_grid_pre(mk(this, 0, i - 1), mk(this, 2, i - 1), restore, sets[0], stream);
-                launch_bwd_fused(mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1], sets[0]);
+                launch_bwd_fused(mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1], sets[0], svd);
                 c ^= 1;
                 enqueue_bwd_grid_adj(mk(this, 2, i - 1), sets[0]);
             }
-            launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1]);
+            launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1], svd);
             return;
         }
         cap_ev_used = 0;
@@ -742,13 +766,13 @@ struct Engine : plb_engine {
                 ev_pre = next_event();
                 cudaEventRecord(ev_pre, side_stream);
             }
-            launch_bwd_fused(mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1], sets[(i - 1) & 1]);
+            launch_bwd_fused(mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1], sets[(i - 1) & 1], svd);
             c ^= 1;
             enqueue_bwd_grid_adj(mk(this, 2, i - 1), sets[(i - 1) & 1]);
             ev_adj = next_event();
             cudaEventRecord(ev_adj, stream);
         }
-        launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1]);
+        launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1], svd);
     }
     // push my listed zone blocks of `grid` into the neighbours' inboxes, publish, wait for theirs
     void halo_exchange(const Vec4<T>* grid) {
@@ -770,10 +794,10 @@ struct Engine : plb_engine {
         if (tile_scatter) {
             const int nbc = blocks(cfg.n_particles, cta);
             const size_t sm = tile_smem_bytes(fwd_plane, cta);
-            if (fwd_plane) k_p2g_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode);
-            else k_p2g_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode);
+            if (fwd_plane) k_p2g_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode, svd_store);
+            else k_p2g_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode, svd_store);
         } else {
-            k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl);
+            k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, svd_store);
         }
     }
     // (which: 0 slot_in base, 1 slot_out base, 2 pose frame base; rel) -> cursor-relative reference
@@ -791,13 +815,14 @@ struct Engine : plb_engine {
         slot_written(so);
         stored[si] = store.vals != nullptr;
         fwd_ok[si] = (so == si + 1);
+        svd_ok[si] = svd_store != nullptr;
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
     }
     int substep_bwd(int si, int pf) override {
         if (int r = check_slot(si)) return r;
         if (int r = check_pf(pf, 1)) return r;
-        enqueue_bwd(abs_ref(si), abs_ref(pf), stored[si] && store.vals, fwd_ok[si] != 0, adj[cur], adj[cur ^ 1]);
+        enqueue_bwd(abs_ref(si), abs_ref(pf), stored[si] && store.vals, fwd_ok[si] != 0, svd_ok[si] && svd_store, adj[cur], adj[cur ^ 1]);
         cur ^= 1;
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
@@ -811,14 +836,14 @@ struct Engine : plb_engine {
             long long l0 = launches;
             PLB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
             const bool fused = fuse && tile_scatter && sparse && key.n >= 2;
-            const bool restore = (key.stored & 1) != 0, next_ok = (key.stored & 2) != 0;
+            const bool restore = (key.stored & 1) != 0, next_ok = (key.stored & 2) != 0, svd = (key.stored & 4) != 0;
             if (key.dir == 0) {
                 if (fused) enqueue_fwd_fused(key.n, &Engine::mk_cursor);
                 else for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
             } else {
                 int c = key.parity;
-                if (fused) enqueue_bwd_fused(key.n, restore, next_ok, c, &Engine::mk_cursor, bwd_overlap && restore && !slab.on);
-                else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), restore, next_ok, adj[c], adj[c ^ 1]); c ^= 1; }
+                if (fused) enqueue_bwd_fused(key.n, restore, next_ok, svd, c, &Engine::mk_cursor, bwd_overlap && restore && !slab.on);
+                else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), restore, next_ok, svd, adj[c], adj[c ^ 1]); c ^= 1; }
             }
             cudaError_t ce = cudaStreamEndCapture(stream, &g);
             graph_nodes[key] = launches - l0;
@@ -847,23 +872,23 @@ struct Engine : plb_engine {
         }
         GraphKey key{0, n, 0, (store.vals != nullptr ? 1 : 0) | (scan_mode() ? 2 : 0)};
         if (int r = launch_graph(key, slot0, pf0)) return r;
-        for (int i = 0; i < n; i++) { stored[slot0 + i] = store.vals != nullptr; fwd_ok[slot0 + i] = 1; }
-        stored[slot0 + n] = 0; fwd_ok[slot0 + n] = 0;
+        for (int i = 0; i < n; i++) { stored[slot0 + i] = store.vals != nullptr; fwd_ok[slot0 + i] = 1; svd_ok[slot0 + i] = svd_store != nullptr; }
+        stored[slot0 + n] = 0; fwd_ok[slot0 + n] = 0; svd_ok[slot0 + n] = 0;
         return PLB_OK;
     }
     int step_bwd(int slot0, int pf0, int n) override {
         if (n <= 0) return PLB_OK;
         if (int r = check_slot(slot0 + n - 1)) return r;
         if (int r = check_pf(pf0, n)) return r;
-        int n_stored = 0, n_ok = 0;
-        for (int i = 0; i < n; i++) { n_stored += stored[slot0 + i] ? 1 : 0; n_ok += fwd_ok[slot0 + i] ? 1 : 0; }
+        int n_stored = 0, n_ok = 0, n_svd = 0;
+        for (int i = 0; i < n; i++) { n_stored += stored[slot0 + i] ? 1 : 0; n_ok += fwd_ok[slot0 + i] ? 1 : 0; n_svd += svd_ok[slot0 + i] ? 1 : 0; }
         // the graphs take clamp masks / gather sums from the successor frames: every substep must have been run forward
         bool uniform = (n_stored == 0 || n_stored == n) && n_ok == n;
         if (!use_graphs || prof_on || !sparse || !uniform) {
             for (int i = n - 1; i >= 0; i--) if (int r = substep_bwd(slot0 + i, pf0 + i)) return r;
             return PLB_OK;
         }
-        GraphKey key{1, n, cur, ((n_stored == n && store.vals) ? 1 : 0) | 2};
+        GraphKey key{1, n, cur, ((n_stored == n && store.vals) ? 1 : 0) | 2 | ((n_svd == n && svd_store) ? 4 : 0)};
         if (int r = launch_graph(key, slot0, pf0)) return r;
         cur ^= (n & 1);
         return PLB_OK;
@@ -965,7 +990,7 @@ struct Engine : plb_engine {
         halo_add(g_out, 1);
         k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, g_out, g_in, 1, d_prim_grad, d_list, d_nactive, own_lo(), own_hi());
         prof_end(); prof_begin(K_P2G_BWD);
-        k_p2g_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(si), adj[cur], adj[cur ^ 1], material(), g_in);
+        k_p2g_bwd<T, false><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(si), adj[cur], adj[cur ^ 1], material(), g_in, (T*)nullptr);
         prof_end();
         launches += 2;
         cur ^= 1;
@@ -1334,7 +1359,7 @@ struct Engine : plb_engine {
     int count_active(int slot, long long* n) override {
         if (int r = check_slot(slot)) return r;
         // scatter this frame's particles (no F store), count, then clear grid_in again
-        k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(slot), abs_ref(slot), 0, material(), grid_in, nullptr);
+        k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(slot), abs_ref(slot), 0, material(), grid_in, nullptr, (T*)nullptr);
         PLB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
         k_count_active<T><<<blocks(n_nodes), kBlock, 0, stream>>>(n_nodes, grid_in, d_count);
         launches += 2;

@@ -244,11 +244,12 @@ template <class T> __global__ void k_add_scalar(long long n, T* dst, const T* __
 // ------------------------------------------------------------------------------------------------ substep
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
-                                                int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags) {
+                                                int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags, T* svd_base) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
     FramePtr<T> fin = frame_at(frames, slot_in.get(), n_pad);
-    p2g_body<T>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in);
+    SvdPtr<T> sp = svd_at(svd_base, slot_in.get(), n_pad);
+    p2g_body<T>(p, P, fin, frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in, svd_base ? &sp : nullptr);
     if (flags) mark_blocks<T>(P, load_x(fin, p), flags);
 }
 
@@ -261,10 +262,12 @@ template <class T, bool kPlane> __device__ __forceinline__ Vec4<T>* warp_tile_pt
 
 template <class T, bool kPlane>
 __global__ void __launch_bounds__(kBlock) k_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
-                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode) {
+                                                     int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode, T* svd_base) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
+    SvdPtr<T> sp = svd_at(svd_base, slot_in.get(), n_pad);
     t_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
-                     frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in, flags, flush_mode);
+                     frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in, flags, flush_mode,
+                     svd_base ? &sp : nullptr);
 }
 
 // G2P of substep s + P2G of substep s+1 in one pass over the particles (inside env-step graphs)
@@ -273,11 +276,12 @@ __global__ void __launch_bounds__(kBlock) k_p2g_warp(SimConst<T> P, T* frames, l
 template <class T, bool kPlane, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB) k_g2p_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in,
                                                                            SlotRef slot_mid, SlotRef slot_out, Material<T> mat,
-                                                                           const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags, int flush_mode) {
+                                                                           const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags, int flush_mode, T* svd_base) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
+    SvdPtr<T> sp = svd_at(svd_base, slot_mid.get(), n_pad);          // the P2G half decomposes F_tmp of frame `mid`
     t_g2p_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                          frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_mid.get(), n_pad),
-                         frame_at(frames, slot_out.get(), n_pad), mat, grid_out, grid_in, flags, flush_mode);
+                         frame_at(frames, slot_out.get(), n_pad), mat, grid_out, grid_in, flags, flush_mode, svd_base ? &sp : nullptr);
 }
 
 // g2p.grad; next_ok: slot_in + 1 holds the frame G2P produced from slot_in (clamp masks and gather sum are read from it)
@@ -293,14 +297,16 @@ __global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_warp(SimCon
 }
 
 // p2g.grad of substep s + g2p.grad of substep s-1 (inside env-step graphs; frame s was produced by G2P(s-1) there)
-template <class T, bool kPlane, int kMinB>
+// kSvd: the decomposition of F_tmp(s) comes from the SVD store (written by the forward pass) instead of the Jacobi iteration
+template <class T, bool kPlane, int kMinB, bool kSvd>
 __global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
                                                                                    SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
-                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode) {
+                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode, T* svd_base) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    t_p2g_bwd_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
-                                 frame_at(frames, slot_s.get(), n_pad), frame_at(frames, slot_prev.get(), n_pad), frame_at(adj_next, 0, n_pad),
-                                 frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out, flush_mode);
+    SvdPtr<T> sp = svd_at(svd_base, slot_s.get(), n_pad);
+    t_p2g_bwd_g2p_bwd<T, kPlane, kSvd>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+                                       frame_at(frames, slot_s.get(), n_pad), frame_at(frames, slot_prev.get(), n_pad), frame_at(adj_next, 0, n_pad),
+                                       frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out, flush_mode, &sp);
 }
 
 template <class T>
@@ -507,12 +513,13 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd(SimConst<T> P, PrimSet<T> p
     }
 }
 
-template <class T>
+template <class T, bool kSvd>
 __global__ void __launch_bounds__(kBlock, Occ<T>::p2g_bwd) k_p2g_bwd(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, T* adj_next,
-                                                    T* adj_cur, Material<T> mat, const Vec4<T>* g_in) {
+                                                    T* adj_cur, Material<T> mat, const Vec4<T>* g_in, T* svd_base) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_particles) return;
-    p2g_bwd_body<T>(p, P, frame_at(frames, slot_in.get(), n_pad), frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad), mat, g_in);
+    SvdPtr<T> sp = svd_at(svd_base, slot_in.get(), n_pad);
+    p2g_bwd_body<T, kSvd>(p, P, frame_at(frames, slot_in.get(), n_pad), frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad), mat, g_in, &sp);
 }
 
 // ------------------------------------------------------------------------------------------------ loss

@@ -73,15 +73,56 @@ template <class T> struct P2GState {      // everything the adjoint needs from t
     bool yield;
 };
 
+// SVD of F_tmp of one particle and substep.  The forward pass can keep it per frame (21 scalars per particle: 5 Vec4 planes +
+// 1 scalar plane, `SvdPtr`) so that the backward pass loads it instead of re-running the Jacobi iteration (~500 of the fused
+// backward kernel's ~4400 instructions per warp); HBM has the headroom (the particle kernels use 2-19 % of it).
+template <class T> struct SvdRec { M3<T> U, V; V3<T> sig; };
+template <class T> struct SvdPtr { Vec4<T>* q[5]; T* s; };
+constexpr int kSvdScalars = 21;
+template <class T> PLB_HD SvdPtr<T> svd_at(T* base, long long slot, long long n_pad) {
+    T* b = base + slot * kSvdScalars * n_pad;
+    SvdPtr<T> r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.q[i] = reinterpret_cast<Vec4<T>*>(b + 4 * i * n_pad);
+    r.s = b + 20 * n_pad;
+    return r;
+}
+template <class T> PLB_HD void store_svd(const SvdPtr<T>& f, int p, const SvdRec<T>& r) {
+    f.q[0][p] = mk4<T>(r.U.m[0][0], r.U.m[0][1], r.U.m[0][2], r.U.m[1][0]);
+    f.q[1][p] = mk4<T>(r.U.m[1][1], r.U.m[1][2], r.U.m[2][0], r.U.m[2][1]);
+    f.q[2][p] = mk4<T>(r.V.m[0][0], r.V.m[0][1], r.V.m[0][2], r.V.m[1][0]);
+    f.q[3][p] = mk4<T>(r.V.m[1][1], r.V.m[1][2], r.V.m[2][0], r.V.m[2][1]);
+    f.q[4][p] = mk4<T>(r.U.m[2][2], r.V.m[2][2], r.sig.x, r.sig.y);
+    f.s[p] = r.sig.z;
+}
+template <class T> PLB_HD SvdRec<T> load_svd(const SvdPtr<T>& f, int p) {
+    Vec4<T> a = f.q[0][p], b = f.q[1][p], c = f.q[2][p], d = f.q[3][p], e = f.q[4][p];
+    SvdRec<T> r;
+    r.U.m[0][0] = a.x; r.U.m[0][1] = a.y; r.U.m[0][2] = a.z; r.U.m[1][0] = a.w;
+    r.U.m[1][1] = b.x; r.U.m[1][2] = b.y; r.U.m[2][0] = b.z; r.U.m[2][1] = b.w;
+    r.V.m[0][0] = c.x; r.V.m[0][1] = c.y; r.V.m[0][2] = c.z; r.V.m[1][0] = c.w;
+    r.V.m[1][1] = d.x; r.V.m[1][2] = d.y; r.V.m[2][0] = d.z; r.V.m[2][1] = d.w;
+    r.U.m[2][2] = e.x; r.V.m[2][2] = e.y;
+    r.sig = mk3<T>(e.z, e.w, f.s[p]);
+    return r;
+}
+
 // Forward: returns new_F (= F[f+1]) and the APIC affine matrix (stress + p_mass C).
-template <class T>
+// kSvdGiven: `svd` holds the decomposition of F_tmp (loaded from the store); otherwise it is computed and, if svd != nullptr,
+// returned through it.
+template <class T, bool kSvdGiven = false>
 PLB_HD void p2g_particle(const SimConst<T>& P, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys,
-                         M3<T>& new_F, M3<T>& affine, P2GState<T>* keep = nullptr) {
+                         M3<T>& new_F, M3<T>& affine, P2GState<T>* keep = nullptr, SvdRec<T>* svd = nullptr) {
     M3<T> A = identM<T>() + P.dt * C;
     M3<T> F_tmp = mm(A, F);
     M3<T> U, V;
     V3<T> sig;
-    svd3(F_tmp, U, sig, V);
+    if (kSvdGiven) {
+        U = svd->U; V = svd->V; sig = svd->sig;
+    } else {
+        svd3(F_tmp, U, sig, V);
+        if (svd) { svd->U = U; svd->V = V; svd->sig = sig; }
+    }
     // compute_von_mises
     V3<T> sc = mk3<T>(tmax(sig.x, T(0.05)), tmax(sig.y, T(0.05)), tmax(sig.z, T(0.05)));
     V3<T> eps = mk3<T>(plb_log(sc.x), plb_log(sc.y), plb_log(sc.z));

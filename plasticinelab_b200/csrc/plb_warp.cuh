@@ -241,21 +241,21 @@ PLB_HD void mark_blocks(const SimConst<T>& P, V3<T> x, unsigned char* flags) {
 // P2G of one substep
 template <class T, bool kPlane>
 PLB_D void t_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>& fout, bool store_F,
-                 const Material<T>& mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode = 0) {
+                 const Material<T>& mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode = 0, const SvdPtr<T>* svd_keep = nullptr) {
     const bool valid = p < P.n_particles;
     if (kPlane) {
         if (!valid) p = P.n_particles - 1;
         V3<T> x = load_x(fin, p);
         WarpPlaneScatter<T> sc{tile, grid_in, lane, valid ? cell_key(x, P.inv_dx) : -1, P.n_grid};
         sc.init();
-        p2g_body<T, WarpPlaneScatter<T>>(p, P, fin, fout, store_F && valid, mat, sc);
+        p2g_body<T, WarpPlaneScatter<T>>(p, P, fin, fout, store_F && valid, mat, sc, svd_keep);
         if (flags && valid) mark_blocks<T>(P, x, flags);
     } else {
         tile_init(tile, lane);
         int key = -1;
         if (valid) {
             WarpTileScatter<T> sc{tile, lane};
-            p2g_body<T, WarpTileScatter<T>>(p, P, fin, fout, store_F, mat, sc);
+            p2g_body<T, WarpTileScatter<T>>(p, P, fin, fout, store_F, mat, sc, svd_keep);
             V3<T> x = load_x(fin, p);
             key = cell_key(x, P.inv_dx);
             if (flags) mark_blocks<T>(P, x, flags);
@@ -268,7 +268,7 @@ PLB_D void t_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const Fra
 template <class T, bool kPlane>
 PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>& fmid,
                      const FramePtr<T>& fout, const Material<T>& mat, const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags,
-                     int flush_mode = 0) {
+                     int flush_mode = 0, const SvdPtr<T>* svd_keep = nullptr) {
     const bool valid = p < P.n_particles;
     if (kPlane) {
         if (!valid) p = P.n_particles - 1;
@@ -281,9 +281,11 @@ PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
         WarpPlaneScatter<T> sc{tile, grid_in, lane, valid ? cell_key(nx, P.inv_dx) : -1, P.n_grid};
         sc.init();
         M3<T> new_F;
-        p2g_core<T, WarpPlaneScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
+        SvdRec<T> rec;
+        p2g_core<T, WarpPlaneScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc, svd_keep ? &rec : nullptr);
         if (valid) {
             store_F(fout, p, new_F);
+            if (svd_keep) store_svd(*svd_keep, p, rec);
             if (flags) mark_blocks<T>(P, nx, flags);
         }
     } else {
@@ -298,8 +300,10 @@ PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
             store_xvC(fmid, p, nx, nv, nC);
             M3<T> new_F;
             WarpTileScatter<T> sc{tile, lane};
-            p2g_core<T, WarpTileScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc);
+            SvdRec<T> rec;
+            p2g_core<T, WarpTileScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc, svd_keep ? &rec : nullptr);
             store_F(fout, p, new_F);
+            if (svd_keep) store_svd(*svd_keep, p, rec);
             key = cell_key(nx, P.inv_dx);
             if (flags) mark_blocks<T>(P, nx, flags);
         }
@@ -351,10 +355,10 @@ PLB_D void t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
 
 // p2g.grad of substep s (frame fs) + g2p.grad of substep s-1 (frame fprev); the adjoint of (x,v,C)[s] stays in registers and
 // the state (x,v)[s] this thread loaded anyway is what G2P(s-1) produced (clamp masks + gather sum come from it)
-template <class T, bool kPlane>
+template <class T, bool kPlane, bool kSvdGiven = false>
 PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fs, const FramePtr<T>& fprev,
                              const FramePtr<T>& next, const FramePtr<T>& cur, const Material<T>& mat, const Vec4<T>* g_in,
-                             const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0) {
+                             const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0, const SvdPtr<T>* svd_kept = nullptr) {
     const bool valid = p < P.n_particles;
     if (valid) prefetch_frame_rest(fprev, p);          // for the next backward kernel (p2g.grad of substep s-1)
     if (kPlane) {
@@ -366,7 +370,9 @@ PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& 
         load_material(P, mat, p, mu, lam, ys);
         Vec4<T> part = cur.A0[p];
         V3<T> gx, gv; M3<T> gC, gF;
-        p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
+        SvdRec<T> rec;
+        if (kSvdGiven) rec = load_svd(*svd_kept, p);
+        p2g_bwd_core<T, kSvdGiven>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF, &rec);
         if (valid) store_F(cur, p, gF);
         V3<T> xp = load_x(fprev, p);
         WarpPlaneScatter<T> sc{tile, g_out, lane, valid ? cell_key(xp, P.inv_dx) : -1, P.n_grid};
@@ -384,7 +390,9 @@ PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& 
             load_material(P, mat, p, mu, lam, ys);
             Vec4<T> part = cur.A0[p];
             V3<T> gx, gv; M3<T> gC, gF;
-            p2g_bwd_core<T>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF);
+            SvdRec<T> rec;
+        if (kSvdGiven) rec = load_svd(*svd_kept, p);
+        p2g_bwd_core<T, kSvdGiven>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF, &rec);
             store_F(cur, p, gF);
             V3<T> xp = load_x(fprev, p);
             WarpTileScatter<T> sc{tile, lane};

@@ -81,7 +81,7 @@ template <class T> struct World {
 template <class T, bool kPlane>
 int check(const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x, const double* v, const double* F,
           const double* C, const double* pose0, const double* pose1, const double* gx, const double* gv, const double* gF,
-          const double* gC, int stored_next, int flush_mode, double* out) {
+          const double* gC, int stored_next, int flush_mode, int svd_store, double* out) {
     World<T> R(*c, pd, softness, pose0, pose1), W(*c, pd, softness, pose0, pose1);
     const int n = c->n_particles;
     const int tile_elems = kPlane ? kPlaneVec4 : kTileVec4;
@@ -117,9 +117,13 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
 
     // ------------------------------------------------ warp kernels
     W.pack(W.f[0], x, v, F, C);
+    // SVD store: two frame slots of 21 scalars per particle (poisoned: whatever the backward loads must have been stored)
+    std::vector<T> svd((size_t)2 * kSvdScalars * W.n_pad);
+    std::memset(svd.data(), 0xFF, svd.size() * sizeof(T));
+    SvdPtr<T> sv0 = svd_at(svd.data(), 0, W.n_pad), sv1 = svd_at(svd.data(), 1, W.n_pad);
     // (1) P2G of substep 0
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), true, W.mat, W.grid_in.data(), W.flags.data(), flush_mode);
+        t_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), true, W.mat, W.grid_in.data(), W.flags.data(), flush_mode, svd_store ? &sv0 : nullptr);
     });
     out[o++] = rel_dev(W.grid_in, ref_in0);
     {   // flags: exactly the blocks touched by a particle stencil
@@ -130,7 +134,7 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     W.grid_op(W.grid_out[0]);
     // (2) fused G2P(0) + P2G(1)
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_g2p_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), W.fr(2), W.mat, W.grid_out[0].data(), W.grid_in.data(), nullptr, flush_mode);
+        t_g2p_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), W.fr(2), W.mat, W.grid_out[0].data(), W.grid_in.data(), nullptr, flush_mode, svd_store ? &sv1 : nullptr);
     });
     out[o++] = rel_dev(W.grid_in, ref_in1);
     out[o++] = rel_dev(W.f[1].data(), R.f[1].data(), W.f[1].size());
@@ -152,7 +156,10 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     W.grid_adj(ref_in1);
     // (4) fused p2g.grad(1) + g2p.grad(0)
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_p2g_bwd_g2p_bwd<T, kPlane>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode);
+        if (svd_store)
+            t_p2g_bwd_g2p_bwd<T, kPlane, true>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode, &sv1);
+        else
+            t_p2g_bwd_g2p_bwd<T, kPlane, false>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode);
     });
     out[o++] = rel_dev(W.g_out, ref_gout0);
     {   // dF[1] (F planes of adj 1) and the partial x-adjoint of frame 0 (written into adj 2's A0 plane)
@@ -235,12 +242,12 @@ int check_grid_bwd(const plb_config* c, const plb_primitive_desc* pd, double sof
 
 extern "C" int wemul_check(int dtype, int plane, const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x,
                            const double* v, const double* F, const double* C, const double* pose0, const double* pose1, const double* gx,
-                           const double* gv, const double* gF, const double* gC, int stored_next, int flush_mode, double* out) {
+                           const double* gv, const double* gF, const double* gC, int stored_next, int flush_mode, int svd_store, double* out) {
     if (dtype == PLB_F32)
-        return plane ? check<float, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out)
-                     : check<float, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out);
-    return plane ? check<double, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out)
-                 : check<double, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, out);
+        return plane ? check<float, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out)
+                     : check<float, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out);
+    return plane ? check<double, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out)
+                 : check<double, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out);
 }
 
 extern "C" int wemul_check_grid_bwd(int dtype, const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x, const double* v,
