@@ -344,13 +344,19 @@ PLB_HD void grid_bwd_body(long long node, const SimConst<T>& P, const PrimSet<T>
 // p2g.grad + svd_grad + compute_F_tmp.grad: gathers g_in at 27 nodes, finishes the adjoint of frame f in adj_cur.
 // register-level core: state of frame f, adjoint of F[f+1], partial x-adjoint -> full adjoint of frame f
 // kSvdGiven: `svd` holds the forward's decomposition of F_tmp (SVD store) and the Jacobi iteration is not re-run
-template <class T, bool kSvdGiven = false>
+// kTwoPhase (with kSvdGiven): the forward particle math is cheap once the SVD is given (~250 instructions), so it is run
+// twice -- before the 27-node gather only for `affine`, and again after it for the adjoint -- instead of keeping its ~58
+// intermediate values (P2GState) in registers across the gather loop, which is where the backward kernels' register peak is.
+template <class T, bool kSvdGiven = false, bool kTwoPhase = false>
 PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys, const Vec4<T>* g_in,
                          const M3<T>& gF_next, V3<T> gx_partial, V3<T>& gx_out, V3<T>& gv_out, M3<T>& gC, M3<T>& gF,
-                         SvdRec<T>* svd = nullptr) {
+                         SvdRec<T>* svd = nullptr, const FramePtr<T>* gF_late = nullptr, int p_late = 0, const FramePtr<T>* state_late = nullptr) {
+    // (kTwoPhase: after the gather loop the adjoint of F[f+1] is loaded from gF_late instead of being passed in gF_next, and
+    //  C, F are loaded again from state_late -- L1 hits -- so that neither occupies registers across the loop)
     M3<T> new_F, affine;
     P2GState<T> keep;
-    p2g_particle<T, kSvdGiven>(P, C, F, mu, lam, ys, new_F, affine, &keep, svd);
+    if (kSvdGiven && kTwoPhase) p2g_particle<T, true>(P, C, F, mu, lam, ys, new_F, affine, nullptr, svd);
+    else p2g_particle<T, kSvdGiven>(P, C, F, mu, lam, ys, new_F, affine, &keep, svd);
     Stencil<T> st = make_stencil(x, P.inv_dx);
     // forward node value: w_o (m_o, p_mass) with m_o = p_mass v + affine (o - fx) dx, evaluated incrementally.
     // With a_o = adjoint of the node momentum: g(weight_o) = a_o . m_o + b_o p_mass;  g(v) = p_mass sum w a;
@@ -403,6 +409,23 @@ PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C,
     gv = P.p_mass * gv;
     gx_out = stencil_backward(st, gw, gfx, P.inv_dx) + gx_partial;
     gv_out = gv;
+    if (kSvdGiven && kTwoPhase) {
+        // second run of the forward particle math, on values the compiler cannot tie to the first run
+        SvdRec<T> r2 = *svd;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) { opaque(r2.U.m[i][j]); opaque(r2.V.m[i][j]); }
+            opaque(r2.sig[i]);
+        }
+        M3<T> nf2, aff2;
+        V3<T> x2, v2; M3<T> C2;
+        load_xvC(*state_late, p_late, x2, v2, C2);
+        M3<T> F2 = load_F(*state_late, p_late);
+        p2g_particle<T, true>(P, C2, F2, mu, lam, ys, nf2, aff2, &keep, &r2);
+        p2g_particle_backward<T>(P, C2, F2, mu, lam, keep, g_aff, load_F(*gF_late, p_late), gC, gF);
+        return;
+    }
     p2g_particle_backward<T>(P, C, F, mu, lam, keep, g_aff, gF_next, gC, gF);
 }
 template <class T, bool kSvdGiven = false>

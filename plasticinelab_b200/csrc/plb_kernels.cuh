@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst
                                                                                    const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode, T* svd_base) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     SvdPtr<T> sp = svd_at(svd_base, slot_s.get(), n_pad);
-    t_p2g_bwd_g2p_bwd<T, kPlane, kSvd>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+    // tight register cap + SVD store: run the (then cheap) forward particle math twice instead of keeping it across the gather
+    t_p2g_bwd_g2p_bwd<T, kPlane, kSvd, (kSvd && kMinB >= 4)>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                                        frame_at(frames, slot_s.get(), n_pad), frame_at(frames, slot_prev.get(), n_pad), frame_at(adj_next, 0, n_pad),
                                        frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out, flush_mode, &sp);
 }

@@ -190,6 +190,16 @@ PLB_HD float plb_rsqrt(float x) { return 1.0f / sqrtf(x); }
 template <class T> PLB_HD T tmax(T a, T b) { return (b < a) ? a : b; }
 template <class T> PLB_HD T tmin(T a, T b) { return (a < b) ? a : b; }
 
+// Optimisation barrier for one value: the compiler may not assume it equals anything it computed before (used to make a
+// deliberately repeated computation really repeat instead of keeping its results alive in registers).
+#if defined(__CUDA_ARCH__)
+PLB_HD void opaque(float& v) { asm volatile("" : "+f"(v)); }
+PLB_HD void opaque(double& v) { asm volatile("" : "+d"(v)); }
+#else
+PLB_HD void opaque(float&) {}
+PLB_HD void opaque(double&) {}
+#endif
+
 // ---- 4-wide storage vector: 16 B (float) / 32 B (double), the unit of the particle planes and grids
 template <class T> struct alignas(4 * sizeof(T)) Vec4 { T x, y, z, w; };
 template <class T> PLB_HD Vec4<T> mk4(T x, T y, T z, T w) { Vec4<T> r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }

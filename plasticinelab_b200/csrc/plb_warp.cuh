@@ -355,7 +355,7 @@ PLB_D void t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
 
 // p2g.grad of substep s (frame fs) + g2p.grad of substep s-1 (frame fprev); the adjoint of (x,v,C)[s] stays in registers and
 // the state (x,v)[s] this thread loaded anyway is what G2P(s-1) produced (clamp masks + gather sum come from it)
-template <class T, bool kPlane, bool kSvdGiven = false>
+template <class T, bool kPlane, bool kSvdGiven = false, bool kTwoPhase = false>
 PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fs, const FramePtr<T>& fprev,
                              const FramePtr<T>& next, const FramePtr<T>& cur, const Material<T>& mat, const Vec4<T>* g_in,
                              const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0, const SvdPtr<T>* svd_kept = nullptr) {
@@ -372,7 +372,8 @@ PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& 
         V3<T> gx, gv; M3<T> gC, gF;
         SvdRec<T> rec;
         if (kSvdGiven) rec = load_svd(*svd_kept, p);
-        p2g_bwd_core<T, kSvdGiven>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF, &rec);
+        p2g_bwd_core<T, kSvdGiven, kTwoPhase>(P, x, v, C, F, mu, lam, ys, g_in, kTwoPhase ? zeroM<T>() : load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF,
+                                                      &rec, &next, p, &fs);
         if (valid) store_F(cur, p, gF);
         V3<T> xp = load_x(fprev, p);
         WarpPlaneScatter<T> sc{tile, g_out, lane, valid ? cell_key(xp, P.inv_dx) : -1, P.n_grid};
@@ -392,7 +393,8 @@ PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& 
             V3<T> gx, gv; M3<T> gC, gF;
             SvdRec<T> rec;
         if (kSvdGiven) rec = load_svd(*svd_kept, p);
-        p2g_bwd_core<T, kSvdGiven>(P, x, v, C, F, mu, lam, ys, g_in, load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF, &rec);
+        p2g_bwd_core<T, kSvdGiven, kTwoPhase>(P, x, v, C, F, mu, lam, ys, g_in, kTwoPhase ? zeroM<T>() : load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF,
+                                                      &rec, &next, p, &fs);
             store_F(cur, p, gF);
             V3<T> xp = load_x(fprev, p);
             WarpTileScatter<T> sc{tile, lane};

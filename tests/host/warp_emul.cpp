@@ -157,7 +157,7 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     // (4) fused p2g.grad(1) + g2p.grad(0)
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
         if (svd_store)
-            t_p2g_bwd_g2p_bwd<T, kPlane, true>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode, &sv1);
+            t_p2g_bwd_g2p_bwd<T, kPlane, true, kPlane>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode, &sv1);
         else
             t_p2g_bwd_g2p_bwd<T, kPlane, false>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode);
     });
