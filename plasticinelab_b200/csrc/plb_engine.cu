@@ -184,7 +184,7 @@ struct Engine : plb_engine {
     bool bwd_plane = false;         // same for the backward scatter kernels (PLB_BWD_PLANE)
     int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
     int fwd_minb = 5, bwd_minb = 3; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 / PLB_BWD_MINB=4 select the tighter cap)
-    int flush_mode = 0;             // full-tile flush: 0 = per-cell groups, 1 = runs of consecutive lanes (PLB_FLUSH_RUNS=1)
+    int flush_mode = 0;             // full-tile flush: 0 = per-cell groups, 1 = runs of consecutive lanes (PLB_FLUSH_RUNS=1), 2 = two cells per round (PLB_FLUSH_PAIRS=1)
     bool grid_bwd_v2 = true;        // grid adjoint with register-resident pose gradients (k_grid_bwd_sparse_v2); PLB_GRID_BWD_V2=0: array form
     bool grid_scan = false;         // forward grid stage as one kernel (flag scan + store + grid operator), PLB_GRID_SCAN=1
     bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
@@ -298,6 +298,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_GRID_SCAN")) grid_scan = atoi(v) != 0;
         if (const char* v = getenv("PLB_SVD_STORE")) svd_enable = atoi(v) != 0;
         if (const char* v = getenv("PLB_FLUSH_RUNS")) flush_mode = atoi(v) != 0 ? 1 : 0;
+        if (const char* v = getenv("PLB_FLUSH_PAIRS")) flush_mode = atoi(v) != 0 ? 2 : flush_mode;
         if (const char* v = getenv("PLB_GRID_BWD_V2")) grid_bwd_v2 = atoi(v) != 0;
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
         if (tile_scatter) {

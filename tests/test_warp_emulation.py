@@ -45,7 +45,7 @@ def _state(n, seed, box, sort, n_grid):
 PRIMS = [dict(shape='Sphere', radius=0.05, init_pos=(0.47, 0.5, 0.5), friction=0.9, action=dict(dim=3, scale=(0.01,) * 3))]
 
 
-@pytest.mark.parametrize('plane,flush_mode,svd_store', [(0, 0, 0), (0, 1, 0), (1, 0, 0), (0, 0, 1), (1, 0, 1)])
+@pytest.mark.parametrize('plane,flush_mode,svd_store', [(0, 0, 0), (0, 1, 0), (0, 2, 0), (1, 0, 0), (0, 0, 1), (1, 0, 1)])
 @pytest.mark.parametrize('dtype,tol', [('float64', 1e-12), ('float32', 3e-4)])
 @pytest.mark.parametrize('n,box,sort,stored_next', [(100, (0.40, 0.52), True, 1),     # ~2 particles per cell, ragged last warp
                                                     (70, (0.45, 0.50), True, 1),      # one or two cells per warp

@@ -7,9 +7,13 @@ T0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a $OUT/timeline.txt; }
 
 stamp "variants agree (one process, all switches)"
-timeout 300 python -m pytest tests/test_gpu_variants.py -m gpu -q -s -p no:cacheprovider > $OUT/pytest_variants.log 2>&1
+PLB_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_gpu_variants.py -m gpu -q -s -p no:cacheprovider > $OUT/pytest_variants.log 2>&1
 stamp "-> exit $? $(tail -1 $OUT/pytest_variants.log)"
 grep "variants float" $OUT/pytest_variants.log | tee -a $OUT/timeline.txt
+
+stamp "policy path parity (first GPU run)"
+PLB_TEST_POLICY=1 timeout 200 python -m pytest tests/test_gpu_policy.py -m gpu -q -p no:cacheprovider > $OUT/pytest_policy.log 2>&1
+stamp "-> exit $? $(tail -1 $OUT/pytest_policy.log)"
 
 stamp "in-process bench A/B"
 timeout ${AB_TIMEOUT:-420} python tools/ab_bench.py $OUT ${AB_BUDGET:-330} 2>&1 | tee -a $OUT/timeline.txt
