@@ -93,7 +93,11 @@ template <class T> inline void scatter_add4(Vec4<T>* addr, Vec4<T> v) { addr->x 
 template <class T> inline void scatter_add1(T* addr, T v) { *addr += v; }
 #endif
 
+#ifdef PLB_INDEX32
+PLB_HD long long node_index(int n, int i, int j, int k) { return (long long)((i * n + j) * n + k); }      // n <= 1024: fits 31 bits
+#else
 PLB_HD long long node_index(int n, int i, int j, int k) { return ((long long)i * n + j) * n + k; }
+#endif
 
 // Scatter policy used by the two scattering bodies.  Direct: one (vector) atomic per node and particle.
 // The CUDA kernels can substitute WarpTileScatter (plb_kernels.cuh), which pre-reduces a warp's contributions.

@@ -287,6 +287,7 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMemset(d_acc, 0, (kAccN + 1 + 8) * sizeof(double)));
         PLB_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
         PLB_REQUIRE(c.n_grid % 4 == 0, "n_grid must be a multiple of 4");
+        PLB_REQUIRE(c.n_grid <= 1024, "n_grid above 1024 is not supported (cell keys pack 10 bits per axis)");
         sparse = c.kernel_variant != 1;
         tile_scatter = c.kernel_variant == 0;
         if (const char* v = getenv("PLB_FWD_PLANE")) fwd_plane = atoi(v) != 0;
