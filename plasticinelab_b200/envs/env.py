@@ -50,7 +50,16 @@ class PlasticineEnv(_EnvBase):
         return self._get_obs()
 
     def step(self, action):
+        self.begin_step(action)
+        return self.finish_step(action)
+
+    # the two halves of `step`: `begin_step` only enqueues work on this env's CUDA stream (the S substeps are one graph
+    # launch), `finish_step` reads loss and observation back (device sync).  `VecPlasticineEnv` calls begin_step on every
+    # env before the first finish_step so that the envs' kernels overlap on the GPU.
+    def begin_step(self, action):
         self.taichi_env.step(action)
+
+    def finish_step(self, action):
         info = self.taichi_env.compute_loss()
         self._recorded_actions.append(action)
         obs, reward = self._get_obs(), info["reward"]

@@ -81,3 +81,24 @@ def test_kernel_variants_agree(monkeypatch, dtype):
         if not (dl < ltol and dg < gtol and dx < xtol):
             bad.append((name, dl, dg, dx))
     assert not bad, bad
+
+
+@pytest.mark.skipif(os.environ.get("PLB_TEST_UNVALIDATED") != "1", reason="vector env not yet run on a GPU: set PLB_TEST_UNVALIDATED=1")
+def test_vec_env_matches_sequential_envs():
+    """K envs stepped as 'enqueue all, read all' (envs/vec_env.py) give what K separately stepped envs give (float64: 1e-9)."""
+    from plasticinelab_b200.envs import make
+    from plasticinelab_b200.envs.vec_env import VecPlasticineEnv
+    K, T = 3, 4
+    rng = np.random.RandomState(0)
+    vec = VecPlasticineEnv('Move-v1', K, dtype='float64')
+    acts = rng.uniform(-1, 1, (T, K, vec.action_space.shape[0]))
+    obs0 = vec.reset()
+    out = [vec.step(acts[t]) for t in range(T)]
+    single = make('Move-v1', dtype='float64')
+    for k in range(K):
+        o = single.reset()
+        assert np.abs(o - obs0[k]).max() < 1e-12
+        for t in range(T):
+            o, r, d, info = single.step(acts[t, k])
+            assert np.abs(o - out[t][0][k]).max() < 1e-9 and abs(r - out[t][1][k]) < 1e-9 * max(1.0, abs(r))
+    vec.close()

@@ -17,4 +17,7 @@ stamp "-> exit $? $(tail -1 $OUT/pytest_policy.log)"
 
 stamp "in-process bench A/B"
 timeout ${AB_TIMEOUT:-420} python tools/ab_bench.py $OUT ${AB_BUDGET:-330} 2>&1 | tee -a $OUT/timeline.txt
+stamp "RL vector env throughput (BASELINE configs[0])"
+timeout 200 python tools/bench_rl.py --envs 1,4,16 > $OUT/bench_rl.jsonl 2> $OUT/bench_rl.err
+stamp "-> exit $? $(tail -1 $OUT/bench_rl.jsonl | cut -c1-200)"
 stamp done
