@@ -100,3 +100,48 @@ def test_policy_backward_matches_autograd_and_routes_observation_adjoints():
 def test_init_mlp_params_layout():
     p = init_mlp_params(20, 4, hidden=(8, 8), seed=0)
     assert p.shape == (20 * 8 + 8 + 8 * 8 + 8 + 8 * 4 + 4,) and np.isfinite(p).all() and np.abs(p).max() < 1.0
+
+
+def test_vec_env_two_phase_stepping_and_time_limit(monkeypatch):
+    """envs/vec_env.py host logic with stand-in envs: every env's begin_step runs before the first finish_step (so the
+    envs' work overlaps on the GPU), rewards/observations come back per env, episodes are cut and reset at the step limit."""
+    from plasticinelab_b200.envs import vec_env
+    log = []
+
+    class FakeBox:
+        shape = (2,)
+
+    class FakeEnv:
+        count = 0
+
+        def __init__(self, **kw):
+            self.i = FakeEnv.count
+            FakeEnv.count += 1
+            self.t = 0
+            self.observation_space = self.action_space = FakeBox()
+            self.taichi_env = type("T", (), {"loss": type("L", (), {"set_weights": staticmethod(lambda **k: None)})()})()
+
+        def reset(self):
+            self.t = 0
+            log.append(("reset", self.i))
+            return np.array([self.i, 0.0])
+
+        def begin_step(self, a):
+            log.append(("begin", self.i))
+
+        def finish_step(self, a):
+            self.t += 1
+            log.append(("finish", self.i))
+            return np.array([self.i, float(self.t)]), float(a[0]) + self.i, False, {"loss": 0.0}
+
+    monkeypatch.setattr(vec_env, "PlasticineEnv", FakeEnv)
+    vec = vec_env.VecPlasticineEnv("Move-v1", 3, max_episode_steps=2)
+    obs = vec.reset()
+    assert obs.shape == (3, 2)
+    log.clear()
+    obs, rew, done, infos = vec.step(np.array([[0.1, 0], [0.2, 0], [0.3, 0]]))
+    assert [e[0] for e in log] == ["begin"] * 3 + ["finish"] * 3
+    assert np.allclose(rew, [0.1, 1.2, 2.3]) and not done.any() and np.array_equal(obs[:, 1], [1, 1, 1])
+    obs, rew, done, infos = vec.step(np.zeros((3, 2)))
+    assert done.all() and np.array_equal(obs[:, 1], [0, 0, 0])                  # auto-reset: first observation of the new episode
+    assert all(np.array_equal(i["terminal_observation"], [k, 2.0]) for k, i in enumerate(infos))
