@@ -186,6 +186,8 @@ struct Engine : plb_engine {
     int fwd_minb = 5, bwd_minb = 3; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 / PLB_BWD_MINB=4 select the tighter cap)
     int flush_mode = 0;             // full-tile flush: 0 = per-cell groups, 1 = runs of consecutive lanes (PLB_FLUSH_RUNS=1), 2 = two cells per round (PLB_FLUSH_PAIRS=1)
     bool grid_bwd_v2 = true;        // grid adjoint with register-resident pose gradients (k_grid_bwd_sparse_v2); PLB_GRID_BWD_V2=0: array form
+    bool env_list = false;          // active-block list built once per env step (dilated by one block) instead of per substep (PLB_ENV_LIST=1)
+    unsigned char* d_flags2 = nullptr; unsigned char* d_listed = nullptr;
     bool grid_scan = false;         // forward grid stage as one kernel (flag scan + store + grid operator), PLB_GRID_SCAN=1
     bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
                                     // particle kernel and grid adjoint of substep s (needs the second grid set; PLB_BWD_OVERLAP=0 disables)
@@ -226,6 +228,7 @@ struct Engine : plb_engine {
         cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_cub); cudaFree(frame_tmp);
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt); cudaFree(store.overflow); cudaFree(d_cursor);
+        cudaFree(d_flags2); cudaFree(d_listed);
         cudaFree(d_inv_perm); cudaFree(d_sel_idx); cudaFree(d_sel_val); cudaFree(svd_store);
         cudaFree(sets[1].in); cudaFree(sets[1].out); cudaFree(sets[1].list); cudaFree(sets[1].count);
         for (cudaEvent_t e : cap_events) cudaEventDestroy(e);
@@ -298,6 +301,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_BWD_OVERLAP")) bwd_overlap = atoi(v) != 0;
         if (const char* v = getenv("PLB_GRID_SCAN")) grid_scan = atoi(v) != 0;
         if (const char* v = getenv("PLB_SVD_STORE")) svd_enable = atoi(v) != 0;
+        if (const char* v = getenv("PLB_ENV_LIST")) env_list = atoi(v) != 0;
         if (const char* v = getenv("PLB_FLUSH_RUNS")) flush_mode = atoi(v) != 0 ? 1 : 0;
         if (const char* v = getenv("PLB_FLUSH_PAIRS")) flush_mode = atoi(v) != 0 ? 2 : flush_mode;
         if (const char* v = getenv("PLB_GRID_BWD_V2")) grid_bwd_v2 = atoi(v) != 0;
@@ -327,6 +331,10 @@ struct Engine : plb_engine {
         n_blocks = (c.n_grid / 4) * (c.n_grid / 4) * (c.n_grid / 4);
         PLB_CUDA(cudaMalloc(&d_flags, n_blocks));
         PLB_CUDA(cudaMemset(d_flags, 0, n_blocks));
+        PLB_CUDA(cudaMalloc(&d_flags2, n_blocks));
+        PLB_CUDA(cudaMemset(d_flags2, 0, n_blocks));
+        PLB_CUDA(cudaMalloc(&d_listed, n_blocks));
+        PLB_CUDA(cudaMemset(d_listed, 0, n_blocks));
         PLB_CUDA(cudaMalloc(&d_list, n_blocks * sizeof(int)));
         PLB_CUDA(cudaMalloc(&d_nactive, sizeof(int)));
         PLB_CUDA(cudaMemset(d_nactive, 0, sizeof(int)));
@@ -480,11 +488,18 @@ struct Engine : plb_engine {
         // size the forward-grid store from the active-block count of this frame (2x margin + 256 blocks)
         if (sparse && cfg.kernel_variant == 0) {
             k_mark_only<T><<<blocks(n), kBlock, 0, stream>>>(P, frame_base(slot), n_pad, d_flags);
-            compact_blocks();
+            if (env_list) {          // env-step lists are dilated by one block: size the store for the dilated count
+                cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
+                k_dilate_flags<<<(n_blocks + 255) / 256, 256, 0, stream>>>(cfg.n_grid / 4, d_flags, d_flags2);
+                k_compact_mark<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags2, d_list, d_nactive, d_listed);
+                launches += 2;
+            } else {
+                compact_blocks();
+            }
             int cnt = 0;
             PLB_CUDA(cudaMemcpyAsync(&cnt, d_nactive, sizeof(int), cudaMemcpyDeviceToHost, stream));
             PLB_CUDA(cudaStreamSynchronize(stream));
-            int want = std::min(n_blocks, 2 * cnt + 256);
+            int want = std::min(n_blocks, (env_list ? cnt + cnt / 2 : 2 * cnt) + 256);
             if (want > store.cap) {
                 cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt);
                 store.vals = nullptr; store.ids = nullptr; store.cnt = nullptr; store.cap = 0;
@@ -575,7 +590,7 @@ struct Engine : plb_engine {
     int scan_ctas() const { return std::min(std::max((n_blocks + kBlock - 1) / kBlock, 1), 148 * 8); }
     // forward grid stage as one kernel (k_grid_fwd_scan): single GPU, forward-grid store present, per-CTA list capacity suffices
     bool scan_mode() const {
-        return grid_scan && sparse && tile_scatter && store.vals && !slab.on && (long long)scan_ctas() * kScanCap >= n_blocks;
+        return grid_scan && !env_list && sparse && tile_scatter && store.vals && !slab.on && (long long)scan_ctas() * kScanCap >= n_blocks;
     }
     void compact_blocks() {
         cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
@@ -585,10 +600,29 @@ struct Engine : plb_engine {
     // Enqueue one forward substep.  Slots/poses are given as SlotRef so the same code serves direct launches
     // (absolute indices) and graph capture (cursor-relative indices).
     // grid stage of a forward substep: (halo) + active-block list + grid operator (+ store of the forward grid for slot `si`)
-    void enqueue_grid_fwd_stage(SlotRef si, SlotRef pf) {
+    // forward graphs in env-list mode: single GPU, forward-grid store present
+    bool env_list_mode() const { return env_list && sparse && tile_scatter && store.vals && !slab.on; }
+    // list of the env step that starts at frame `slot`: blocks touched by that frame, dilated by one block
+    void enqueue_env_list(SlotRef slot) {
+        const int nbx = cfg.n_grid / 4, nb = (n_blocks + 255) / 256;
+        cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
+        k_mark_slot<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, d_flags);
+        k_dilate_flags<<<nb, 256, 0, stream>>>(nbx, d_flags, d_flags2);
+        k_compact_mark<<<nb, 256, 0, stream>>>(n_blocks, d_flags2, d_list, d_nactive, d_listed);
+        launches += 3;
+    }
+    // the frame the env step produced must still lie inside its list (else *store.overflow = 2 -> check_overflow reports it)
+    void enqueue_env_list_check(SlotRef slot) {
+        k_mark_slot<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, d_flags);
+        k_check_listed<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags, d_listed, store.overflow);
+        launches += 2;
+    }
+    void enqueue_grid_fwd_stage(SlotRef si, SlotRef pf, bool fixed_list = false) {
         prof_begin(K_GRID_FWD);
         if (sparse) {
-            if (slab.peer_ready) {
+            if (fixed_list) {
+                // (the list in d_list / d_nactive was built by enqueue_env_list for the whole env step)
+            } else if (slab.peer_ready) {
                 k_halo_next_seq<<<1, 1, 0, stream>>>(slab.seq);
                 cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
                 k_compact_stamped<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags, d_list, d_nactive, slab.listed_stamp, slab.seq);
@@ -627,13 +661,14 @@ struct Engine : plb_engine {
         launches += 2;
     }
     // n >= 2 forward substeps with G2P(i-1) and P2G(i) fused into one particle kernel (refs are cursor-relative or absolute)
-    void enqueue_fwd_fused(int n, SlotRef (*mk)(const Engine*, int, int)) {
+    void enqueue_fwd_fused(int n, SlotRef (*mk)(const Engine*, int, int), bool fixed_list = false) {
         const int nb = blocks(cfg.n_particles);
-        unsigned char* fl = sparse ? d_flags : nullptr;
+        unsigned char* fl = (sparse && !fixed_list) ? d_flags : nullptr;
+        if (fixed_list) enqueue_env_list(mk(this, 0, 0));
         prof_begin(K_P2G);
-        launch_p2g(mk(this, 0, 0), mk(this, 1, 0), 1);
+        launch_p2g(mk(this, 0, 0), mk(this, 1, 0), 1, !fixed_list);
         prof_end();
-        enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0));
+        enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0), fixed_list);
         const int nbc = blocks(cfg.n_particles, cta);
         const size_t sm = tile_smem_bytes(fwd_plane, cta);
         for (int i = 1; i < n; i++) {
@@ -642,13 +677,14 @@ struct Engine : plb_engine {
                                   : (fwd_minb >= 6 ? k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>);
             kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), grid_out, grid_in, fl, flush_mode, svd_store);
             prof_end();
-            enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i));
+            enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i), fixed_list);
             launches++;
         }
         prof_begin(K_G2P);
         k_g2p<T><<<nb, kBlock, 0, stream>>>(P, frames, n_pad, mk(this, 0, n - 1), mk(this, 1, n - 1), grid_out);
         prof_end();
         launches += 2;
+        if (fixed_list) enqueue_env_list_check(mk(this, 1, n - 1));
     }
     // backward stages of one substep, on grid set `gs`, enqueued on stream `st`
     void enqueue_bwd_grid_pre(SlotRef si, SlotRef pf, bool restore, const GridSet& gs, cudaStream_t st) {   // forward grid of the substep + grid_out
@@ -791,8 +827,8 @@ struct Engine : plb_engine {
     }
     int own_lo() const { return slab.on ? slab.own_lo : 0; }
     int own_hi() const { return slab.on ? slab.own_hi : cfg.n_grid; }
-    void launch_p2g(SlotRef si, SlotRef so, int store_F) {
-        unsigned char* fl = sparse ? d_flags : nullptr;
+    void launch_p2g(SlotRef si, SlotRef so, int store_F, bool mark = true) {
+        unsigned char* fl = (sparse && mark) ? d_flags : nullptr;
         if (tile_scatter) {
             const int nbc = blocks(cfg.n_particles, cta);
             const size_t sm = tile_smem_bytes(fwd_plane, cta);
@@ -840,7 +876,7 @@ struct Engine : plb_engine {
             const bool fused = fuse && tile_scatter && sparse && key.n >= 2;
             const bool restore = (key.stored & 1) != 0, next_ok = (key.stored & 2) != 0, svd = (key.stored & 4) != 0;
             if (key.dir == 0) {
-                if (fused) enqueue_fwd_fused(key.n, &Engine::mk_cursor);
+                if (fused) enqueue_fwd_fused(key.n, &Engine::mk_cursor, env_list_mode());
                 else for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
             } else {
                 int c = key.parity;
@@ -872,7 +908,7 @@ struct Engine : plb_engine {
             for (int i = 0; i < n; i++) if (int r = substep_fwd(slot0 + i, slot0 + i + 1, pf0 + i)) return r;
             return PLB_OK;
         }
-        GraphKey key{0, n, 0, (store.vals != nullptr ? 1 : 0) | (scan_mode() ? 2 : 0)};
+        GraphKey key{0, n, 0, (store.vals != nullptr ? 1 : 0) | (scan_mode() ? 2 : 0) | (env_list_mode() ? 4 : 0)};
         if (int r = launch_graph(key, slot0, pf0)) return r;
         for (int i = 0; i < n; i++) { stored[slot0 + i] = store.vals != nullptr; fwd_ok[slot0 + i] = 1; svd_ok[slot0 + i] = svd_store != nullptr; }
         stored[slot0 + n] = 0; fwd_ok[slot0 + n] = 0; svd_ok[slot0 + n] = 0;
@@ -1142,6 +1178,12 @@ struct Engine : plb_engine {
             int he = 0;
             PLB_CUDA(cudaMemcpy(&he, slab.err, sizeof(int), cudaMemcpyDeviceToHost));
             if (he) { cudaMemset(slab.err, 0, sizeof(int)); err = "slab halo: timed out waiting for a neighbour's push"; return PLB_ERR_CUDA; }
+        }
+        if (ov == 2) {
+            PLB_CUDA(cudaMemsetAsync(store.overflow, 0, sizeof(int), stream));
+            err = "PLB_ENV_LIST: the material left the block list of its env step (it moved more than one 4^3 block within the step); "
+                  "results of this episode are invalid -- run without PLB_ENV_LIST";
+            return PLB_ERR_NOMEM;
         }
         if (ov) {
             PLB_CUDA(cudaMemsetAsync(store.overflow, 0, sizeof(int), stream));

@@ -83,6 +83,47 @@ __global__ void k_compact(int n_blocks, unsigned char* flags, int* list, int* co
     }
 }
 
+// ---- env-step block list (PLB_ENV_LIST=1): the active-block list is built ONCE per env step from the frame the step starts
+// at, dilated by one block in every direction (a particle moves far less than 4 nodes in one env step), and every substep
+// of the step walks that fixed list: no per-substep flag marking, memset or compaction.  k_check_listed verifies at the
+// end of the step that the frame it produced still lies inside the list.
+template <class T>
+__global__ void k_mark_slot(SimConst<T> P, T* frames, long long n_pad, SlotRef slot, unsigned char* flags) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P.n_particles) mark_blocks<T>(P, load_x(frame_at(frames, slot.get(), n_pad), p), flags);
+}
+// out[b'] = 1 for the 27 neighbours b' of every flagged block b; clears in[b]
+__global__ void k_dilate_flags(int nbx, unsigned char* in, unsigned char* out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbx * nbx * nbx || !in[b]) return;
+    in[b] = 0;
+    const int bk = b % nbx, bj = (b / nbx) % nbx, bi = b / (nbx * nbx);
+    for (int di = -1; di <= 1; di++)
+        for (int dj = -1; dj <= 1; dj++)
+            for (int dk = -1; dk <= 1; dk++) {
+                const int i = bi + di, j = bj + dj, k = bk + dk;
+                if (i >= 0 && j >= 0 && k >= 0 && i < nbx && j < nbx && k < nbx) out[(i * nbx + j) * nbx + k] = 1;
+            }
+}
+// compaction that also records membership (listed[b] = 1 / 0 for every block) and clears the flags
+__global__ void k_compact_mark(int n_blocks, unsigned char* flags, int* list, int* count, unsigned char* listed) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const bool on = flags[b] != 0;
+    listed[b] = on ? 1 : 0;
+    if (on) {
+        flags[b] = 0;
+        list[atomicAdd(count, 1)] = b;
+    }
+}
+// every flagged block must be listed; clears the flags; *err = 2 otherwise
+__global__ void k_check_listed(int n_blocks, unsigned char* flags, const unsigned char* __restrict__ listed, int* err) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks || !flags[b]) return;
+    flags[b] = 0;
+    if (!listed[b]) *err = 2;
+}
+
 // node handled by thread `local` (0..63) of listed block `blk`
 __device__ __forceinline__ long long block_node(int n_grid, int blk, int local) {
     const int nbx = n_grid >> kBlkShift;

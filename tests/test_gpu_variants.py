@@ -17,7 +17,7 @@ from test_gpu_parity import _episode_cfg, _target32
 
 pytestmark = pytest.mark.gpu
 
-KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS"]
+KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST"]
 VARIANTS = {
     "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3,
                          PLB_GRID_BWD_V2=0, PLB_FLUSH_RUNS=0),
@@ -41,6 +41,8 @@ UNVALIDATED = {
     "svd_store": dict(PLB_SVD_STORE=1),
     "svd_store_tight": dict(PLB_SVD_STORE=1, PLB_BWD_MINB=4),
     "flush_pairs": dict(PLB_FLUSH_PAIRS=1),
+    "env_list": dict(PLB_ENV_LIST=1),
+    "env_list_svd_tight_pairs": dict(PLB_ENV_LIST=1, PLB_SVD_STORE=1, PLB_BWD_MINB=4, PLB_FLUSH_PAIRS=1),
 }
 if os.environ.get("PLB_TEST_UNVALIDATED") == "1":
     VARIANTS.update(UNVALIDATED)

@@ -13,17 +13,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-KEYS = ["PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_GRID_BWD_V2", "PLB_FLUSH_RUNS", "PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA"]
+KEYS = ["PLB_ENV_LIST", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_GRID_BWD_V2", "PLB_FLUSH_RUNS", "PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA"]
 VARIANTS = [     # the queue for the next GPU session: switches built and CPU-emulated after the round-1 GPU budget was spent
     ("def100k", "move100k", dict()),
     ("svd100k", "move100k", dict(PLB_SVD_STORE=1)),
     ("svd4_100k", "move100k", dict(PLB_SVD_STORE=1, PLB_BWD_MINB=4)),
     ("pairs100k", "move100k", dict(PLB_FLUSH_PAIRS=1)),
     ("svd4pairs", "move100k", dict(PLB_SVD_STORE=1, PLB_BWD_MINB=4, PLB_FLUSH_PAIRS=1)),
+    ("envlist100k", "move100k", dict(PLB_ENV_LIST=1)),
+    ("all100k", "move100k", dict(PLB_ENV_LIST=1, PLB_SVD_STORE=1, PLB_BWD_MINB=4, PLB_FLUSH_PAIRS=1)),
     ("def1m", "move1m", dict()),
     ("svd1m", "move1m", dict(PLB_SVD_STORE=1)),
     ("svd4_1m", "move1m", dict(PLB_SVD_STORE=1, PLB_BWD_MINB=4)),
     ("pairs1m", "move1m", dict(PLB_FLUSH_PAIRS=1)),
+    ("all1m", "move1m", dict(PLB_ENV_LIST=1, PLB_SVD_STORE=1, PLB_BWD_MINB=4)),
 ]
 
 
