@@ -1,0 +1,75 @@
+"""Full-size GPU checks (BASELINE.json configs 2-3 and the north-star roofline size), through size-independent properties:
+mass conservation of the scatter, finite non-zero action gradients, agreement of the kernel variants with the conservative
+configuration on a short episode.  OPT-IN (PLB_TEST_LARGE=1): each case allocates 5-40 GB of HBM and takes seconds to a minute.
+Tolerances (float32 engine): total mass 2e-5 relative, episode loss between variants 1e-5 relative, action gradient 5e-2
+(float32 summation-order noise through ~80-160 substeps).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import plb_test_helpers as H
+from plasticinelab_b200 import _capi
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PLB_TEST_LARGE") != "1", reason="full-size cases: set PLB_TEST_LARGE=1")]
+D = _capi.dptr
+KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE",
+        "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST"]
+CONSERVATIVE = dict(PLB_BWD_OVERLAP=0, PLB_GRID_BWD_V2=0)
+CASES = {      # name -> (scene file, particles, quality, env steps)
+    "move1m_128": ("move.yml", 1_000_000, 2, 2),          # north-star roofline size
+    "rope1m_256": ("rope.yml", 1_000_000, 4, 1),          # BASELINE config 3 (about 28 particles per cell)
+}
+
+
+def _episode(monkeypatch, case, env_vars):
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.envs.scene import load_variants
+    from plasticinelab_b200.optimizer.solver import Solver
+    scene, n, quality, horizon = CASES[case]
+    for k in KEYS:
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env_vars.items():
+        monkeypatch.setenv(k, str(v))
+    cfg = load_variants(scene, 1)
+    cfg.SIMULATOR.quality = quality
+    cfg.SHAPES[0]["n_particles"] = n
+    S = _capi.sim_constants(dict(cfg.SIMULATOR))["substeps"]
+    cfg.SIMULATOR.max_steps = horizon * S + 2
+    env = TaichiEnv(cfg, dtype="float32", max_prim_frames=horizon * S + 2)
+    env.initialize()
+    env.loss.set_weights(10, 10, 1, False)
+    A = env.primitives.action_dim
+    actions = np.random.RandomState(0).uniform(-0.5, 0.5, (horizon, A))
+    solver = Solver(env, None, None, n_iters=1, softness=666.0, horizon=horizon)
+    solver.total_steps = 0
+    loss, grad = solver.forward(env.get_state()["state"], actions)
+    info = dict(n=env.n_particles, p_mass=env.simulator.p_mass)
+    # total grid mass of the last frame through the density term against a zero target
+    ng = env.simulator.n_grid
+    zeros = np.zeros((ng, ng, ng))
+    env.engine.call("plb_set_target", D(zeros), D(zeros))               # (as in test_full_size_properties_config2)
+    env.engine.call("plb_set_loss_weights", C.c_double(0.0), C.c_double(1.0), C.c_double(0.0), 0, 1)
+    out = np.zeros(8)
+    env.engine.call("plb_loss_fwd", int(env.simulator.cur), int(env.simulator.cur), D(out))
+    info["mass"] = out[2]
+    env.engine.close()
+    return loss, grad, info
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_full_size_episode_properties_and_variant_agreement(monkeypatch, case):
+    ref_loss, ref_grad, info = _episode(monkeypatch, case, CONSERVATIVE)
+    assert np.isfinite(ref_loss) and np.isfinite(ref_grad).all() and np.abs(ref_grad).max() > 0
+    assert abs(info["mass"] - info["n"] * info["p_mass"]) < 2e-5 * info["n"] * info["p_mass"]       # the scatter conserves mass
+    variants = {"defaults": {}}
+    if os.environ.get("PLB_TEST_UNVALIDATED") == "1":
+        variants.update({"svd_tight": dict(PLB_SVD_STORE=1, PLB_BWD_MINB=4), "env_list": dict(PLB_ENV_LIST=1),
+                         "pairs": dict(PLB_FLUSH_PAIRS=1)})
+    for name, env_vars in variants.items():
+        loss, grad, _ = _episode(monkeypatch, case, env_vars)
+        assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (name, loss, ref_loss)
+        assert H.relerr(grad, ref_grad) < 5e-2, (name, H.relerr(grad, ref_grad))
