@@ -20,4 +20,7 @@ timeout ${AB_TIMEOUT:-420} python tools/ab_bench.py $OUT ${AB_BUDGET:-330} 2>&1 
 stamp "RL vector env throughput (BASELINE configs[0])"
 timeout 200 python tools/bench_rl.py --envs 1,4,16 > $OUT/bench_rl.jsonl 2> $OUT/bench_rl.err
 stamp "-> exit $? $(tail -1 $OUT/bench_rl.jsonl | cut -c1-200)"
+stamp "full-size property tests (1M particles)"
+PLB_TEST_LARGE=1 PLB_TEST_UNVALIDATED=1 timeout 400 python -m pytest tests/test_gpu_large.py -m gpu -q -p no:cacheprovider > $OUT/pytest_large.log 2>&1
+stamp "-> exit $? $(tail -1 $OUT/pytest_large.log)"
 stamp done
