@@ -183,10 +183,10 @@ struct Engine : plb_engine {
     bool fwd_plane = false;         // plane (9-node) tile in the forward scatter kernels: 1/3 shared memory (PLB_FWD_PLANE)
     bool bwd_plane = false;         // same for the backward scatter kernels (PLB_BWD_PLANE)
     int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
-    int fwd_minb = 5, bwd_minb = 3; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 / PLB_BWD_MINB=4 select the tighter cap)
+    int fwd_minb = 5, bwd_minb = 4; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 selects the tighter forward cap, PLB_BWD_MINB=3 the looser backward one)
     int flush_mode = 0;             // full-tile flush: 0 = per-cell groups, 1 = runs of consecutive lanes (PLB_FLUSH_RUNS=1), 2 = two cells per round (PLB_FLUSH_PAIRS=1)
     bool grid_bwd_v2 = true;        // grid adjoint with register-resident pose gradients (k_grid_bwd_sparse_v2); PLB_GRID_BWD_V2=0: array form
-    bool env_list = false;          // active-block list built once per env step (dilated by one block) instead of per substep (PLB_ENV_LIST=1)
+    bool env_list = true;           // active-block list built once per env step (dilated by one block) instead of per substep (PLB_ENV_LIST=0: per substep)
     unsigned char* d_flags2 = nullptr; unsigned char* d_listed = nullptr;
     bool grid_scan = false;         // forward grid stage as one kernel (flag scan + store + grid operator), PLB_GRID_SCAN=1
     bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
@@ -204,7 +204,7 @@ struct Engine : plb_engine {
     std::vector<char> fwd_ok;       // host view: slot s+1 holds the frame the forward substep produced from slot s
     // SVD store (PLB_SVD_STORE=1): U, sigma, V of F_tmp per particle and frame slot, written by the forward P2G, read by the
     // backward pass instead of re-running the Jacobi iteration; 84 B (f32) per particle and frame
-    T* svd_store = nullptr; bool svd_enable = false;
+    T* svd_store = nullptr; bool svd_enable = true;
     std::vector<char> svd_ok;       // host view: svd_store[slot] holds the decomposition of the substep that started at slot
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
     int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
@@ -398,7 +398,7 @@ struct Engine : plb_engine {
         T** dst[3] = {&mat_mu, &mat_lam, &mat_ys};
         for (int i = 0; i < 3; i++) {
             if (!src[i]) continue;
-            if (!*dst[i]) PLB_CUDA(cudaMalloc(dst[i], n_pad * sizeof(T)));
+            if (!*dst[i]) { PLB_CUDA(cudaMalloc(dst[i], n_pad * sizeof(T))); drop_graphs(); }     // (graphs hold the pointer by value)
             PLB_CUDA(cudaMemcpyAsync(d_stage, src[i], cfg.n_particles * sizeof(double), cudaMemcpyHostToDevice, stream));
             k_convert_perm<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(cfg.n_particles, d_stage, *dst[i], d_perm);
             launches++;
@@ -467,9 +467,9 @@ struct Engine : plb_engine {
             PLB_CUDA(cudaMalloc(&d_cub, cub_bytes));
         }
         k_sort_keys<T><<<blocks(n), kBlock, 0, stream>>>(P, frame_base(slot), n_pad, d_keys, d_vals);
-        int bits = 6;
-        for (int nb = n_blocks; nb > 1; nb >>= 1) bits++;
-        PLB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, bits > 32 ? 32 : bits, stream));
+        int bits = 1;
+        while (bits < 32 && (1ull << bits) < (unsigned long long)n_blocks * 64ull) bits++;      // ceil(log2(largest key + 1))
+        PLB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, bits, stream));
         k_permute_frame<T><<<blocks(n), kBlock, 0, stream>>>(n, n_pad, frame_base(slot), frame_tmp, d_vals2, d_perm, d_perm2);
         PLB_CUDA(cudaMemcpyAsync(frame_base(slot), frame_tmp, (size_t)24 * n_pad * sizeof(T), cudaMemcpyDeviceToDevice, stream));
         T* mats[3] = {mat_mu, mat_lam, mat_ys};
@@ -553,8 +553,17 @@ struct Engine : plb_engine {
         std::memcpy(pose(dst, 0), pose(src, 0), PLB_MAX_PRIM * 8 * sizeof(double));
         return upload_poses(dst, 1);
     }
+    void drop_graphs() {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+    }
+    // kernel arguments (PrimSet with the softness, the material pointers) are baked into captured graphs by value:
+    // a change must drop the cache, or a replayed forward graph would run with the old value beside a freshly captured
+    // backward graph with the new one
     int set_softness(double s) override {
-        for (int k = 0; k < cfg.n_primitives; k++) prims.s[k].softness = (T)s;
+        bool changed = false;
+        for (int k = 0; k < cfg.n_primitives; k++) { changed = changed || prims.s[k].softness != (T)s; prims.s[k].softness = (T)s; }
+        if (changed) drop_graphs();
         return PLB_OK;
     }
     int set_action(int step, int S, const double* a, int n) override {

@@ -54,3 +54,15 @@ def c_setup(cfg, n, dtype='float64', **kw):
 def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def record(name, **vals):
+    """Append measured parity errors to $PLB_PARITY_LOG (one JSON line per call): the tolerances in the GPU tests are set
+    to about 3x what this log showed on a B200 (profiles/r2_parity_measured.md)."""
+    import json
+    import os
+    path = os.environ.get("PLB_PARITY_LOG")
+    if path:
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(test=name, **{k: float(v) for k, v in vals.items()})) + "\n")

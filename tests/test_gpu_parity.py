@@ -69,6 +69,10 @@ def test_substep_parity(name, softness, gf, seed, dtype):
     ref = osim.substep(st, pf, pf1)
     o_adj, o_g0, o_g1 = osim.substep_vjp(st, pf, pf1, tuple(torch.as_tensor(a) for a in adj))
     ftol, atol = (1e-9, 1e-7) if dtype == 'float64' else (2e-4, 3e-3)
+    H.record(f"substep[{name},{seed},{dtype}]", fwd=max(H.relerr(a, b.numpy()) for a, b in zip(out, ref)),
+             adj=max(H.relerr(a, b.numpy()) for a, b in zip(gadj, o_adj)),
+             pose=max([np.abs(gp[w, k, :p.state_dim] - g[k].numpy()).max() / max(np.abs(o_g0[k].numpy()).max(), np.abs(o_g1[k].numpy()).max(), 1e-12)
+                       for k, p in enumerate(osim.prims) for w, g in ((0, o_g0), (1, o_g1))] + [0.0]))
     for a, b in zip(out, ref):
         assert H.relerr(a, b.numpy()) < ftol
     for a, b in zip(gadj, o_adj):
@@ -122,10 +126,12 @@ def test_episode_loss_and_action_gradient(dtype, contact_all):
                        contact_grad='taichi' if contact_all else 'argmin')
     out = oenv.rollout(actions, softness=666.0)
     ltol, gtol = (1e-9, 1e-6) if dtype == 'float64' else (1e-4, 5e-2)
+    sim_state = env.simulator.get_state(env.simulator.cur)
+    H.record(f"episode[{dtype},{contact_all}]", loss=abs(loss - out['loss']) / abs(out['loss']), grad=H.relerr(grad, out['grad']),
+             x=np.abs(sim_state[0] - out['final_state'][0].numpy()).max())
     assert abs(loss - out['loss']) < ltol * abs(out['loss'])
     assert H.relerr(grad, out['grad']) < gtol
     # final particle state
-    sim_state = env.simulator.get_state(env.simulator.cur)
     xtol = 1e-10 if dtype == 'float64' else 1e-5
     assert np.abs(sim_state[0] - out['final_state'][0].numpy()).max() < xtol
 
@@ -437,3 +443,47 @@ def test_per_particle_materials_episode_f64():
     assert abs(loss - out['loss']) < 1e-9 * abs(out['loss'])
     assert H.relerr(grad, out['grad']) < 1e-6
     assert np.abs(env.simulator.get_state(env.simulator.cur)[2] - out['final_state'][3].numpy()).max() < 1e-10     # F
+
+
+def test_softness_and_material_change_after_graph_capture():
+    """Env-step graphs bake the softness (PrimSet) and the material pointers in by value: changing either after the first
+    capture must not replay stale graphs (RL stepping at softness 0, then Solver.forward at 666 on the same engine)."""
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.optimizer.solver import Solver
+    cfg = _episode_cfg(400)
+    actions = np.random.RandomState(5).uniform(-1, 1, (2, 6))
+
+    def solve(env):
+        solver = Solver(env, None, None, n_iters=1, softness=666., horizon=2)
+        solver.total_steps = 0
+        return solver.forward(env.get_state()['state'], actions)
+
+    def make():
+        env = TaichiEnv(cfg, dtype='float64')
+        env.initialize()
+        env.loss.load_target_density(grids=_target32(env))
+        env.loss.set_weights(10, 10, 1, False)
+        return env
+
+    fresh = make()
+    l0, g0 = solve(fresh)
+    used = make()
+    state0 = used.get_state()
+    used.set_copy(True)
+    for a in actions:                       # captures forward graphs at softness 0
+        used.step(a)
+    used.set_state(**state0)
+    l1, g1 = solve(used)                    # softness 666: must re-capture
+    assert abs(l1 - l0) < 1e-12 * abs(l0) and H.relerr(g1, g0) < 1e-9
+    # per-particle materials installed after graphs exist
+    n = used.n_particles
+    mu = np.where(used.init_particles[:, 0] < 0.5, 2083.33, 8000.0)
+    for env in (fresh, used):
+        env.set_state(**state0)
+        env.simulator.set_materials(mu=mu, lam=np.full(n, 1388.89), yield_stress=np.full(n, 200.0))
+    fresh2 = make()
+    fresh2.simulator.set_materials(mu=mu, lam=np.full(n, 1388.89), yield_stress=np.full(n, 200.0))
+    l2, g2 = solve(fresh2)
+    l3, g3 = solve(used)
+    assert abs(l3 - l2) < 1e-12 * abs(l2) and H.relerr(g3, g2) < 1e-9
+    assert abs(l2 - l0) > 1e-9 * abs(l0)    # (the materials did change the episode)

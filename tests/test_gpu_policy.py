@@ -2,9 +2,9 @@
 (plb_gather_particles / plb_scatter_adjoint / plb_action_grad_step / plb_add_pose_adjoint behind engine/nn/mlp.py) against the
 float64 oracle's restatement (OracleEnv.rollout_policy, itself checked against finite differences on the CPU).
 
-OPT-IN (PLB_TEST_POLICY=1) until its first run on a B200: the engine side of this path was written after the round's GPU
-budget was spent; everything that can be checked without a GPU is (tests/test_policy_host.py, the stepwise kinematics scan in
-tests/test_host_emulation.py, the oracle in tests/test_oracle.py).  Tolerances: float64 1e-9 loss / 1e-6 gradient,
+First green run on a B200: round 2 (gpurun_out/ab/pytest_policy.log); part of the default GPU suite since.  What can be checked
+without a GPU is checked there too (tests/test_policy_host.py, the stepwise kinematics scan in tests/test_host_emulation.py,
+the oracle in tests/test_oracle.py).  Tolerances: float64 1e-9 loss / 1e-6 gradient,
 float32 1e-4 / 5e-2 (as for the action-gradient episodes in test_gpu_parity.py).
 """
 import os
@@ -16,8 +16,7 @@ import plb_test_helpers as H
 from test_gpu_parity import _episode_cfg, _target32
 from oracle import plb_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PLB_TEST_POLICY") != "1", reason="policy path not yet validated on a GPU: set PLB_TEST_POLICY=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('dtype', ['float64', 'float32'])

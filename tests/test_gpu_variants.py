@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST"]
 VARIANTS = {
     "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3,
-                         PLB_GRID_BWD_V2=0, PLB_FLUSH_RUNS=0),
+                         PLB_GRID_BWD_V2=0, PLB_FLUSH_RUNS=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0),
     "defaults": {},
     "overlap": dict(PLB_BWD_OVERLAP=1),
     "scan": dict(PLB_GRID_SCAN=1),
@@ -35,17 +35,14 @@ VARIANTS = {
 }
 
 
-# switches whose engine side has not run on a GPU yet (written after the round's GPU budget was spent; CPU-emulated only):
-# included with PLB_TEST_UNVALIDATED=1, to be moved into VARIANTS after their first green run on a B200
-UNVALIDATED = {
-    "svd_store": dict(PLB_SVD_STORE=1),
-    "svd_store_tight": dict(PLB_SVD_STORE=1, PLB_BWD_MINB=4),
+# (first green run on a B200: round 2, gpurun_out/ab/pytest_variants.log; SVD store + 128-register cap + env-step block list are the defaults since)
+VARIANTS.update({
+    "no_svd_store": dict(PLB_SVD_STORE=0),
+    "svd_store_loose": dict(PLB_SVD_STORE=1, PLB_BWD_MINB=3),
     "flush_pairs": dict(PLB_FLUSH_PAIRS=1),
-    "env_list": dict(PLB_ENV_LIST=1),
-    "env_list_svd_tight_pairs": dict(PLB_ENV_LIST=1, PLB_SVD_STORE=1, PLB_BWD_MINB=4, PLB_FLUSH_PAIRS=1),
-}
-if os.environ.get("PLB_TEST_UNVALIDATED") == "1":
-    VARIANTS.update(UNVALIDATED)
+    "substep_list": dict(PLB_ENV_LIST=0),
+    "substep_list_no_svd_pairs": dict(PLB_ENV_LIST=0, PLB_SVD_STORE=0, PLB_BWD_MINB=3, PLB_FLUSH_PAIRS=1),
+})
 
 
 def _run(monkeypatch, env_vars, dtype):
@@ -85,7 +82,6 @@ def test_kernel_variants_agree(monkeypatch, dtype):
     assert not bad, bad
 
 
-@pytest.mark.skipif(os.environ.get("PLB_TEST_UNVALIDATED") != "1", reason="vector env not yet run on a GPU: set PLB_TEST_UNVALIDATED=1")
 def test_vec_env_matches_sequential_envs():
     """K envs stepped as 'enqueue all, read all' (envs/vec_env.py) give what K separately stepped envs give (float64: 1e-9)."""
     from plasticinelab_b200.envs import make
