@@ -195,6 +195,10 @@ int  plb_device_buffer(plb_engine* e, int which, void** ptr, long long* bytes);
  * are CUDA graphs again.  handle64: 64 bytes (cudaIpcMemHandle_t). */
 int  plb_slab_ipc_export(plb_engine* e, int side, void* handle64);
 int  plb_slab_ipc_import(plb_engine* e, int side, const void* handle64);
+/* Unmaps the neighbours' inboxes (cudaIpcCloseMemHandle) and returns to the host-driven halo.  Every rank must call this --
+ * and the ranks must meet at a barrier -- before any rank destroys its engine: CUDA forbids freeing exported memory while an
+ * importer still maps it. */
+int  plb_slab_ipc_close(plb_engine* e);
 
 /* ---- introspection for tests / profiling ------------------------------------------------------------------ */
 /* copies the dense grids of the last substep: any of in4/out4 may be NULL; [n_grid^3][4] float64 */

@@ -35,9 +35,9 @@ static std::string g_create_error;
     } while (0)
 
 enum KernelId { K_P2G = 0, K_GRID_FWD, K_G2P, K_P2G_RECOMPUTE, K_GRID_FWD_RECOMPUTE, K_G2P_BWD, K_GRID_BWD, K_P2G_BWD,
-                K_LOSS_FWD, K_LOSS_BWD, K_MISC, K_COUNT };
+                K_LOSS_FWD, K_LOSS_BWD, K_MISC, K_G2P_P2G, K_P2G_BWD_G2P_BWD, K_COUNT };
 static const char* kKernelNames[K_COUNT] = {"p2g", "grid_fwd", "g2p", "p2g_recompute", "grid_fwd_recompute", "g2p_bwd", "grid_bwd",
-                                            "p2g_bwd", "loss_fwd", "loss_bwd", "misc"};
+                                            "p2g_bwd", "loss_fwd", "loss_bwd", "misc", "g2p_p2g", "p2g_bwd_g2p_bwd"};
 
 struct plb_engine {
     std::string err;
@@ -49,8 +49,10 @@ struct plb_engine {
     double prof_ms[K_COUNT] = {0};
     long long prof_cnt[K_COUNT] = {0};
     cudaStream_t prof_stream = 0;
-    void prof_begin(int kid) {
+    cudaStream_t prof_cur = 0;
+    void prof_begin(int kid, cudaStream_t st = nullptr) {
         if (!prof_on) return;
+        prof_cur = st ? st : prof_stream;
         if (prof_used * 2 + 2 > prof_ev.size()) {
             size_t old = prof_ev.size();
             prof_ev.resize(old + 8192);
@@ -58,15 +60,15 @@ struct plb_engine {
         }
         if (prof_kid.size() <= prof_used) prof_kid.resize(prof_used + 4096);
         prof_kid[prof_used] = kid;
-        cudaEventRecord(prof_ev[prof_used * 2], prof_stream);
+        cudaEventRecord(prof_ev[prof_used * 2], prof_cur);
     }
     void prof_end() {
         if (!prof_on) return;
-        cudaEventRecord(prof_ev[prof_used * 2 + 1], prof_stream);
+        cudaEventRecord(prof_ev[prof_used * 2 + 1], prof_cur);
         prof_used++;
     }
     void prof_collect() {
-        cudaStreamSynchronize(prof_stream);
+        if (prof_used) cudaDeviceSynchronize();          // (launches may sit on the engine's side stream too)
         for (size_t i = 0; i < prof_used; i++) {
             float ms = 0;
             cudaEventElapsedTime(&ms, prof_ev[i * 2], prof_ev[i * 2 + 1]);
@@ -123,6 +125,7 @@ struct plb_engine {
     virtual int device_buffer(int which, void** ptr, long long* bytes) = 0;
     virtual int slab_ipc_export(int side, void* handle64) = 0;
     virtual int slab_ipc_import(int side, const void* handle64) = 0;
+    virtual int slab_ipc_close() = 0;
     virtual int set_stream(void* s) = 0;
     virtual int synchronize() = 0;
     long long launches = 0;
@@ -177,7 +180,7 @@ struct Engine : plb_engine {
                   void* recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
                   // peer-memory halo: my inboxes (neighbours write here), the neighbours' inboxes mapped through CUDA IPC
                   char* inbox[2] = {nullptr, nullptr}; char* peer[2] = {nullptr, nullptr}; HaloGeom geom[2]; size_t inbox_bytes = 0;
-                  int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; bool peer_ready = false; } slab;
+                  int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; bool peer_ready = false; bool exported = false, ipc_closed = false; } slab;
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     bool fuse = true;               // fused G2P+P2G / P2G.grad+G2P.grad particle kernels inside env-step graphs (PLB_FUSE=0 disables)
     bool fwd_plane = false;         // plane (9-node) tile in the forward scatter kernels: 1/3 shared memory (PLB_FWD_PLANE)
@@ -231,6 +234,13 @@ struct Engine : plb_engine {
         cudaFree(d_flags2); cudaFree(d_listed);
         cudaFree(d_inv_perm); cudaFree(d_sel_idx); cudaFree(d_sel_val); cudaFree(svd_store);
         cudaFree(sets[1].in); cudaFree(sets[1].out); cudaFree(sets[1].list); cudaFree(sets[1].count);
+        for (int side = 0; side < 2; side++) {
+            // an exported inbox may only be freed once every importer has unmapped it: after plb_slab_ipc_close + a barrier
+            // (engine/sharded.py close()); otherwise it is left to process exit
+            if (!slab.peer[side] && (slab.ipc_closed || !slab.exported)) cudaFree(slab.inbox[side]);
+            for (int which = 0; which < 3; which++) cudaFree(slab.recv[which][side]);
+        }
+        cudaFree(slab.seq); cudaFree(slab.err); cudaFree(slab.listed_stamp);
         for (cudaEvent_t e : cap_events) cudaEventDestroy(e);
         if (side_stream) cudaStreamDestroy(side_stream);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -681,7 +691,7 @@ struct Engine : plb_engine {
         const int nbc = blocks(cfg.n_particles, cta);
         const size_t sm = tile_smem_bytes(fwd_plane, cta);
         for (int i = 1; i < n; i++) {
-            prof_begin(K_P2G);
+            prof_begin(K_G2P_P2G);
             auto kern = fwd_plane ? (fwd_minb >= 6 ? k_g2p_p2g_warp<T, true, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, true, OccSel<T>::fwd_lo>)
                                   : (fwd_minb >= 6 ? k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>);
             kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), grid_out, grid_in, fl, flush_mode, svd_store);
@@ -699,14 +709,14 @@ struct Engine : plb_engine {
     void enqueue_bwd_grid_pre(SlotRef si, SlotRef pf, bool restore, const GridSet& gs, cudaStream_t st) {   // forward grid of the substep + grid_out
         const int ng = blocks(n_nodes);
         GridStore<T> nostore{nullptr, nullptr, nullptr, nullptr, 0};
-        prof_begin(K_P2G_RECOMPUTE);
+        prof_begin(K_P2G_RECOMPUTE, st);
         if (restore) {
             k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, st>>>(cfg.n_grid, gs.in, gs.list, gs.count, store, si);
         } else {
             launch_p2g(si, si, 0);                      // (set 0 on the main stream: the non-stored path is never overlapped)
             if (sparse) compact_blocks();
         }
-        prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
+        prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE, st);
         if (sparse)
             k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, gs.list, gs.count, nostore, si);
         else
@@ -755,7 +765,7 @@ struct Engine : plb_engine {
     void launch_bwd_fused(SlotRef s_cur, SlotRef s_prev, T* a_next, T* a_cur, const GridSet& gs, bool svd) {
         const int nbc = blocks(cfg.n_particles, cta);
         const size_t sm = tile_smem_bytes(bwd_plane, cta);
-        prof_begin(K_P2G_BWD);
+        prof_begin(K_P2G_BWD_G2P_BWD);
         // (the plane-tile variants are instantiated without the SVD-store form: they lost at every size measured)
         auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo, false>)
                     : svd     ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>)
@@ -876,22 +886,39 @@ struct Engine : plb_engine {
     }
 
     // ---- whole env steps: one captured CUDA graph per (direction, n, adjoint parity, stored), replayed with a new cursor
+    // the kernel sequence of one env step (cursor-relative frame references)
+    void enqueue_step(const GraphKey& key) {
+        const bool fused = fuse && tile_scatter && sparse && key.n >= 2;
+        const bool restore = (key.stored & 1) != 0, next_ok = (key.stored & 2) != 0, svd = (key.stored & 4) != 0;
+        if (key.dir == 0) {
+            if (fused) enqueue_fwd_fused(key.n, &Engine::mk_cursor, env_list_mode());
+            else for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
+        } else {
+            int c = key.parity;
+            if (fused) enqueue_bwd_fused(key.n, restore, next_ok, svd, c, &Engine::mk_cursor, bwd_overlap && restore && !slab.on);
+            else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), restore, next_ok, svd, adj[c], adj[c ^ 1]); c ^= 1; }
+        }
+    }
     int launch_graph(const GraphKey& key, int slot0, int pf0) {
+        if (prof_on) {
+            // profiling (bench.py's live per-kernel times): the SAME kernel sequence as the graph, launched one by one with a
+            // CUDA-event pair around every kernel, on the streams the graph's branches were captured from
+            if (key.dir == 0 && scan_mode()) k_set_cursor_zero<<<1, 256, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0, store.cnt, key.n);
+            else k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
+            launches++;
+            enqueue_step(key);
+            cudaEvent_t join = next_event();            // (the overlapped backward leaves work on the side stream)
+            cudaEventRecord(join, side_stream);
+            cudaStreamWaitEvent(stream, join, 0);
+            PLB_CUDA(cudaGetLastError());
+            return PLB_OK;
+        }
         auto it = graphs.find(key);
         if (it == graphs.end()) {
             cudaGraph_t g = nullptr;
             long long l0 = launches;
             PLB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            const bool fused = fuse && tile_scatter && sparse && key.n >= 2;
-            const bool restore = (key.stored & 1) != 0, next_ok = (key.stored & 2) != 0, svd = (key.stored & 4) != 0;
-            if (key.dir == 0) {
-                if (fused) enqueue_fwd_fused(key.n, &Engine::mk_cursor, env_list_mode());
-                else for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
-            } else {
-                int c = key.parity;
-                if (fused) enqueue_bwd_fused(key.n, restore, next_ok, svd, c, &Engine::mk_cursor, bwd_overlap && restore && !slab.on);
-                else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), restore, next_ok, svd, adj[c], adj[c ^ 1]); c ^= 1; }
-            }
+            enqueue_step(key);
             cudaError_t ce = cudaStreamEndCapture(stream, &g);
             graph_nodes[key] = launches - l0;
             launches = l0;
@@ -913,7 +940,7 @@ struct Engine : plb_engine {
         if (int r = check_slot(slot0)) return r;
         if (int r = check_slot(slot0 + n)) return r;
         if (int r = check_pf(pf0, n)) return r;
-        if (!use_graphs || prof_on || !sparse) {
+        if (!use_graphs || !sparse) {
             for (int i = 0; i < n; i++) if (int r = substep_fwd(slot0 + i, slot0 + i + 1, pf0 + i)) return r;
             return PLB_OK;
         }
@@ -931,7 +958,7 @@ struct Engine : plb_engine {
         for (int i = 0; i < n; i++) { n_stored += stored[slot0 + i] ? 1 : 0; n_ok += fwd_ok[slot0 + i] ? 1 : 0; n_svd += svd_ok[slot0 + i] ? 1 : 0; }
         // the graphs take clamp masks / gather sums from the successor frames: every substep must have been run forward
         bool uniform = (n_stored == 0 || n_stored == n) && n_ok == n;
-        if (!use_graphs || prof_on || !sparse || !uniform) {
+        if (!use_graphs || !sparse || !uniform) {
             for (int i = n - 1; i >= 0; i--) if (int r = substep_bwd(slot0 + i, pf0 + i)) return r;
             return PLB_OK;
         }
@@ -1117,6 +1144,7 @@ struct Engine : plb_engine {
         if (int r = alloc_inboxes()) return r;
         cudaIpcMemHandle_t h;
         PLB_CUDA(cudaIpcGetMemHandle(&h, slab.inbox[side]));
+        slab.exported = true;
         static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
         std::memcpy(handle64, &h, 64);
         return PLB_OK;
@@ -1138,6 +1166,15 @@ struct Engine : plb_engine {
             for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
             graphs.clear();
         }
+        return PLB_OK;
+    }
+    int slab_ipc_close() override {
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        drop_graphs();                         // (they hold the peer pointers by value)
+        for (int side = 0; side < 2; side++)
+            if (slab.peer[side]) { cudaIpcCloseMemHandle(slab.peer[side]); slab.peer[side] = nullptr; }
+        slab.peer_ready = false; slab.ipc_closed = true;
+        use_graphs = false;
         return PLB_OK;
     }
     // which: 0 loss accumulators (kAccN doubles), 1 primitive pose gradients (max_prim_frames*8*8 doubles)
@@ -1496,6 +1533,7 @@ int plb_slab_loss_finish(plb_engine* e, int slot, int pf, int backward, double* 
 int plb_device_buffer(plb_engine* e, int which, void** ptr, long long* bytes) { return e->device_buffer(which, ptr, bytes); }
 int plb_slab_ipc_export(plb_engine* e, int side, void* handle64) { return e->slab_ipc_export(side, handle64); }
 int plb_slab_ipc_import(plb_engine* e, int side, const void* handle64) { return e->slab_ipc_import(side, handle64); }
+int plb_slab_ipc_close(plb_engine* e) { return e->slab_ipc_close(); }
 int plb_debug_get_grid(plb_engine* e, double* in4, double* out4) { return e->debug_get_grid(in4, out4); }
 long long plb_launch_count(const plb_engine* e) { return e->launches; }
 int plb_profile_enable(plb_engine* e, int on) {

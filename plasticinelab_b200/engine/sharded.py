@@ -33,7 +33,7 @@ def _tensor(ptr, nbytes, device, f64=False):
 
 
 class ShardedEnv:
-    def __init__(self, cfg, rank=None, world=None, dtype="float32", device=None, halo_w=8, group=None, peer=None):
+    def __init__(self, cfg, rank=None, world=None, dtype="float32", device=None, halo_w=8, group=None, peer=None, materials=None):
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.group = group
@@ -50,6 +50,8 @@ class ShardedEnv:
         self.env = TaichiEnv(cfg, dtype=dtype, device=dev_index, particle_index=self.index)
         self.env.initialize()
         self.env.set_copy(False)
+        if materials is not None:          # callable: positions (n, 3) of this rank's particles -> (mu, lam, yield_stress) arrays
+            self.env.simulator.set_materials(*materials(self.env.init_particles))
         self.engine = eng = self.env.engine
         self.S = self.env.simulator.substeps
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
@@ -92,6 +94,17 @@ class ShardedEnv:
             h = gathered[peer][1 - side]          # the neighbour's inbox that faces me
             eng.call("plb_slab_ipc_import", side, C.create_string_buffer(h, 64))
         dist.barrier(group=self.group)
+
+    def close(self):
+        """Collective: unmap the neighbours' inboxes on every rank BEFORE any rank frees its own (CUDA IPC rule), then destroy."""
+        if self.engine is None:
+            return
+        if self.peer:
+            self.engine.call("plb_slab_ipc_close")
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+        self.engine.close()
+        self.engine = None
 
     # ---- communication
     def _exchange(self, which):
