@@ -99,6 +99,19 @@ PLB_HD long long node_index(int n, int i, int j, int k) { return (long long)((i 
 PLB_HD long long node_index(int n, int i, int j, int k) { return ((long long)i * n + j) * n + k; }
 #endif
 
+// 27-node stencil window of a Vec4 grid: at(i, j, k) = node (b0 + i, b1 + j, b2 + k) of the particle's stencil.  `p` points at
+// node (b0, b1, b2) either in the dense global grid (strides n^2, n) or in a shared-memory tile of 8^3 nodes (strides 64, 8)
+// that TMA loaded for the CTA (plb_tile.cuh): a generic pointer, so the gather loops have one code path.
+template <class T> struct GridView {
+    const Vec4<T>* p; int si, sj;
+    PLB_HD Vec4<T> at(int i, int j, int k) const { return p[i * si + j * sj + k]; }
+};
+template <class T> PLB_HD GridView<T> global_view(const Vec4<T>* grid, int n, const int b[3]) {
+    GridView<T> v;
+    v.p = grid + node_index(n, b[0], b[1], b[2]); v.si = n * n; v.sj = n;
+    return v;
+}
+
 // Scatter policy used by the two scattering bodies.  Direct: one (vector) atomic per node and particle.
 // The CUDA kernels can substitute WarpTileScatter (plb_kernels.cuh), which pre-reduces a warp's contributions.
 template <class T> struct DirectScatter {
@@ -187,29 +200,26 @@ PLB_HD void grid_fwd_body(long long node, const SimConst<T>& P, const PrimSet<T>
 
 // G2P: 27-node gather, APIC C, advection
 template <class T>
-PLB_HD void g2p_core(const SimConst<T>& P, V3<T> x, const Vec4<T>* grid_out, V3<T>& nx, V3<T>& nv_out, M3<T>& nC_out) {
-    Stencil<T> st = make_stencil(x, P.inv_dx);
+PLB_HD void g2p_core(const SimConst<T>& P, V3<T> x, const Stencil<T>& st, const GridView<T>& gv, V3<T>& nx, V3<T>& nv_out, M3<T>& nC_out) {
     // v' = sum w g;  C' = 4 inv_dx sum w g (x) (o - fx) = 4 inv_dx (sum w g (x) o - v' (x) fx): accumulate sum w g and the
     // three offset-weighted sums (offsets are 0/1/2, so these are adds), one rank-1 correction at the end
+    // (written as multiply-add chains: t0 = sum_k w_k g_k and tk = sum_k k w_k g_k per (i, j) column, then four accumulations
+    //  with the column weight -- 23 FMA-class instructions per column instead of the ~40 of the product-then-add form)
     V3<T> nv = zero3<T>(), si = zero3<T>(), sj = zero3<T>(), sk = zero3<T>();
+    const T wk0 = st.w[0][2], wk1 = st.w[1][2], wk2 = st.w[2][2], wk2x2 = T(2) * st.w[2][2];
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            T wij = st.w[i][0] * st.w[j][1];
-            V3<T> t0 = zero3<T>(), tk = zero3<T>();
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                Vec4<T> g4 = grid_out[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
-                V3<T> wg = st.w[k][2] * mk3<T>(g4.x, g4.y, g4.z);
-                t0 += wg;
-                if (k > 0) tk += T(k) * wg;
-            }
-            V3<T> u = wij * t0;
-            nv += u;
-            sk += wij * tk;
-            if (i > 0) si += T(i) * u;
-            if (j > 0) sj += T(j) * u;
+            const T wij = st.w[i][0] * st.w[j][1];
+            const Vec4<T> a4 = gv.at(i, j, 0), b4 = gv.at(i, j, 1), c4v = gv.at(i, j, 2);
+            const V3<T> g0 = mk3<T>(a4.x, a4.y, a4.z), g1 = mk3<T>(b4.x, b4.y, b4.z), g2 = mk3<T>(c4v.x, c4v.y, c4v.z);
+            const V3<T> t0 = fma3(wk2, g2, fma3(wk1, g1, wk0 * g0));
+            const V3<T> tk = fma3(wk2x2, g2, wk1 * g1);
+            nv = fma3(wij, t0, nv);
+            sk = fma3(wij, tk, sk);
+            if (i > 0) si = fma3(T(i) * wij, t0, si);
+            if (j > 0) sj = fma3(T(j) * wij, t0, sj);
         }
     M3<T> nC;
     const T c4 = T(4) * P.inv_dx;
@@ -222,6 +232,11 @@ PLB_HD void g2p_core(const SimConst<T>& P, V3<T> x, const Vec4<T>* grid_out, V3<
     nx = advect(P, x, nv);
     nv_out = nv;
     nC_out = nC;
+}
+template <class T>
+PLB_HD void g2p_core(const SimConst<T>& P, V3<T> x, const Vec4<T>* grid_out, V3<T>& nx, V3<T>& nv_out, M3<T>& nC_out) {
+    Stencil<T> st = make_stencil(x, P.inv_dx);
+    g2p_core<T>(P, x, st, global_view(grid_out, P.n_grid, st.b), nx, nv_out, nC_out);
 }
 template <class T>
 PLB_HD void g2p_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& out, const Vec4<T>* grid_out) {
@@ -305,6 +320,113 @@ PLB_HD V3<T> g2p_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> gxn, V3<T> gvn, c
     gx += stencil_backward(st, gw, gfx, P.inv_dx);
     return gx;
 }
+// ---- g2p.grad split in two passes (plb_tile.cuh): the gather pass reads grid_out (through a view, possibly a shared-memory
+// tile) and produces the partial x-adjoint; the scatter pass only needs the stencil and the coefficients of h_o, so that the
+// shared-memory tile can be dead -- and its space reused by the scatter tiles -- before the first contribution is parked.
+template <class T> struct G2PBwdCarry { V3<T> h0, hc0, hc1, hc2; };
+template <class T, bool kStoredNext>
+PLB_HD V3<T> g2p_bwd_gather(const SimConst<T>& P, V3<T> x, const Stencil<T>& st, const GridView<T>& gv, V3<T> gxn, V3<T> gvn, const M3<T>& gCn,
+                            V3<T> xn, V3<T> nv_stored, G2PBwdCarry<T>& carry) {
+    V3<T> nv, gy;
+    if (kStoredNext) {
+        nv = nv_stored;
+        gy = advect_backward_stored(P, xn, gxn);
+    } else {
+        nv = zero3<T>();
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                V3<T> t0 = zero3<T>();
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    Vec4<T> g4 = gv.at(i, j, k);
+                    t0 += st.w[k][2] * mk3<T>(g4.x, g4.y, g4.z);
+                }
+                nv += (st.w[i][0] * st.w[j][1]) * t0;
+            }
+        gy = advect_backward(P, x, nv, gxn);
+    }
+    V3<T> gx = gy;
+    V3<T> gvv = gvn + P.dt * gy;
+    T gw[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) gw[a][d] = T(0);
+    const T c4 = T(4) * P.inv_dx;
+    carry.hc0 = mk3<T>(c4 * gCn.m[0][0], c4 * gCn.m[1][0], c4 * gCn.m[2][0]);
+    carry.hc1 = mk3<T>(c4 * gCn.m[0][1], c4 * gCn.m[1][1], c4 * gCn.m[2][1]);
+    carry.hc2 = mk3<T>(c4 * gCn.m[0][2], c4 * gCn.m[1][2], c4 * gCn.m[2][2]);
+    carry.h0 = gvv - (st.fx.x * carry.hc0 + st.fx.y * carry.hc1 + st.fx.z * carry.hc2);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        V3<T> hi = carry.h0 + T(i) * carry.hc0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            V3<T> hij = hi + T(j) * carry.hc1;
+            T wij = st.w[i][0] * st.w[j][1];
+            T tij = T(0);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                V3<T> h = hij + T(k) * carry.hc2;
+                Vec4<T> g4 = gv.at(i, j, k);
+                T gwt = g4.x * h.x + g4.y * h.y + g4.z * h.z;
+                tij += gwt * st.w[k][2];
+                gw[k][2] += gwt * wij;
+            }
+            gw[i][0] += tij * st.w[j][1];
+            gw[j][1] += tij * st.w[i][0];
+        }
+    }
+    V3<T> gfx = (-c4) * mTv(gCn, nv);
+    gx += stencil_backward(st, gw, gfx, P.inv_dx);
+    return gx;
+}
+template <class T, class Sc>
+PLB_HD void g2p_bwd_scatter(const Stencil<T>& st, const G2PBwdCarry<T>& carry, const Sc& sc) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        V3<T> hi = carry.h0 + T(i) * carry.hc0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            V3<T> hij = hi + T(j) * carry.hc1;
+            T wij = st.w[i][0] * st.w[j][1];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T w = wij * st.w[k][2];
+                V3<T> h = hij + T(k) * carry.hc2;
+                sc.add((i * 3 + j) * 3 + k, st.b[0] + i, st.b[1] + j, st.b[2] + k, mk4<T>(w * h.x, w * h.y, w * h.z, T(0)));
+            }
+        }
+        sc.end_plane(i);
+    }
+}
+// P2G scatter loop alone (the particle part -- p2g_particle -- already ran): 27 contributions through the scatter policy
+template <class T, class Sc>
+PLB_HD void p2g_scatter(const SimConst<T>& P, const Stencil<T>& st, V3<T> v, const M3<T>& affine, const Sc& sc) {
+    V3<T> c0 = mk3<T>(affine.m[0][0] * P.dx, affine.m[1][0] * P.dx, affine.m[2][0] * P.dx);
+    V3<T> c1 = mk3<T>(affine.m[0][1] * P.dx, affine.m[1][1] * P.dx, affine.m[2][1] * P.dx);
+    V3<T> c2 = mk3<T>(affine.m[0][2] * P.dx, affine.m[1][2] * P.dx, affine.m[2][2] * P.dx);
+    V3<T> m0 = P.p_mass * v - (st.fx.x * c0 + st.fx.y * c1 + st.fx.z * c2);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        V3<T> mi = m0 + T(i) * c0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            V3<T> mij = mi + T(j) * c1;
+            T wij = st.w[i][0] * st.w[j][1];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T w = wij * st.w[k][2];
+                V3<T> mom = w * (mij + T(k) * c2);
+                sc.add((i * 3 + j) * 3 + k, st.b[0] + i, st.b[1] + j, st.b[2] + k, mk4<T>(mom.x, mom.y, mom.z, w * P.p_mass));
+            }
+        }
+        sc.end_plane(i);
+    }
+}
+
 // fnext: the frame G2P produced from `in` (null: not available, recompute the gather sum)
 template <class T, class Sc>
 PLB_HD void g2p_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,
@@ -352,7 +474,7 @@ PLB_HD void grid_bwd_body(long long node, const SimConst<T>& P, const PrimSet<T>
 // twice -- before the 27-node gather only for `affine`, and again after it for the adjoint -- instead of keeping its ~58
 // intermediate values (P2GState) in registers across the gather loop, which is where the backward kernels' register peak is.
 template <class T, bool kSvdGiven = false, bool kTwoPhase = false>
-PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys, const Vec4<T>* g_in,
+PLB_HD void p2g_bwd_core(const SimConst<T>& P, const Stencil<T>& st, const GridView<T>& gin_view, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys,
                          const M3<T>& gF_next, V3<T> gx_partial, V3<T>& gx_out, V3<T>& gv_out, M3<T>& gC, M3<T>& gF,
                          SvdRec<T>* svd = nullptr, const FramePtr<T>* gF_late = nullptr, int p_late = 0, const FramePtr<T>* state_late = nullptr) {
     // (kTwoPhase: after the gather loop the adjoint of F[f+1] is loaded from gF_late instead of being passed in gF_next, and
@@ -361,7 +483,6 @@ PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C,
     P2GState<T> keep;
     if (kSvdGiven && kTwoPhase) p2g_particle<T, true>(P, C, F, mu, lam, ys, new_F, affine, nullptr, svd);
     else p2g_particle<T, kSvdGiven>(P, C, F, mu, lam, ys, new_F, affine, &keep, svd);
-    Stencil<T> st = make_stencil(x, P.inv_dx);
     // forward node value: w_o (m_o, p_mass) with m_o = p_mass v + affine (o - fx) dx, evaluated incrementally.
     // With a_o = adjoint of the node momentum: g(weight_o) = a_o . m_o + b_o p_mass;  g(v) = p_mass sum w a;
     // g(affine) = (sum w a (x) o - (sum w a) (x) fx) dx;  g(fx) -= dx affine^T (sum w a)  -- the last two leave the loop.
@@ -376,28 +497,27 @@ PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C,
     for (int a = 0; a < 3; a++)
 #pragma unroll
         for (int d = 0; d < 3; d++) gw[a][d] = T(0);
+    // per (i, j) column, multiply-add chains over k (as in g2p_core): A0 = sum_k w_k a_k, Ak = sum_k k w_k a_k feed the four
+    // accumulators with the column weight; the weight adjoints take gwt_k = a_k . m_ijk + b_k p_mass
+    const T wk0 = st.w[0][2], wk1 = st.w[1][2], wk2 = st.w[2][2], wk2x2 = T(2) * st.w[2][2];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         V3<T> mi = m0 + T(i) * c0;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            V3<T> mij = mi + T(j) * c1;
-            T wij = st.w[i][0] * st.w[j][1];
-            T tij = T(0);
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                T w = wij * st.w[k][2];
-                Vec4<T> g4 = g_in[node_index(P.n_grid, st.b[0] + i, st.b[1] + j, st.b[2] + k)];
-                V3<T> a = mk3<T>(g4.x, g4.y, g4.z);
-                T gwt = dot(a, mij + T(k) * c2) + g4.w * P.p_mass;
-                V3<T> wa = w * a;
-                gv += wa;
-                if (i > 0) si += T(i) * wa;
-                if (j > 0) sj += T(j) * wa;
-                if (k > 0) sk += T(k) * wa;
-                tij += gwt * st.w[k][2];
-                gw[k][2] += gwt * wij;
-            }
+            const V3<T> mij0 = mi + T(j) * c1, mij1 = mij0 + c2, mij2 = mij1 + c2;
+            const T wij = st.w[i][0] * st.w[j][1];
+            const Vec4<T> q0 = gin_view.at(i, j, 0), q1 = gin_view.at(i, j, 1), q2 = gin_view.at(i, j, 2);
+            const V3<T> a0 = mk3<T>(q0.x, q0.y, q0.z), a1 = mk3<T>(q1.x, q1.y, q1.z), a2 = mk3<T>(q2.x, q2.y, q2.z);
+            const V3<T> A0 = fma3(wk2, a2, fma3(wk1, a1, wk0 * a0));
+            const V3<T> Ak = fma3(wk2x2, a2, wk1 * a1);
+            gv = fma3(wij, A0, gv);
+            sk = fma3(wij, Ak, sk);
+            if (i > 0) si = fma3(T(i) * wij, A0, si);
+            if (j > 0) sj = fma3(T(j) * wij, A0, sj);
+            const T gw0 = dot(a0, mij0) + q0.w * P.p_mass, gw1 = dot(a1, mij1) + q1.w * P.p_mass, gw2 = dot(a2, mij2) + q2.w * P.p_mass;
+            const T tij = gw0 * wk0 + gw1 * wk1 + gw2 * wk2;
+            gw[0][2] += gw0 * wij; gw[1][2] += gw1 * wij; gw[2][2] += gw2 * wij;
             gw[i][0] += tij * st.w[j][1];
             gw[j][1] += tij * st.w[i][0];
         }
@@ -431,6 +551,14 @@ PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C,
         return;
     }
     p2g_particle_backward<T>(P, C, F, mu, lam, keep, g_aff, gF_next, gC, gF);
+}
+template <class T, bool kSvdGiven = false, bool kTwoPhase = false>
+PLB_HD void p2g_bwd_core(const SimConst<T>& P, V3<T> x, V3<T> v, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys, const Vec4<T>* g_in,
+                         const M3<T>& gF_next, V3<T> gx_partial, V3<T>& gx_out, V3<T>& gv_out, M3<T>& gC, M3<T>& gF,
+                         SvdRec<T>* svd = nullptr, const FramePtr<T>* gF_late = nullptr, int p_late = 0, const FramePtr<T>* state_late = nullptr) {
+    Stencil<T> st = make_stencil(x, P.inv_dx);
+    p2g_bwd_core<T, kSvdGiven, kTwoPhase>(P, st, global_view(g_in, P.n_grid, st.b), v, C, F, mu, lam, ys, gF_next, gx_partial, gx_out, gv_out, gC, gF,
+                                          svd, gF_late, p_late, state_late);
 }
 template <class T, bool kSvdGiven = false>
 PLB_HD void p2g_bwd_body(int p, const SimConst<T>& P, const FramePtr<T>& in, const FramePtr<T>& adj_next,

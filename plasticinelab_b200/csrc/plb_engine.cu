@@ -135,6 +135,10 @@ struct plb_engine {
 template <class T> struct OccSel { static constexpr int fwd_lo = 1, fwd_hi = 1, bwd_lo = 1, bwd_hi = 1; };
 template <> struct OccSel<float> { static constexpr int fwd_lo = 5, fwd_hi = 6, bwd_lo = 3, bwd_hi = 4; };
 
+// same for the chunked kernels (plb_tile.cuh): 28.5 KB of shared memory per CTA, so the register cap decides the resident CTAs
+template <class T> struct TileOcc { static constexpr int fwd = 1, fwd_hi = 1, bwd_lo = 1, bwd_hi = 1; };
+template <> struct TileOcc<float> { static constexpr int fwd = 5, fwd_hi = 6, bwd_lo = 3, bwd_hi = 4; };
+
 template <class T>
 struct Engine : plb_engine {
     plb_config cfg{};
@@ -212,6 +216,18 @@ struct Engine : plb_engine {
     // spatial sort: d_perm[p] = caller-side index of the particle stored at position p
     int* d_perm = nullptr; int* d_perm2 = nullptr; unsigned* d_keys = nullptr; unsigned* d_keys2 = nullptr;
     int* d_vals = nullptr; int* d_vals2 = nullptr; void* d_cub = nullptr; size_t cub_bytes = 0; T* frame_tmp = nullptr;
+    // chunked particle kernels with TMA-loaded grid windows (plb_tile.cuh) inside the env-step graphs; PLB_TILE=0: the
+    // per-thread-gather kernels.  The chunk table indexes the sorted order: rebuilt by every plb_sort_particles.
+    bool tile_mode = true;
+    // backward chunk kernels (PLB_TILE_BWD=1): measured slower than the per-thread-gather backward kernel on a B200 (171 vs 159 us
+    // at 1M particles: the chunk -> TMA -> wait chain at CTA start and instruction-fetch stalls outweigh the shared-memory
+    // gathers in a kernel that registers cap at 16 warps per SM either way), so the default backward path keeps the latter
+    bool tile_bwd = false;
+    int tile_fwd_minb = 6;          // chunked forward kernel: 6 resident CTAs per SM (80 registers, no spills) | 5 (96 registers): PLB_TILE_FWD_MINB
+    bool svd_warm = true;           // Jacobi SVD of substep s+1 started from V of substep s (needs the SVD store; PLB_SVD_WARM=0: from the identity)
+    Chunk* d_chunks = nullptr; int* d_nchunks = nullptr; int chunk_cap = 0, chunk_grid = 0;
+    CUtensorMap tm_out[2], tm_gin;  // grid_out of the two grid sets, g_in
+    ChunkTable chunk_table() const { ChunkTable t; t.chunks = d_chunks; t.n_chunks = d_nchunks; return t; }
     bool has_target = false;
     double target_max = 0, target_sum = 0;
     LossWeights lw{10.0, 10.0, 1.0, 0};
@@ -229,6 +245,7 @@ struct Engine : plb_engine {
         cudaFree(target_sdf); cudaFree(d_stage); cudaFree(d_traj); cudaFree(d_prim_grad); cudaFree(d_acc); cudaFree(d_count);
         cudaFree(d_flags); cudaFree(d_list); cudaFree(d_nactive); cudaFree(d_perm); cudaFree(d_perm2); cudaFree(d_keys);
         cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_cub); cudaFree(frame_tmp);
+        cudaFree(d_chunks); cudaFree(d_nchunks);
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt); cudaFree(store.overflow); cudaFree(d_cursor);
         cudaFree(d_flags2); cudaFree(d_listed);
@@ -383,7 +400,63 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMalloc(&d_perm, n_pad * sizeof(int)));
         PLB_CUDA(cudaMalloc(&d_perm2, n_pad * sizeof(int)));
         k_iota<<<blocks(n_pad), kBlock>>>((int)n_pad, d_perm);
+        if (const char* v = getenv("PLB_TILE")) tile_mode = atoi(v) != 0;
+        if (const char* v = getenv("PLB_SVD_WARM")) svd_warm = atoi(v) != 0;
+        if (const char* v = getenv("PLB_TILE_BWD")) tile_bwd = atoi(v) != 0;
+        if (const char* v = getenv("PLB_TILE_FWD_MINB")) tile_fwd_minb = atoi(v);
+        tile_mode = tile_mode && tile_scatter && sparse && fuse;
+        tile_bwd = tile_bwd && tile_mode;
+        if (tile_mode) {
+            chunk_cap = (c.n_particles + kChunk - 1) / kChunk + std::min(n_blocks, c.n_particles);
+            PLB_CUDA(cudaMalloc(&d_chunks, (size_t)chunk_cap * sizeof(Chunk)));
+            PLB_CUDA(cudaMalloc(&d_nchunks, sizeof(int)));
+            chunk_grid = (c.n_particles + kChunk - 1) / kChunk;
+            k_trivial_chunks<<<blocks(chunk_grid), kBlock>>>(c.n_particles, d_chunks, d_nchunks);
+            if (int r = make_tile_map(&tm_out[0], sets[0].out)) return r;
+            if (sets[1].out) { if (int r = make_tile_map(&tm_out[1], sets[1].out)) return r; } else tm_out[1] = tm_out[0];
+            if (int r = make_tile_map(&tm_gin, g_in)) return r;
+            // (without the carve-out hint the driver picked a shared-memory split that held 4 CTAs of 28.5 KB: ncu launch__occupancy_limit_shared_mem)
+            const int fwd_sm = (int)chunk_smem_bytes(kFwdTiles), bwd_sm = (int)chunk_smem_bytes(kBwdTiles), carve = cudaSharedmemCarveoutMaxShared;
+#define PLB_TILE_ATTR(k) do { PLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(fwd_sm, bwd_sm))); \
+                              PLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve)); } while (0)
+            PLB_TILE_ATTR((k_fwd_chunk<T, FWD_P2G, TileOcc<T>::fwd>));
+            PLB_TILE_ATTR((k_fwd_chunk<T, FWD_G2P | FWD_P2G, TileOcc<T>::fwd>));
+            PLB_TILE_ATTR((k_fwd_chunk<T, FWD_G2P | FWD_P2G, TileOcc<T>::fwd_hi>));
+            PLB_TILE_ATTR((k_fwd_chunk<T, FWD_G2P, TileOcc<T>::fwd>));
+            PLB_TILE_ATTR((k_bwd_chunk<T, BWD_G2P, TileOcc<T>::bwd_lo, false>));
+            PLB_TILE_ATTR((k_bwd_chunk<T, BWD_P2G | BWD_G2P, TileOcc<T>::bwd_lo, false>));
+            PLB_TILE_ATTR((k_bwd_chunk<T, BWD_P2G | BWD_G2P, TileOcc<T>::bwd_hi, true>));
+            PLB_TILE_ATTR((k_bwd_chunk<T, BWD_P2G, TileOcc<T>::bwd_lo, false>));
+            PLB_TILE_ATTR((k_bwd_chunk<T, BWD_P2G, TileOcc<T>::bwd_hi, true>));
+#undef PLB_TILE_ATTR
+        }
         PLB_CUDA(cudaDeviceSynchronize());
+        return PLB_OK;
+    }
+    // shared memory of a chunk CTA: its scatter tiles; the TMA windows (one forward, two backward) alias them
+    static size_t chunk_smem_bytes(int tiles) { return std::max((size_t)tiles * kTileVec4, (size_t)2 * kTileNodes) * sizeof(Vec4<T>); }
+
+    // ---------------------------------------------------------------- TMA descriptors (one per grid array the particle kernels gather from)
+    int make_tile_map(CUtensorMap* tm, const Vec4<T>* grid) {
+        typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static Encode encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            PLB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+            PLB_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+            encode = (Encode)fn;
+        }
+        // tensor (component, k, j, i): 4 scalars per node, node index (i n + j) n + k; box = all 4 components of 8 x 8 x 8 nodes;
+        // nodes outside the grid (a window that starts at -1 or ends past n - 1) are zero-filled by the hardware
+        const cuuint64_t n = (cuuint64_t)cfg.n_grid, node = 4 * sizeof(T);
+        const cuuint64_t dims[4] = {4, n, n, n};
+        const cuuint64_t strides[3] = {node, node * n, node * n * n};
+        const cuuint32_t box[4] = {4, kTileEdge, kTileEdge, kTileEdge}, estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(tm, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)grid, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PLB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
         return PLB_OK;
     }
 
@@ -491,6 +564,19 @@ struct Engine : plb_engine {
         std::swap(d_perm, d_perm2);
         inv_perm_valid = false;
         launches += 3;
+        if (tile_mode) {
+            PLB_CUDA(cudaMemsetAsync(d_nchunks, 0, sizeof(int), stream));
+            k_build_chunks<<<blocks(n), kBlock, 0, stream>>>(n, cfg.n_grid, d_keys2, d_chunks, d_nchunks, chunk_cap, store.overflow);
+            launches++;
+            int nch = 0;
+            PLB_CUDA(cudaMemcpyAsync(&nch, d_nchunks, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            PLB_CUDA(cudaStreamSynchronize(stream));
+            PLB_REQUIRE(nch > 0 && nch <= chunk_cap, "chunk table overflow");
+            if (nch > chunk_grid) {                 // (captured graphs hold the launch geometry)
+                chunk_grid = std::min(chunk_cap, nch + nch / 16 + 64);
+                drop_graphs();
+            }
+        }
         PLB_CUDA(cudaGetLastError());
         std::fill(stored.begin(), stored.end(), 0);
         std::fill(fwd_ok.begin(), fwd_ok.end(), 0);
@@ -684,6 +770,32 @@ struct Engine : plb_engine {
         const int nb = blocks(cfg.n_particles);
         unsigned char* fl = (sparse && !fixed_list) ? d_flags : nullptr;
         if (fixed_list) enqueue_env_list(mk(this, 0, 0));
+        if (tile_mode) {
+            // chunked kernels: one CTA per <= 128 particles of one grid block, grid_out window by TMA (plb_tile.cuh)
+            const size_t sm = chunk_smem_bytes(kFwdTiles);
+            const SlotRef none = abs_ref(0);
+            prof_begin(K_P2G);
+            k_fwd_chunk<T, FWD_P2G, TileOcc<T>::fwd><<<chunk_grid, kBlock, sm, stream>>>(tm_out[0], P, frames, n_pad, mk(this, 0, 0), none, mk(this, 1, 0), material(),
+                                                                                      chunk_table(), grid_out, grid_in, fl, svd_store, 0);
+            prof_end();
+            enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0), fixed_list);
+            for (int i = 1; i < n; i++) {
+                prof_begin(K_G2P_P2G);
+                auto kern = tile_fwd_minb >= 6 ? k_fwd_chunk<T, FWD_G2P | FWD_P2G, TileOcc<T>::fwd_hi> : k_fwd_chunk<T, FWD_G2P | FWD_P2G, TileOcc<T>::fwd>;
+                kern<<<chunk_grid, kBlock, sm, stream>>>(tm_out[0], P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), chunk_table(),
+                                                         grid_out, grid_in, fl, svd_store, svd_warm ? 1 : 0);
+                prof_end();
+                enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i), fixed_list);
+                launches++;
+            }
+            prof_begin(K_G2P);
+            k_fwd_chunk<T, FWD_G2P, TileOcc<T>::fwd><<<chunk_grid, kBlock, sm, stream>>>(tm_out[0], P, frames, n_pad, mk(this, 0, n - 1), none, mk(this, 1, n - 1), material(),
+                                                                                      chunk_table(), grid_out, grid_in, nullptr, (T*)nullptr, 0);
+            prof_end();
+            launches += 2;
+            if (fixed_list) enqueue_env_list_check(mk(this, 1, n - 1));
+            return;
+        }
         prof_begin(K_P2G);
         launch_p2g(mk(this, 0, 0), mk(this, 1, 0), 1, !fixed_list);
         prof_end();
@@ -742,9 +854,15 @@ struct Engine : plb_engine {
         prof_end();
         launches++;
     }
-    void launch_g2p_bwd(SlotRef si, T* a_next, T* a_cur, const GridSet& gs, bool next_ok) {
+    // (grid set -> its TMA descriptor)
+    const CUtensorMap& tm_of(const GridSet& gs) const { return gs.out == sets[1].out ? tm_out[1] : tm_out[0]; }
+    // s_next: the successor frame of si (only dereferenced when next_ok)
+    void launch_g2p_bwd(SlotRef si, T* a_next, T* a_cur, const GridSet& gs, bool next_ok, bool chunked = false, SlotRef s_next = SlotRef{nullptr, 0, 0}) {
         prof_begin(K_G2P_BWD);
-        if (tile_scatter) {
+        if (chunked) {
+            k_bwd_chunk<T, BWD_G2P, TileOcc<T>::bwd_lo, false><<<chunk_grid, kBlock, chunk_smem_bytes(kBwdTiles), stream>>>(
+                tm_gin, tm_of(gs), P, frames, n_pad, s_next, si, next_ok ? 1 : 0, a_next, a_cur, material(), chunk_table(), g_in, gs.out, g_out, (T*)nullptr);
+        } else if (tile_scatter) {
             const int nbc = blocks(cfg.n_particles, cta);
             const size_t sm = tile_smem_bytes(bwd_plane, cta);
             if (bwd_plane) k_g2p_bwd_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode);
@@ -755,9 +873,17 @@ struct Engine : plb_engine {
         prof_end();
         launches++;
     }
-    void launch_p2g_bwd(SlotRef si, T* a_next, T* a_cur, bool svd) {
+    void launch_p2g_bwd(SlotRef si, T* a_next, T* a_cur, bool svd, bool chunked = false) {
         prof_begin(K_P2G_BWD);
-        if (svd) k_p2g_bwd<T, true><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in, svd_store);
+        if (chunked) {
+            const size_t sm = chunk_smem_bytes(kBwdTiles);
+            if (svd && bwd_minb >= 4)
+                k_bwd_chunk<T, BWD_P2G, TileOcc<T>::bwd_hi, true><<<chunk_grid, kBlock, sm, stream>>>(tm_gin, tm_out[0], P, frames, n_pad, si, si, 0, a_next, a_cur, material(),
+                                                                                                   chunk_table(), g_in, grid_out, g_out, svd_store);
+            else
+                k_bwd_chunk<T, BWD_P2G, TileOcc<T>::bwd_lo, false><<<chunk_grid, kBlock, sm, stream>>>(tm_gin, tm_out[0], P, frames, n_pad, si, si, 0, a_next, a_cur, material(),
+                                                                                                    chunk_table(), g_in, grid_out, g_out, (T*)nullptr);
+        } else if (svd) k_p2g_bwd<T, true><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in, svd_store);
         else k_p2g_bwd<T, false><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, material(), g_in, (T*)nullptr);
         prof_end();
         launches++;
@@ -766,6 +892,17 @@ struct Engine : plb_engine {
         const int nbc = blocks(cfg.n_particles, cta);
         const size_t sm = tile_smem_bytes(bwd_plane, cta);
         prof_begin(K_P2G_BWD_G2P_BWD);
+        if (tile_bwd) {
+            if (svd && bwd_minb >= 4)
+                k_bwd_chunk<T, BWD_P2G | BWD_G2P, TileOcc<T>::bwd_hi, true><<<chunk_grid, kBlock, chunk_smem_bytes(kBwdTiles), stream>>>(
+                    tm_gin, tm_of(gs), P, frames, n_pad, s_cur, s_prev, 1, a_next, a_cur, material(), chunk_table(), g_in, gs.out, g_out, svd_store);
+            else
+                k_bwd_chunk<T, BWD_P2G | BWD_G2P, TileOcc<T>::bwd_lo, false><<<chunk_grid, kBlock, chunk_smem_bytes(kBwdTiles), stream>>>(
+                    tm_gin, tm_of(gs), P, frames, n_pad, s_cur, s_prev, 1, a_next, a_cur, material(), chunk_table(), g_in, gs.out, g_out, (T*)nullptr);
+            prof_end();
+            launches++;
+            return;
+        }
         // (the plane-tile variants are instantiated without the SVD-store form: they lost at every size measured)
         auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo, false>)
                     : svd     ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>)
@@ -791,7 +928,7 @@ struct Engine : plb_engine {
         svd = svd && !bwd_plane;
         if (!overlap) {
             enqueue_bwd_grid_pre(mk(this, 0, n - 1), mk(this, 2, n - 1), restore, sets[0], stream);
-            launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[0], next_ok);
+            launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[0], next_ok, tile_bwd, mk(this, 1, n - 1));
             enqueue_bwd_grid_adj(mk(this, 2, n - 1), sets[0]);
             for (int i = n - 1; i >= 1; i--) {
                 enqueue_bwd_grid_pre(mk(this, 0, i - 1), mk(this, 2, i - 1), restore, sets[0], stream);
@@ -799,7 +936,7 @@ struct Engine : plb_engine {
                 c ^= 1;
                 enqueue_bwd_grid_adj(mk(this, 2, i - 1), sets[0]);
             }
-            launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1], svd);
+            launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1], svd, tile_bwd);
             return;
         }
         cap_ev_used = 0;
@@ -811,7 +948,7 @@ struct Engine : plb_engine {
         cudaEvent_t ev_pre = next_event();
         enqueue_bwd_grid_pre(mk(this, 0, n - 2), mk(this, 2, n - 2), true, sets[(n - 2) & 1], side_stream);
         cudaEventRecord(ev_pre, side_stream);
-        launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[(n - 1) & 1], next_ok);
+        launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[(n - 1) & 1], next_ok, tile_bwd, mk(this, 1, n - 1));
         enqueue_bwd_grid_adj(mk(this, 2, n - 1), sets[(n - 1) & 1]);
         cudaEvent_t ev_adj = next_event();              // A(i) done, for the i of the coming iteration
         cudaEventRecord(ev_adj, stream);
@@ -829,7 +966,7 @@ struct Engine : plb_engine {
             ev_adj = next_event();
             cudaEventRecord(ev_adj, stream);
         }
-        launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1], svd);
+        launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1], svd, tile_bwd);
     }
     // push my listed zone blocks of `grid` into the neighbours' inboxes, publish, wait for theirs
     void halo_exchange(const Vec4<T>* grid) {

@@ -304,7 +304,7 @@ template <class T, bool kPlane> __device__ __forceinline__ Vec4<T>* warp_tile_pt
 template <class T, bool kPlane>
 __global__ void __launch_bounds__(kBlock) k_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
                                                      int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode, T* svd_base) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     SvdPtr<T> sp = svd_at(svd_base, slot_in.get(), n_pad);
     t_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                      frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in, flags, flush_mode,
@@ -318,7 +318,7 @@ template <class T, bool kPlane, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB) k_g2p_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in,
                                                                            SlotRef slot_mid, SlotRef slot_out, Material<T> mat,
                                                                            const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags, int flush_mode, T* svd_base) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     SvdPtr<T> sp = svd_at(svd_base, slot_mid.get(), n_pad);          // the P2G half decomposes F_tmp of frame `mid`
     t_g2p_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                          frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_mid.get(), n_pad),
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kBlock, kMinB) k_g2p_p2g_warp(SimConst<T> P, T
 template <class T, bool kPlane>
 __global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, int next_ok,
                                                                            T* adj_next, T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int si = slot_in.get();
     FramePtr<T> fnext = frame_at(frames, si + 1, n_pad);
     t_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
@@ -343,7 +343,7 @@ template <class T, bool kPlane, int kMinB, bool kSvd>
 __global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
                                                                                    SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
                                                                                    const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode, T* svd_base) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     SvdPtr<T> sp = svd_at(svd_base, slot_s.get(), n_pad);
     // tight register cap + SVD store: run the (then cheap) forward particle math twice instead of keeping it across the gather
     t_p2g_bwd_g2p_bwd<T, kPlane, kSvd, (kSvd && kMinB >= 4)>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
@@ -836,3 +836,5 @@ template <class T> __global__ void k_count_active(long long n, const Vec4<T>* gr
 }
 
 }  // namespace plb
+
+#include "plb_tile.cuh"

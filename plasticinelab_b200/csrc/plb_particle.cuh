@@ -95,6 +95,15 @@ template <class T> PLB_HD void store_svd(const SvdPtr<T>& f, int p, const SvdRec
     f.q[4][p] = mk4<T>(r.U.m[2][2], r.V.m[2][2], r.sig.x, r.sig.y);
     f.s[p] = r.sig.z;
 }
+// V alone (3 of the 6 planes): warm start of the next substep's iteration
+template <class T> PLB_HD M3<T> load_svd_V(const SvdPtr<T>& f, int p) {
+    Vec4<T> c = f.q[2][p], d = f.q[3][p], e = f.q[4][p];
+    M3<T> V;
+    V.m[0][0] = c.x; V.m[0][1] = c.y; V.m[0][2] = c.z; V.m[1][0] = c.w;
+    V.m[1][1] = d.x; V.m[1][2] = d.y; V.m[2][0] = d.z; V.m[2][1] = d.w;
+    V.m[2][2] = e.y;
+    return V;
+}
 template <class T> PLB_HD SvdRec<T> load_svd(const SvdPtr<T>& f, int p) {
     Vec4<T> a = f.q[0][p], b = f.q[1][p], c = f.q[2][p], d = f.q[3][p], e = f.q[4][p];
     SvdRec<T> r;
@@ -109,10 +118,10 @@ template <class T> PLB_HD SvdRec<T> load_svd(const SvdPtr<T>& f, int p) {
 
 // Forward: returns new_F (= F[f+1]) and the APIC affine matrix (stress + p_mass C).
 // kSvdGiven: `svd` holds the decomposition of F_tmp (loaded from the store); otherwise it is computed and, if svd != nullptr,
-// returned through it.
+// returned through it.  warmV (optional, with !kSvdGiven): V of this particle's previous substep, starting point of the iteration.
 template <class T, bool kSvdGiven = false>
 PLB_HD void p2g_particle(const SimConst<T>& P, const M3<T>& C, const M3<T>& F, T mu, T lam, T ys,
-                         M3<T>& new_F, M3<T>& affine, P2GState<T>* keep = nullptr, SvdRec<T>* svd = nullptr) {
+                         M3<T>& new_F, M3<T>& affine, P2GState<T>* keep = nullptr, SvdRec<T>* svd = nullptr, const M3<T>* warmV = nullptr) {
     M3<T> A = identM<T>() + P.dt * C;
     M3<T> F_tmp = mm(A, F);
     M3<T> U, V;
@@ -120,16 +129,16 @@ PLB_HD void p2g_particle(const SimConst<T>& P, const M3<T>& C, const M3<T>& F, T
     if (kSvdGiven) {
         U = svd->U; V = svd->V; sig = svd->sig;
     } else {
-        svd3(F_tmp, U, sig, V);
+        svd3(F_tmp, U, sig, V, warmV);
         if (svd) { svd->U = U; svd->V = V; svd->sig = sig; }
     }
     // compute_von_mises
     V3<T> sc = mk3<T>(tmax(sig.x, T(0.05)), tmax(sig.y, T(0.05)), tmax(sig.z, T(0.05)));
     V3<T> eps = mk3<T>(plb_log(sc.x), plb_log(sc.y), plb_log(sc.z));
-    T mean = (eps.x + eps.y + eps.z) / T(3);
+    T mean = (eps.x + eps.y + eps.z) * T(1.0 / 3.0);
     V3<T> eh = mk3<T>(eps.x - mean, eps.y - mean, eps.z - mean);
     T n = plb_sqrt(dot(eh, eh) + T(1e-8));
-    T c = ys / (T(2) * mu);
+    T c = ys * plb_rcp_nr(T(2) * mu);
     T dgamma = n - c;
     bool yield = dgamma > T(0);
     V3<T> e = zero3<T>();

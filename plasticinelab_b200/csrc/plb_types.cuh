@@ -41,6 +41,7 @@ template <class T> PLB_HD V3<T> operator*(T s, V3<T> a) { return mk3<T>(s * a.x,
 template <class T> PLB_HD V3<T> operator*(V3<T> a, T s) { return mk3<T>(s * a.x, s * a.y, s * a.z); }
 template <class T> PLB_HD V3<T>& operator+=(V3<T>& a, V3<T> b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
 template <class T> PLB_HD V3<T>& operator-=(V3<T>& a, V3<T> b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; return a; }
+template <class T> PLB_HD V3<T> fma3(T s, V3<T> a, V3<T> c) { return mk3<T>(s * a.x + c.x, s * a.y + c.y, s * a.z + c.z); }   // s a + c
 template <class T> PLB_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 template <class T> PLB_HD V3<T> cross(V3<T> a, V3<T> b) {
     return mk3<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
@@ -183,6 +184,23 @@ PLB_HD float plb_rsqrt(float x) { float r = rsqrtf(x); return r * (1.5f - 0.5f *
 #else
 PLB_HD float plb_rcp(float x) { return 1.0f / x; }
 PLB_HD float plb_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
+
+// Raw MUFU approximations (float on the device, ~1e-7 relative, no special-case handling) for quantities whose error only
+// perturbs an iteration that corrects itself (the Jacobi rotation ANGLE: any angle close to the optimal one still converges,
+// the rotation itself is built from a refined c with s = c t, so it stays orthogonal to rounding), and a 2-instruction refined
+// reciprocal for the places that used an IEEE division of well-scaled positive values.  double / host: exact.
+PLB_HD double plb_rcp_fast(double x) { return 1.0 / x; }
+PLB_HD double plb_rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+PLB_HD double plb_rcp_nr(double x) { return 1.0 / x; }
+#if defined(__CUDA_ARCH__)
+PLB_HD float plb_rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+PLB_HD float plb_rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+PLB_HD float plb_rcp_nr(float x) { float r = plb_rcp_fast(x); return r * (2.0f - x * r); }       // <= 1 ulp for normal x
+#else
+PLB_HD float plb_rcp_fast(float x) { return 1.0f / x; }
+PLB_HD float plb_rsqrt_fast(float x) { return 1.0f / sqrtf(x); }
+PLB_HD float plb_rcp_nr(float x) { return 1.0f / x; }
 #endif
 
 // ti.max / ti.min value semantics and the gradient routing of Taichi's autodiff:

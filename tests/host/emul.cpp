@@ -245,5 +245,21 @@ void emul_svd(int dtype, const double* F9, double* U9, double* s3, double* V9) {
         s3[0] = s.x; s3[1] = s.y; s3[2] = s.z;
     }
 }
+// same with a starting V (the decomposition of a nearby matrix); returns nothing else
+void emul_svd_warm(int dtype, const double* F9, const double* W9, double* U9, double* s3, double* V9) {
+    if (dtype == PLB_F32) {
+        M3<float> F, U, V, W; V3<float> s;
+        for (int i = 0; i < 9; i++) { F.m[i / 3][i % 3] = (float)F9[i]; W.m[i / 3][i % 3] = (float)W9[i]; }
+        svd3(F, U, s, V, &W);
+        for (int i = 0; i < 9; i++) { U9[i] = U.m[i / 3][i % 3]; V9[i] = V.m[i / 3][i % 3]; }
+        s3[0] = s.x; s3[1] = s.y; s3[2] = s.z;
+    } else {
+        M3<double> F, U, V, W; V3<double> s;
+        for (int i = 0; i < 9; i++) { F.m[i / 3][i % 3] = F9[i]; W.m[i / 3][i % 3] = W9[i]; }
+        svd3(F, U, s, V, &W);
+        for (int i = 0; i < 9; i++) { U9[i] = U.m[i / 3][i % 3]; V9[i] = V.m[i / 3][i % 3]; }
+        s3[0] = s.x; s3[1] = s.y; s3[2] = s.z;
+    }
+}
 
 }  // extern "C"

@@ -17,8 +17,8 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("PLB_TEST_LARGE") == "0", reason="full-size cases switched off (PLB_TEST_LARGE=0)")]
 D = _capi.dptr
 KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE",
-        "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST"]
-CONSERVATIVE = dict(PLB_BWD_OVERLAP=0, PLB_GRID_BWD_V2=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_BWD_MINB=3)
+        "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST", "PLB_TILE"]
+CONSERVATIVE = dict(PLB_BWD_OVERLAP=0, PLB_GRID_BWD_V2=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_BWD_MINB=3, PLB_TILE=0)
 CASES = {      # name -> (scene file, particles, quality, env steps)
     "move1m_128": ("move.yml", 1_000_000, 2, 2),          # north-star roofline size
     "rope1m_256": ("rope.yml", 1_000_000, 4, 1),          # BASELINE config 3 (about 28 particles per cell)
@@ -68,6 +68,7 @@ def test_full_size_episode_properties_and_variant_agreement(monkeypatch, case):
     variants = {"defaults": {}}
     for name, env_vars in variants.items():
         loss, grad, _ = _episode(monkeypatch, case, env_vars)
+        H.record(f"large_variants[{case},{name}]", loss=abs(loss - ref_loss) / abs(ref_loss), grad=H.relerr(grad, ref_grad), grad_norm=np.linalg.norm(ref_grad))
         assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (name, loss, ref_loss)
         assert H.relerr(grad, ref_grad) < 5e-2, (name, H.relerr(grad, ref_grad))
 
@@ -85,9 +86,10 @@ def _move_cfg(n, quality, horizon):
 def test_config2_float32_against_float64_engine(monkeypatch):
     """BASELINE config 2 (Move-v1 geometry, 100k particles, 128^3), 5 env steps = 195 substeps under the tape: the float32
     production kernels against the float64 engine (itself 1e-9 from the float64 oracle, test_gpu_parity.py).  This is the
-    number bench.py reports as `parity`.  Tolerances = 3x what a B200 measured (profiles/r2_parity_measured.md):
-    loss 1e-5 relative, action gradient 2e-3 relative (north-star target 1e-4: see DESIGN.md 2 on float32 noise), final
-    positions 0.02 cells."""
+    number bench.py reports as `parity`.  Tolerances = 3x what a B200 measured (profiles/r2_parity_measured.md: loss 1.4e-8,
+    gradient 1.9e-3 of |grad| = 0.70, positions 3e-4 cells): loss 1e-6 relative, action gradient 6e-3 relative (the north-star
+    target of 1e-4 is met on the scenes with contact -- slab1m 2e-5, rope1m 1e-5 -- not on this one, whose tiny gradient is a
+    difference of large float32 terms), final positions 2e-3 cells."""
     from plasticinelab_b200.engine.taichi_env import TaichiEnv
     from plasticinelab_b200.optimizer.solver import Solver
     for k in KEYS:
@@ -109,9 +111,9 @@ def test_config2_float32_against_float64_engine(monkeypatch):
     el, eg, ex = abs(l32 - l64) / abs(l64), H.relerr(g32, g64), np.abs(x32 - x64).max() * ng
     H.record("config2_f32_vs_f64", loss=el, grad=eg, x_cells=ex, grad_norm=np.linalg.norm(g64))
     assert np.abs(g64).max() > 0
-    assert el < 1e-5, el
-    assert eg < 2e-3, eg
-    assert ex < 2e-2, ex
+    assert el < 1e-6, el
+    assert eg < 6e-3, eg
+    assert ex < 2e-3, ex
 
 
 def test_1m_float64_engine_against_c_port():

@@ -1,7 +1,9 @@
 """GPU parity tests (run with -m gpu on the B200 box): the CUDA engine, called through the C ABI, against the float64
 oracle on the same seeded inputs.  Tolerances are written next to each assert:
   float64 kernels: 1e-9 relative on one substep, 1e-6 on short episodes (different SVD algorithm / summation order);
-  float32 kernels: 2e-4 relative on one substep forward, 2e-3 on its adjoint, 1e-4 on the episode loss.
+  float32 kernels: about 5x what a B200 measured (profiles/r2_parity_measured.md; float atomics make the last digits vary
+  run to run): one substep 5e-5 forward and adjoint (measured <= 1e-5), pose gradients 5e-4 of their scale (<= 9e-5);
+  27-substep episode: loss 1e-6 (3e-9), action gradient 1e-4 (2e-5), final positions 2e-6 (3e-7).
 """
 import ctypes as C
 
@@ -68,7 +70,7 @@ def test_substep_parity(name, softness, gf, seed, dtype):
     pf, pf1 = H.oracle_prim_states(osim, pose0), H.oracle_prim_states(osim, pose1)
     ref = osim.substep(st, pf, pf1)
     o_adj, o_g0, o_g1 = osim.substep_vjp(st, pf, pf1, tuple(torch.as_tensor(a) for a in adj))
-    ftol, atol = (1e-9, 1e-7) if dtype == 'float64' else (2e-4, 3e-3)
+    ftol, atol = (1e-9, 1e-7) if dtype == 'float64' else (5e-5, 5e-5)
     H.record(f"substep[{name},{seed},{dtype}]", fwd=max(H.relerr(a, b.numpy()) for a, b in zip(out, ref)),
              adj=max(H.relerr(a, b.numpy()) for a, b in zip(gadj, o_adj)),
              pose=max([np.abs(gp[w, k, :p.state_dim] - g[k].numpy()).max() / max(np.abs(o_g0[k].numpy()).max(), np.abs(o_g1[k].numpy()).max(), 1e-12)
@@ -77,7 +79,7 @@ def test_substep_parity(name, softness, gf, seed, dtype):
         assert H.relerr(a, b.numpy()) < ftol
     for a, b in zip(gadj, o_adj):
         assert H.relerr(a, b.numpy()) < atol
-    ptol = 1e-6 if dtype == 'float64' else 2e-2
+    ptol = 1e-6 if dtype == 'float64' else 5e-4
     for k, p in enumerate(osim.prims):
         d = p.state_dim
         for w, ref_g in ((0, o_g0[k].numpy()), (1, o_g1[k].numpy())):
@@ -125,14 +127,14 @@ def test_episode_loss_and_action_gradient(dtype, contact_all):
     oenv = O.OracleEnv(cfg, env.init_particles, t32, target_sdf=O.build_target_sdf_c(t32, 1 / 32),
                        contact_grad='taichi' if contact_all else 'argmin')
     out = oenv.rollout(actions, softness=666.0)
-    ltol, gtol = (1e-9, 1e-6) if dtype == 'float64' else (1e-4, 5e-2)
+    ltol, gtol = (1e-9, 1e-6) if dtype == 'float64' else (1e-6, 1e-4)
     sim_state = env.simulator.get_state(env.simulator.cur)
     H.record(f"episode[{dtype},{contact_all}]", loss=abs(loss - out['loss']) / abs(out['loss']), grad=H.relerr(grad, out['grad']),
              x=np.abs(sim_state[0] - out['final_state'][0].numpy()).max())
     assert abs(loss - out['loss']) < ltol * abs(out['loss'])
     assert H.relerr(grad, out['grad']) < gtol
     # final particle state
-    xtol = 1e-10 if dtype == 'float64' else 1e-5
+    xtol = 1e-10 if dtype == 'float64' else 2e-6
     assert np.abs(sim_state[0] - out['final_state'][0].numpy()).max() < xtol
 
 

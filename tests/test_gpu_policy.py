@@ -39,5 +39,6 @@ def test_policy_episode_matches_oracle(dtype):
     oenv = O.OracleEnv(cfg, env.init_particles, t32, target_sdf=O.build_target_sdf_c(t32, 1 / 32), contact_grad='taichi')
     out = oenv.rollout_policy(params, 3, hidden=(16,), n_observed=30, softness=666.0)
     ltol, gtol = (1e-9, 1e-6) if dtype == 'float64' else (1e-4, 5e-2)
+    H.record(f"policy[{dtype}]", loss=abs(loss - out['loss']) / abs(out['loss']), grad=H.relerr(grad, out['grad']))
     assert abs(loss - out['loss']) < ltol * abs(out['loss'])
     assert H.relerr(grad, out['grad']) < gtol

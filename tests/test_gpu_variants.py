@@ -4,8 +4,8 @@ The variants are chosen with environment switches read at plb_create (plb_engine
 (full 27-node tile / 9-node plane tile), register caps of the fused particle kernels, CTA size, the one-kernel forward grid
 stage and the forked grid pre-stage of the backward graphs.  The conservative configuration (everything serial, full tiles)
 is compared against the float64 oracle by tests/test_gpu_parity.py; here all other variants are compared with it on the
-same episode, in one process.  Tolerances: float64 1e-10 on the loss, 1e-7 on the gradient (summation order only), float32 1e-4 on the loss,
-2e-2 on the gradient (float32 summation-order noise through 27 substeps of contact dynamics).
+same episode, in one process.  Tolerances: float64 1e-10 on the loss, 1e-7 on the gradient (summation order only); float32 1e-6 on the loss,
+2e-5 on the gradient, 2e-6 on positions (about 10x what a B200 measured: <= 5e-9, 1.8e-6, 1.8e-7, gpurun_out/ab/pytest_variants.log).
 """
 import os
 
@@ -17,10 +17,10 @@ from test_gpu_parity import _episode_cfg, _target32
 
 pytestmark = pytest.mark.gpu
 
-KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST"]
+KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST", "PLB_TILE"]
 VARIANTS = {
     "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3,
-                         PLB_GRID_BWD_V2=0, PLB_FLUSH_RUNS=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0),
+                         PLB_GRID_BWD_V2=0, PLB_FLUSH_RUNS=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_TILE=0),
     "defaults": {},
     "overlap": dict(PLB_BWD_OVERLAP=1),
     "scan": dict(PLB_GRID_SCAN=1),
@@ -41,6 +41,10 @@ VARIANTS.update({
     "svd_store_loose": dict(PLB_SVD_STORE=1, PLB_BWD_MINB=3),
     "flush_pairs": dict(PLB_FLUSH_PAIRS=1),
     "substep_list": dict(PLB_ENV_LIST=0),
+    # chunked TMA-window kernels (plb_tile.cuh) are the default since round 2; PLB_TILE=0 = the per-thread-gather kernels
+    "no_tile": dict(PLB_TILE=0),
+    "tile_no_svd_store": dict(PLB_SVD_STORE=0, PLB_BWD_MINB=3),
+    "tile_serial_bwd": dict(PLB_BWD_OVERLAP=0),
     "substep_list_no_svd_pairs": dict(PLB_ENV_LIST=0, PLB_SVD_STORE=0, PLB_BWD_MINB=3, PLB_FLUSH_PAIRS=1),
 })
 
@@ -69,7 +73,7 @@ def _run(monkeypatch, env_vars, dtype):
 @pytest.mark.parametrize('dtype', ['float64', 'float32'])
 def test_kernel_variants_agree(monkeypatch, dtype):
     ref = _run(monkeypatch, VARIANTS["conservative"], dtype)
-    ltol, gtol, xtol = (1e-10, 1e-7, 1e-10) if dtype == 'float64' else (1e-4, 2e-2, 1e-5)
+    ltol, gtol, xtol = (1e-10, 1e-7, 1e-10) if dtype == 'float64' else (1e-6, 2e-5, 2e-6)
     bad = []
     for name, env_vars in VARIANTS.items():
         if name == "conservative":

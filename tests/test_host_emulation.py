@@ -138,6 +138,30 @@ def test_svd_convention_and_accuracy(emul_lib):
             assert np.sign(s[2]) == np.sign(np.linalg.det(F)) or abs(np.linalg.det(F)) < 1e-6
 
 
+def test_svd_warm_start_chain_stays_accurate(emul_lib):
+    """Warm-started Jacobi (V of the previous substep as the starting point, plb_svd.cuh): a chain of 2000 slowly drifting
+    matrices, each decomposition started from the previous V, stays an SVD to working precision (V is re-orthonormalised at
+    every start, so nothing accumulates), keeps the convention, and U V^T / U S V^T agree with the cold start."""
+    rng = np.random.RandomState(8)
+    for dtype, tol in ((_capi.PLB_F64, 1e-13), (_capi.PLB_F32, 3e-6)):
+        F = np.eye(3) + 0.2 * rng.randn(3, 3)
+        U, s, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        emul_lib.emul_svd(dtype, D(np.ascontiguousarray(F)), D(U), D(s), D(V))
+        for i in range(2000):
+            F = (np.eye(3) + 2e-3 * rng.randn(3, 3)) @ F
+            if i == 1000:
+                F = np.eye(3) + 1e-9 * rng.randn(3, 3)          # (nearly) degenerate: any V is a valid start
+            W = V.copy()
+            emul_lib.emul_svd_warm(dtype, D(np.ascontiguousarray(F)), D(W), D(U), D(s), D(V))
+            assert abs(np.linalg.det(U) - 1) < 10 * tol and abs(np.linalg.det(V) - 1) < 10 * tol
+            assert np.abs(V.T @ V - np.eye(3)).max() < 10 * tol and np.abs(U.T @ U - np.eye(3)).max() < 10 * tol
+            assert np.abs(U @ np.diag(s) @ V.T - F).max() < tol * max(1.0, np.abs(F).max()) * 10
+            assert s[0] >= s[1] >= abs(s[2]) - 10 * tol
+        Uc, sc, Vc = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        emul_lib.emul_svd(dtype, D(np.ascontiguousarray(F)), D(Uc), D(sc), D(Vc))
+        assert np.abs(U @ V.T - Uc @ Vc.T).max() < 100 * tol and np.abs(s - sc).max() < 100 * tol
+
+
 @pytest.mark.parametrize('fscale,ys', [(0.004, 30.0), (0.1, 1e9), (0.0, 50.0)])
 def test_substep_adjoint_mixed_and_elastic_f64(emul_lib, fscale, ys):
     """Return-mapping branch coverage: ~half of the particles yield / none yield / exactly F = I (degenerate SVD)."""
