@@ -191,7 +191,8 @@ PLB_HD void grid_fwd_body(long long node, const SimConst<T>& P, const PrimSet<T>
                           Vec4<T>* grid_in, Vec4<T>* grid_out, bool clear_in) {
     Vec4<T> in4 = grid_in[node];
     const int n = P.n_grid;
-    int k = (int)(node % n), j = (int)((node / n) % n), i = (int)(node / ((long long)n * n));
+    const unsigned un = (unsigned)node, nn = (unsigned)n, row = un / nn;        // n_grid <= 1024: node < 2^30, 32-bit divisions
+    int k = (int)(un - row * nn), i = (int)(row / nn), j = (int)(row - (unsigned)i * nn);
     V3<T> v = grid_node_forward<T>(P, prims, s0, s1, i, j, k, in4);
     grid_out[node] = mk4<T>(v.x, v.y, v.z, T(0));
     if (clear_in && (in4.x != T(0) || in4.y != T(0) || in4.z != T(0) || in4.w != T(0)))
@@ -458,7 +459,8 @@ PLB_HD void grid_bwd_body(long long node, const SimConst<T>& P, const PrimSet<T>
     Vec4<T> in4 = grid_in[node];
     Vec4<T> go = g_out[node];
     const int n = P.n_grid;
-    int k = (int)(node % n), j = (int)((node / n) % n), i = (int)(node / ((long long)n * n));
+    const unsigned un = (unsigned)node, nn = (unsigned)n, row = un / nn;        // n_grid <= 1024: node < 2^30, 32-bit divisions
+    int k = (int)(un - row * nn), i = (int)(row / nn), j = (int)(row - (unsigned)i * nn);
     Vec4<T> gi = grid_node_backward<T>(P, prims, s0, s1, i, j, k, in4, mk3<T>(go.x, go.y, go.z), g0, g1, touched);
     g_in[node] = gi;
     if (clear) {

@@ -184,7 +184,8 @@ struct Engine : plb_engine {
                   void* recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
                   // peer-memory halo: my inboxes (neighbours write here), the neighbours' inboxes mapped through CUDA IPC
                   char* inbox[2] = {nullptr, nullptr}; char* peer[2] = {nullptr, nullptr}; HaloGeom geom[2]; size_t inbox_bytes = 0;
-                  int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; bool peer_ready = false; bool exported = false, ipc_closed = false; } slab;
+                  int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; unsigned* done = nullptr; bool peer_ready = false; bool exported = false, ipc_closed = false;
+                  bool fused = true; } slab;      // fused: env-step block list + one push launch per exchange, receive inside the grid kernels (PLB_SLAB_FUSED=0: the per-substep chain)
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     bool fuse = true;               // fused G2P+P2G / P2G.grad+G2P.grad particle kernels inside env-step graphs (PLB_FUSE=0 disables)
     bool fwd_plane = false;         // plane (9-node) tile in the forward scatter kernels: 1/3 shared memory (PLB_FWD_PLANE)
@@ -257,7 +258,7 @@ struct Engine : plb_engine {
             if (!slab.peer[side] && (slab.ipc_closed || !slab.exported)) cudaFree(slab.inbox[side]);
             for (int which = 0; which < 3; which++) cudaFree(slab.recv[which][side]);
         }
-        cudaFree(slab.seq); cudaFree(slab.err); cudaFree(slab.listed_stamp);
+        cudaFree(slab.seq); cudaFree(slab.err); cudaFree(slab.listed_stamp); cudaFree(slab.done);
         for (cudaEvent_t e : cap_events) cudaEventDestroy(e);
         if (side_stream) cudaStreamDestroy(side_stream);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -403,6 +404,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_TILE")) tile_mode = atoi(v) != 0;
         if (const char* v = getenv("PLB_SVD_WARM")) svd_warm = atoi(v) != 0;
         if (const char* v = getenv("PLB_TILE_BWD")) tile_bwd = atoi(v) != 0;
+        if (const char* v = getenv("PLB_SLAB_FUSED")) slab.fused = atoi(v) != 0;
         if (const char* v = getenv("PLB_TILE_FWD_MINB")) tile_fwd_minb = atoi(v);
         tile_mode = tile_mode && tile_scatter && sparse && fuse;
         tile_bwd = tile_bwd && tile_mode;
@@ -595,6 +597,7 @@ struct Engine : plb_engine {
             int cnt = 0;
             PLB_CUDA(cudaMemcpyAsync(&cnt, d_nactive, sizeof(int), cudaMemcpyDeviceToHost, stream));
             PLB_CUDA(cudaStreamSynchronize(stream));
+            listed_est = cnt;
             int want = std::min(n_blocks, (env_list ? cnt + cnt / 2 : 2 * cnt) + 256);
             if (want > store.cap) {
                 cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt);
@@ -691,7 +694,16 @@ struct Engine : plb_engine {
     }
 
     // ---------------------------------------------------------------- substeps
-    int sparse_ctas() const { return std::min(std::max(n_blocks / 2, 1), 148 * 8); }
+    // CTAs of the list-driven grid kernels (2 blocks of 64 nodes per CTA and round).  These kernels are latency chains over a few
+    // hundred to a few thousand blocks: n_blocks / 2 CTAs (1184 at 128^3) made the 96-register grid adjoint run in two waves
+    // with the SMs idle half of its 14 us (ncu at move100k, profiles/r2_grid_kernels_ncu_summary.md), so the launch is sized from
+    // the block count seen at the last sort (1.25x margin, whole multiples of the 148 SMs) and capped at one wave.
+    int listed_est = 0;
+    int sparse_ctas(int wave_cap = 148 * 8) const {
+        if (listed_est <= 0) return std::min(std::max(n_blocks / 2, 1), wave_cap);
+        const int want = (listed_est + listed_est / 4 + 1) / 2;
+        return std::min(std::max((want + 147) / 148 * 148, 148), wave_cap);
+    }
     int scan_ctas() const { return std::min(std::max((n_blocks + kBlock - 1) / kBlock, 1), 148 * 8); }
     // forward grid stage as one kernel (k_grid_fwd_scan): single GPU, forward-grid store present, per-CTA list capacity suffices
     bool scan_mode() const {
@@ -706,12 +718,33 @@ struct Engine : plb_engine {
     // (absolute indices) and graph capture (cursor-relative indices).
     // grid stage of a forward substep: (halo) + active-block list + grid operator (+ store of the forward grid for slot `si`)
     // forward graphs in env-list mode: single GPU, forward-grid store present
-    bool env_list_mode() const { return env_list && sparse && tile_scatter && store.vals && !slab.on; }
+    bool slab_fused() const { return slab.peer_ready && slab.fused && env_list && store.vals; }
+    bool env_list_mode() const { return env_list && sparse && tile_scatter && store.vals && (!slab.on || slab_fused()); }
+    HaloIn halo_in(bool on) const {
+        HaloIn h;
+        for (int side = 0; side < 2; side++) { h.inbox[side] = (on && slab.has[side]) ? slab.inbox[side] : nullptr; h.g[side] = slab.geom[side]; }
+        h.seq = slab.seq; h.err = slab.err; h.on = on ? 1 : 0;
+        return h;
+    }
+    // one launch: my listed zone blocks of `grid` -> both neighbours' inboxes, published by the last CTA (k_halo_push2)
+    void halo_push_fused(const Vec4<T>* grid, const int* list, const int* count) {
+        k_halo_push2<T><<<148, kBlock, 0, stream>>>(cfg.n_grid, grid, list, count, slab.has[0] ? slab.peer[0] : nullptr, slab.has[1] ? slab.peer[1] : nullptr,
+                                                    slab.geom[0], slab.geom[1], slab.seq, slab.done);
+        launches++;
+    }
     // list of the env step that starts at frame `slot`: blocks touched by that frame, dilated by one block
     void enqueue_env_list(SlotRef slot) {
         const int nbx = cfg.n_grid / 4, nb = (n_blocks + 255) / 256;
         cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
         k_mark_slot<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, d_flags);
+        if (slab_fused()) {
+            // the neighbours' particles scatter into the zones too: exchange the zone flags once per env step, so that both sides
+            // list (and push / receive) the same zone blocks for all of its substeps
+            k_halo_push_flags<<<32, 256, 0, stream>>>(cfg.n_grid, d_flags, slab.has[0] ? slab.peer[0] : nullptr, slab.has[1] ? slab.peer[1] : nullptr,
+                                                      slab.geom[0], slab.geom[1], slab.seq, slab.done);
+            k_halo_or_flags<<<32, 256, 0, stream>>>(cfg.n_grid, d_flags, halo_in(true));
+            launches += 2;
+        }
         k_dilate_flags<<<nb, 256, 0, stream>>>(nbx, d_flags, d_flags2);
         k_compact_mark<<<nb, 256, 0, stream>>>(n_blocks, d_flags2, d_list, d_nactive, d_listed);
         launches += 3;
@@ -721,12 +754,24 @@ struct Engine : plb_engine {
         k_mark_slot<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, d_flags);
         k_check_listed<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags, d_listed, store.overflow);
         launches += 2;
+        if (slab.on && slab.err) {       // ownership is fixed for the episode (no migration): the material must stay within owned planes + halo
+            k_check_margin<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, slab.has[0] ? slab.own_lo - slab.w : 0,
+                                                                          slab.has[1] ? slab.own_hi + slab.w : cfg.n_grid, slab.err);
+            launches++;
+        }
     }
     void enqueue_grid_fwd_stage(SlotRef si, SlotRef pf, bool fixed_list = false) {
         prof_begin(K_GRID_FWD);
         if (sparse) {
             if (fixed_list) {
                 // (the list in d_list / d_nactive was built by enqueue_env_list for the whole env step)
+                if (slab_fused()) {
+                    halo_push_fused(grid_in, d_list, d_nactive);
+                    k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si, halo_in(true));
+                    prof_end();
+                    launches++;
+                    return;
+                }
             } else if (slab.peer_ready) {
                 k_halo_next_seq<<<1, 1, 0, stream>>>(slab.seq);
                 cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
@@ -747,7 +792,7 @@ struct Engine : plb_engine {
             } else {
                 compact_blocks();
             }
-            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si);
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si, halo_in(false));
         } else {
             k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
         }
@@ -830,7 +875,7 @@ struct Engine : plb_engine {
         }
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE, st);
         if (sparse)
-            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, gs.list, gs.count, nostore, si);
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, gs.list, gs.count, nostore, si, halo_in(false));
         else
             k_grid_fwd<T><<<ng, kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, n_nodes);
         prof_end();
@@ -839,6 +884,13 @@ struct Engine : plb_engine {
     void enqueue_bwd_grid_adj(SlotRef pf, const GridSet& gs) {               // (halo of g_out) + grid_op.grad
         const int ng = blocks(n_nodes);
         prof_begin(K_GRID_BWD);
+        if (slab_fused() && sparse && grid_bwd_v2) {
+            halo_push_fused(g_out, gs.list, gs.count);
+            k_grid_bwd_sparse_v2<T><<<sparse_ctas(148 * 5), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(true));
+            prof_end();
+            launches++;
+            return;
+        }
         if (slab.peer_ready) {
             k_halo_next_seq<<<1, 1, 0, stream>>>(slab.seq);
             halo_exchange(g_out);
@@ -846,7 +898,7 @@ struct Engine : plb_engine {
             launches += 6;
         }
         if (sparse && grid_bwd_v2 && !slab.on)         // (slab runs keep the array form: the register form was validated on one GPU only)
-            k_grid_bwd_sparse_v2<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());
+            k_grid_bwd_sparse_v2<T><<<sparse_ctas(148 * 5), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(false));
         else if (sparse)
             k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());
         else
@@ -1032,7 +1084,7 @@ struct Engine : plb_engine {
             else for (int i = 0; i < key.n; i++) enqueue_fwd(cur_ref(0, i), cur_ref(1, i), cur_ref(2, i));
         } else {
             int c = key.parity;
-            if (fused) enqueue_bwd_fused(key.n, restore, next_ok, svd, c, &Engine::mk_cursor, bwd_overlap && restore && !slab.on);
+            if (fused) enqueue_bwd_fused(key.n, restore, next_ok, svd, c, &Engine::mk_cursor, bwd_overlap && restore && (!slab.on || slab_fused()));
             else for (int i = key.n - 1; i >= 0; i--) { enqueue_bwd(cur_ref(0, i), cur_ref(2, i), restore, next_ok, svd, adj[c], adj[c ^ 1]); c ^= 1; }
         }
     }
@@ -1170,7 +1222,7 @@ struct Engine : plb_engine {
             }
         compact_blocks();
         halo_add(grid_in, 0);
-        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 1, d_list, d_nactive, store, abs_ref(si));
+        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 1, d_list, d_nactive, store, abs_ref(si), halo_in(false));
         prof_end(); prof_begin(K_G2P);
         k_g2p<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(si), abs_ref(so), grid_out);
         prof_end();
@@ -1188,7 +1240,7 @@ struct Engine : plb_engine {
         prof_begin(K_P2G_RECOMPUTE);
         k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid_in, d_list, d_nactive, store, abs_ref(si));
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
-        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 0, d_list, d_nactive, nostore, abs_ref(si));
+        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 0, d_list, d_nactive, nostore, abs_ref(si), halo_in(false));
         prof_end();
         launch_g2p_bwd(abs_ref(si), adj[cur], adj[cur ^ 1], sets[0], fwd_ok[si] != 0);
         launches += 2;
@@ -1262,7 +1314,8 @@ struct Engine : plb_engine {
             g.nzb = (2 * slab.w / 4) * nbx * nbx;
             g.stamps_off = 256;
             g.data_off = (256 + 2LL * g.nzb * (long long)sizeof(int) + 255) / 256 * 256;
-            slab.inbox_bytes = (size_t)g.data_off + 2ULL * g.nzb * kBlkNodes * sizeof(Vec4<T>);
+            g.flags_off = g.data_off + 2LL * g.nzb * kBlkNodes * (long long)sizeof(Vec4<T>);
+            slab.inbox_bytes = (size_t)g.flags_off + 2ULL * g.nzb;
             if (!slab.has[side]) continue;
             PLB_CUDA(cudaMalloc(&slab.inbox[side], slab.inbox_bytes));
             PLB_CUDA(cudaMemset(slab.inbox[side], 0, 256));
@@ -1272,6 +1325,8 @@ struct Engine : plb_engine {
         PLB_CUDA(cudaMemset(slab.seq, 0, sizeof(int)));
         PLB_CUDA(cudaMalloc(&slab.err, sizeof(int)));
         PLB_CUDA(cudaMemset(slab.err, 0, sizeof(int)));
+        PLB_CUDA(cudaMalloc(&slab.done, sizeof(unsigned)));
+        PLB_CUDA(cudaMemset(slab.done, 0, sizeof(unsigned)));
         PLB_CUDA(cudaMalloc(&slab.listed_stamp, n_blocks * sizeof(int)));
         PLB_CUDA(cudaMemset(slab.listed_stamp, 0xFF, n_blocks * sizeof(int)));
         return PLB_OK;
@@ -1360,6 +1415,12 @@ struct Engine : plb_engine {
         if (slab.err) {
             int he = 0;
             PLB_CUDA(cudaMemcpy(&he, slab.err, sizeof(int), cudaMemcpyDeviceToHost));
+            if (he == 2) {
+                cudaMemset(slab.err, 0, sizeof(int));
+                err = "slab decomposition: a particle's stencil left this rank's owned planes + halo (particles do not migrate between slabs "
+                      "inside an episode); results of this episode are invalid -- re-partition from the current state or use wider halos";
+                return PLB_ERR_INVALID;
+            }
             if (he) { cudaMemset(slab.err, 0, sizeof(int)); err = "slab halo: timed out waiting for a neighbour's push"; return PLB_ERR_CUDA; }
         }
         if (ov == 2) {

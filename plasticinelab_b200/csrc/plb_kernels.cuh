@@ -31,7 +31,7 @@ template <class T> struct GridStore {
 template <class T>
 __device__ __forceinline__ void load_poses_smem(const double* __restrict__ traj, int pf, int n_prim, Pose<T>* s0, Pose<T>* s1) {
     if (threadIdx.x < 2 * n_prim) {
-        int which = threadIdx.x / n_prim, k = threadIdx.x % n_prim;
+        int which = threadIdx.x >= n_prim ? 1 : 0, k = threadIdx.x - which * n_prim;
         const double* src = traj + ((long long)(pf + which) * PLB_MAX_PRIM + k) * PLB_POSE_DIM;
         Pose<T> p = load_pose<T>(src);
         if (which == 0) s0[k] = p; else s1[k] = p;
@@ -93,6 +93,15 @@ __global__ void k_mark_slot(SimConst<T> P, T* frames, long long n_pad, SlotRef s
     if (p < P.n_particles) mark_blocks<T>(P, load_x(frame_at(frames, slot.get(), n_pad), p), flags);
 }
 // out[b'] = 1 for the 27 neighbours b' of every flagged block b; clears in[b]
+// slab runs: every stencil of this rank's particles must stay inside [lo, hi) planes (owned planes + halo); *err = 2 otherwise
+template <class T>
+__global__ void k_check_margin(SimConst<T> P, T* frames, long long n_pad, SlotRef slot, int lo, int hi, int* err) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_particles) return;
+    const V3<T> x = load_x(frame_at(frames, slot.get(), n_pad), p);
+    const int b = (int)(x.x * P.inv_dx - T(0.5));
+    if (b < lo || b + 2 >= hi) *err = 2;
+}
 __global__ void k_dilate_flags(int nbx, unsigned char* in, unsigned char* out) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbx * nbx * nbx || !in[b]) return;
@@ -177,7 +186,56 @@ __global__ void __launch_bounds__(kBlock) k_halo_add_listed(int n_grid, Vec4<T>*
 //   int stamps[2][zone_blocks]        per parity: sequence number at which the block's data were pushed
 //   Vec4 data[2][zone_blocks][64]     per parity: the block's 64 node values (block-major, same order as the store)
 // A push writes only the sender's ACTIVE blocks inside the zone; the receiver trusts a block iff its stamp == seq.
-struct HaloGeom { int zone_lo, zone_hi, nzb; long long stamps_off, data_off; };   // offsets in bytes from the inbox base
+//   uchar zflags[2][zone_blocks]      per parity: the sender's block flags of the zone (env-step list exchange)
+struct HaloGeom { int zone_lo, zone_hi, nzb; long long stamps_off, data_off, flags_off; };   // offsets in bytes from the inbox base
+
+// What a grid kernel needs to take the neighbours' partial sums itself (fused receive): my two inboxes, their geometry, the
+// exchange counter.  on == 0: no halo (single GPU, or the stage reads an already summed grid).
+struct HaloIn { const char* inbox[2]; HaloGeom g[2]; const int* seq; int* err; int on; };
+__device__ __forceinline__ HaloIn halo_none() { HaloIn h; h.inbox[0] = h.inbox[1] = nullptr; h.seq = nullptr; h.err = nullptr; h.on = 0; return h; }
+
+// thread 0 of the CTA spins until both neighbours have published exchange `s` in MY inboxes (local memory: the neighbour wrote
+// it over NVLink), then the CTA may read what they pushed.  ~4 s timeout -> *err = 1 (reported by the next readback).
+__device__ __forceinline__ int halo_wait_cta(const HaloIn& h) {
+    const int s = *h.seq;
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int side = 0; side < 2; side++) {
+            if (!h.inbox[side]) continue;
+            const volatile int* f = reinterpret_cast<const volatile int*>(h.inbox[side]);
+            while (f[0] < s) {
+                if (clock64() - t0 > 8000000000LL) { *h.err = 1; break; }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    return s;
+}
+// the neighbours' contribution to node `local` of listed block `blk` in exchange s (zero if the block is outside the zones or
+// was not pushed); inbox data bypass L1 (the same addresses held the exchange before last)
+template <class T>
+__device__ __forceinline__ bool halo_fetch(const HaloIn& h, int n_grid, int blk, int local, int s, Vec4<T>& out) {
+    const int nbx = n_grid >> kBlkShift;
+    const int i0 = (blk / (nbx * nbx)) << kBlkShift;
+    bool any = false;
+    out = mk4<T>(T(0), T(0), T(0), T(0));
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        if (!h.inbox[side]) continue;
+        const HaloGeom& g = h.g[side];
+        if (i0 < g.zone_lo || i0 + 4 > g.zone_hi) continue;
+        const int zb = (i0 - g.zone_lo) / 4 * nbx * nbx + blk % (nbx * nbx);
+        const int par = s & 1;
+        const int* stamps = reinterpret_cast<const int*>(h.inbox[side] + g.stamps_off) + (long long)par * g.nzb;
+        if (__ldcg(stamps + zb) != s) continue;
+        const Vec4<T>* data = reinterpret_cast<const Vec4<T>*>(h.inbox[side] + g.data_off) + ((long long)par * g.nzb + zb) * kBlkNodes;
+        const T* q = reinterpret_cast<const T*>(data + local);
+        out.x += __ldcg(q); out.y += __ldcg(q + 1); out.z += __ldcg(q + 2); out.w += __ldcg(q + 3);
+        any = true;
+    }
+    return any;
+}
 
 __device__ __forceinline__ int zone_block_index(int n_grid, int blk, int zone_lo) {
     const int nbx = n_grid >> kBlkShift;
@@ -225,6 +283,76 @@ __global__ void k_halo_wait(const char* inbox0, const char* inbox1, const int* s
     __threadfence_system();
 }
 __global__ void k_halo_next_seq(int* seq_ptr) { *seq_ptr += 1; }
+
+// ---- fused halo (slab runs with the env-step block list): ONE launch per exchange on the sending side, none on the receiving
+// side (the grid kernel that consumes the data waits for it itself, halo_wait_cta / halo_fetch).
+// Exchange number s = *seq + 1.  Every CTA copies its share of my listed zone blocks into the neighbours' inboxes (parity
+// s & 1) and stamps them; every thread fences its stores; the LAST CTA to finish publishes s in both neighbours' flags and
+// stores it to *seq (the consumer kernel launched next reads it there).
+__device__ __forceinline__ void halo_publish_last_cta(char* peer0, char* peer1, int* seq_ptr, unsigned* done, int s) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(done, 1u);
+        if (t == gridDim.x - 1) {
+            *done = 0u;
+            __threadfence_system();
+            if (peer0) { volatile int* f = reinterpret_cast<volatile int*>(peer0); f[0] = s; }
+            if (peer1) { volatile int* f = reinterpret_cast<volatile int*>(peer1); f[0] = s; }
+            __threadfence_system();
+            *seq_ptr = s;
+        }
+    }
+}
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_halo_push2(int n_grid, const Vec4<T>* __restrict__ grid, const int* __restrict__ list,
+                                                       const int* __restrict__ count, char* peer0, char* peer1, HaloGeom g0, HaloGeom g1,
+                                                       int* seq_ptr, unsigned* done) {
+    const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1), n = *count, s = *seq_ptr + 1, par = s & 1;
+    const int nbx = n_grid >> kBlkShift;
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
+        const int blk = list[e];
+        const int i0 = (blk / (nbx * nbx)) << kBlkShift;
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            char* peer = side == 0 ? peer0 : peer1;
+            const HaloGeom& g = side == 0 ? g0 : g1;
+            if (!peer || i0 < g.zone_lo || i0 + 4 > g.zone_hi) continue;
+            const int zb = zone_block_index(n_grid, blk, g.zone_lo);
+            int* stamps = reinterpret_cast<int*>(peer + g.stamps_off) + (long long)par * g.nzb;
+            Vec4<T>* data = reinterpret_cast<Vec4<T>*>(peer + g.data_off) + (long long)par * g.nzb * kBlkNodes;
+            data[(long long)zb * kBlkNodes + local] = grid[block_node(n_grid, blk, local)];
+            if (local == 0) stamps[zb] = s;
+        }
+    }
+    halo_publish_last_cta(peer0, peer1, seq_ptr, done, s);
+}
+// env-step list exchange: my block flags inside the zones -> the neighbours' inboxes (one byte per zone block), published like a push
+__global__ void k_halo_push_flags(int n_grid, const unsigned char* __restrict__ flags, char* peer0, char* peer1, HaloGeom g0, HaloGeom g1,
+                                  int* seq_ptr, unsigned* done) {
+    const int s = *seq_ptr + 1, par = s & 1, nbx = n_grid >> kBlkShift;
+    for (int side = 0; side < 2; side++) {
+        char* peer = side == 0 ? peer0 : peer1;
+        const HaloGeom& g = side == 0 ? g0 : g1;
+        if (!peer) continue;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(peer + g.flags_off) + (long long)par * g.nzb;
+        const int first = (g.zone_lo >> kBlkShift) * nbx * nbx;
+        for (int zb = blockIdx.x * blockDim.x + threadIdx.x; zb < g.nzb; zb += gridDim.x * blockDim.x) dst[zb] = flags[first + zb];
+    }
+    halo_publish_last_cta(peer0, peer1, seq_ptr, done, s);
+}
+// ... and OR what the neighbours sent into my flags (whole zones: the list is dilated afterwards, also across the ownership boundary)
+__global__ void k_halo_or_flags(int n_grid, unsigned char* flags, HaloIn h) {
+    const int s = halo_wait_cta(h), par = s & 1, nbx = n_grid >> kBlkShift;
+    for (int side = 0; side < 2; side++) {
+        if (!h.inbox[side]) continue;
+        const HaloGeom& g = h.g[side];
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(h.inbox[side] + g.flags_off) + (long long)par * g.nzb;
+        const int first = (g.zone_lo >> kBlkShift) * nbx * nbx;
+        for (int zb = blockIdx.x * blockDim.x + threadIdx.x; zb < g.nzb; zb += gridDim.x * blockDim.x)
+            if (__ldcg(src + zb)) flags[first + zb] = 1;
+    }
+}
 
 // receiver, forward only: blocks of the zone in MY owned planes that the neighbour pushed but I do not list yet are
 // appended to my list (the owner of a plane accumulates its nodes' pose gradients)
@@ -355,11 +483,12 @@ template <class T>
 __global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pf,
                                                             Vec4<T>* grid_in, Vec4<T>* grid_out, int clear_in,
                                                             const int* __restrict__ list, const int* __restrict__ count,
-                                                            GridStore<T> store, SlotRef slot) {
+                                                            GridStore<T> store, SlotRef slot, HaloIn halo) {
     __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
     load_poses_smem<T>(traj, pf.get(), P.n_prim, s0, s1);
     const int per_cta = kBlock / kBlkNodes, n = *count;
     const int local = threadIdx.x & (kBlkNodes - 1);
+    const int hs = halo.on ? halo_wait_cta(halo) : 0;          // fused receive: the neighbours' partial sums of this exchange
     Vec4<T>* svals = nullptr; int* sids = nullptr;
     if (store.vals) {
         const long long sl = slot.get();
@@ -373,6 +502,13 @@ __global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimS
     for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
         const int blk = list[e];
         const long long node = block_node(P.n_grid, blk, local);
+        if (halo.on) {
+            Vec4<T> r;
+            if (halo_fetch<T>(halo, P.n_grid, blk, local, hs, r)) {
+                const Vec4<T> v = grid_in[node];
+                grid_in[node] = mk4<T>(v.x + r.x, v.y + r.y, v.z + r.z, v.w + r.w);
+            }
+        }
         if (svals && e < store.cap) {
             svals[(long long)e * kBlkNodes + local] = grid_in[node];
             if (local == 0) sids[e] = blk;
@@ -485,21 +621,30 @@ template <class T>
 __global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse_v2(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pfr,
                                                                Vec4<T>* grid_in, Vec4<T>* g_out, Vec4<T>* g_in, int clear,
                                                                double* prim_grad, const int* __restrict__ list,
-                                                               const int* __restrict__ count, int own_lo, int own_hi) {
+                                                               const int* __restrict__ count, int own_lo, int own_hi, HaloIn halo) {
     __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
     const int pf = pfr.get();
     load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
     const int per_cta = kBlock / kBlkNodes, n = *count;
     const int rounds = (n + gridDim.x * per_cta - 1) / (gridDim.x * per_cta);
+    const int hs = halo.on ? halo_wait_cta(halo) : 0;          // fused receive of the neighbours' adjoint of grid_out
     for (int r = 0; r < rounds; r++) {              // uniform trip count: warp collectives inside
         const int e = (r * gridDim.x + blockIdx.x) * per_cta + threadIdx.x / kBlkNodes;
         const bool act = e < n;
         long long node = 0;
         bool owned = false;
         if (act) {
-            node = block_node(P.n_grid, list[e], threadIdx.x & (kBlkNodes - 1));
+            const int blk = list[e], local = threadIdx.x & (kBlkNodes - 1);
+            node = block_node(P.n_grid, blk, local);
             const int plane = (int)(node / ((long long)P.n_grid * P.n_grid));
             owned = plane >= own_lo && plane < own_hi;
+            if (halo.on) {
+                Vec4<T> q;
+                if (halo_fetch<T>(halo, P.n_grid, blk, local, hs, q)) {
+                    const Vec4<T> v = g_out[node];
+                    g_out[node] = mk4<T>(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+                }
+            }
         }
         t_grid_bwd_node<T>(act, owned, node, threadIdx.x & 31, P, prims, s0, s1, grid_in, g_out, g_in, clear != 0, prim_grad, pf);
     }
@@ -689,7 +834,8 @@ __global__ void __launch_bounds__(128) k_sdf_sweep(int n, double dx, const doubl
     long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)n * n * n;
     if (node >= total) return;
-    int k = (int)(node % n), j = (int)((node / n) % n), i = (int)(node / ((long long)n * n));
+    const unsigned un = (unsigned)node, nn = (unsigned)n, row = un / nn;        // n_grid <= 1024: node < 2^30, 32-bit divisions
+    int k = (int)(un - row * nn), i = (int)(row / nn), j = (int)(row - (unsigned)i * nn);
     const double inf = 1000.0;
     double gx = i * dx, gy = j * dx, gz = k * dx;
     double best = inf;

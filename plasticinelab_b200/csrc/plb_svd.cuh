@@ -79,8 +79,8 @@ PLB_HD void svd3(const M3<T>& F, M3<T>& U, V3<T>& sig, M3<T>& V, const M3<T>* wa
 #undef PLB_SWAPCOL
     // det(V) = +1
     if (dot(v[0], cross(v[1], v[2])) < T(0)) { v[2] = -v[2]; a[2] = -a[2]; }
-    const T tiny = T(1e-30);
-    const bool ok0 = n0 > tiny * tiny, ok1 = n1 > tiny * tiny;
+    const T tiny2 = sizeof(T) == 4 ? T(1e-36) : T(1e-60);          // squared norm below which a column counts as zero
+    const bool ok0 = n0 > tiny2, ok1 = n1 > tiny2;
     const T r0 = ok0 ? plb_rsqrt(n0) : T(0), r1 = ok1 ? plb_rsqrt(n1) : T(0);
     T s0 = n0 * r0, s1 = n1 * r1;               // sqrt(n) = n / sqrt(n)
     V3<T> u0 = ok0 ? r0 * a[0] : mk3<T>(T(1), T(0), T(0));

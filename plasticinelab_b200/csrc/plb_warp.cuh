@@ -496,7 +496,8 @@ PLB_D void t_grid_bwd_node(bool act, bool owned, long long node, int lane, const
         in4 = grid_in[node];
         go = g_out[node];
         const int n = P.n_grid;
-        iz = (int)(node % n); iy = (int)((node / n) % n); ix = (int)(node / ((long long)n * n));
+        const unsigned un = (unsigned)node, nn = (unsigned)n, row = un / nn;        // n_grid <= 1024: node < 2^30, 32-bit divisions
+        iz = (int)(un - row * nn); ix = (int)(row / nn); iy = (int)(row - (unsigned)ix * nn);
     }
     const bool live = act && (in4.w > T(1e-12));
     V3<T> vstack[PLB_MAX_PRIM];

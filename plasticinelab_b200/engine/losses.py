@@ -30,7 +30,7 @@ class Loss:
         self.res = sim.res
         self.n_grid = sim.n_grid
         self.dx = sim.dx
-        self.n_particles = sim.n_particles
+        self.n_particles = getattr(sim, 'n_particles_global', sim.n_particles)
         self.loss = _LossScalar(self)
         self.soft_contact_loss = False
         self.contact_grad_all = True     # reference autodiff of ti.atomic_min (see oracle docstring)

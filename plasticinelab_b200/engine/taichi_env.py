@@ -36,6 +36,7 @@ class TaichiEnv:
         self.primitives = Primitives(cfg.PRIMITIVES, max_timesteps=sim_cfg.max_steps)
         self.shapes = Shapes(cfg.SHAPES)
         pts, colors = self.shapes.get()
+        n_global = len(pts)
         if particle_index is not None:
             pts, colors = np.ascontiguousarray(pts[particle_index]), colors[particle_index]
         self.init_particles, self.particle_colors = pts, colors
@@ -48,6 +49,7 @@ class TaichiEnv:
         self.primitives.bind(self.engine)
         self.simulator = MPMSimulator(sim_cfg, self.primitives, self.engine)
         self.simulator._env = self
+        self.simulator.n_particles_global = n_global      # (a slab rank holds a share; target densities are scaled to the whole body)
         if nn:
             from .nn.mlp import MLP
             self.nn = MLP(self.simulator, self.primitives, (256, 256))     # taichi_env.py:35-36

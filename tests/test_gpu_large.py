@@ -17,7 +17,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("PLB_TEST_LARGE") == "0", reason="full-size cases switched off (PLB_TEST_LARGE=0)")]
 D = _capi.dptr
 KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE",
-        "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST", "PLB_TILE"]
+        "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST", "PLB_TILE", "PLB_TILE_BWD", "PLB_TILE_FWD_MINB", "PLB_SVD_WARM"]
 CONSERVATIVE = dict(PLB_BWD_OVERLAP=0, PLB_GRID_BWD_V2=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_BWD_MINB=3, PLB_TILE=0)
 CASES = {      # name -> (scene file, particles, quality, env steps)
     "move1m_128": ("move.yml", 1_000_000, 2, 2),          # north-star roofline size
