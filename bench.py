@@ -70,7 +70,7 @@ WORKLOADS = {
     # 8-plane halos, so the slab run uses 4-plane halos (the material moves < 1 plane per env step here).
     "torus4m": dict(scene="torus.yml", n=1_000_000, quality=4, horizon=1, materials="split", scale_n=True, halo_w=4,
                     desc="Torus-v1 geometry (box 0.3 x 0.1 x 0.3, Torus primitive, sticky ground), per-particle mu/lam/yield "
-                         "(E 5e3 / yield 50 for x < 0.5, E 2e4 / yield 200 otherwise), 1M particles per GPU, 256^3 grid, "
+                         "(E 3e3 / yield 50 for x < 0.5, E 6.5e3 / yield 200 otherwise), 1M particles per GPU, 256^3 grid, "
                          "1 env step x 79 substeps, fwd+bwd"),
     # BASELINE.json configs[4]: synthetic elastic block, 2M particles and 64 planes of 512^3 per GPU, no primitives
     "block16m": dict(scene="block", n=2_000_000, quality=8, horizon=1,
@@ -122,9 +122,12 @@ def build_cfg(w, world=1):
 
 
 def split_materials(x0):
-    """BASELINE configs[3] 'multi-material': E 5e3 / yield 50 for x < 0.5, E 2e4 / yield 200 otherwise (nu 0.2)."""
+    """BASELINE configs[3] 'multi-material': E 3e3 / yield 50 for x < 0.5, E 6.5e3 / yield 200 otherwise (nu 0.2).
+    (SURVEY.md 8d suggests E 2e4 for the stiff half "e.g."; at 256^3 the reference's fixed dt = 2.5e-5 puts its P-wave at
+    0.95 cells per substep, beyond the usual stability limit of an explicit MPM step (the 200k-particle instance of this scene
+    left its env-step block list within one env step, gpurun_out/multi4), so the stiff half stays at 0.54 cells per substep.)"""
     stiff = x0[:, 0] >= 0.5
-    E = np.where(stiff, 2e4, 5e3)
+    E = np.where(stiff, 6.5e3, 3e3)
     return E / 2.4, E * 0.2 / (1.2 * 0.6), np.where(stiff, 200.0, 50.0)
 
 

@@ -199,6 +199,14 @@ int  plb_slab_ipc_import(plb_engine* e, int side, const void* handle64);
  * and the ranks must meet at a barrier -- before any rank destroys its engine: CUDA forbids freeing exported memory while an
  * importer still maps it. */
 int  plb_slab_ipc_close(plb_engine* e);
+/* Direct halo (on top of the inbox exchange above; optional): the ranks also map each other's scatter targets -- which = 0 / 1:
+ * grid_in of even / odd substeps, 2 / 3: adjoint of grid_out of even / odd substeps -- and the scatter kernels add their zone
+ * contributions straight into the neighbours' copies (red.global over NVLink) while they add them locally; an exchange is then
+ * only the completion flag published by the last CTA of the scatter kernel, and the grid kernels wait for it.  Export all four,
+ * import the four of each neighbour (side: 0 = left neighbour's, 1 = right neighbour's).  Without these calls the engine pushes
+ * zone blocks into the inboxes instead. */
+int  plb_slab_ipc_export_grid(plb_engine* e, int which, void* handle64);
+int  plb_slab_ipc_import_grid(plb_engine* e, int side, int which, const void* handle64);
 
 /* ---- introspection for tests / profiling ------------------------------------------------------------------ */
 /* copies the dense grids of the last substep: any of in4/out4 may be NULL; [n_grid^3][4] float64 */

@@ -191,6 +191,8 @@ _SIGNATURES = {
     "plb_slab_ipc_export": ([C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "plb_slab_ipc_import": ([C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "plb_slab_ipc_close": ([C.c_void_p], C.c_int),
+    "plb_slab_ipc_export_grid": ([C.c_void_p, C.c_int, C.c_void_p], C.c_int),
+    "plb_slab_ipc_import_grid": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "plb_profile_enable": ([C.c_void_p, C.c_int], C.c_int),
     "plb_profile_read": ([C.c_void_p, C.c_int, _D, C.POINTER(C.c_longlong)], C.c_int),
     "plb_kernel_name": ([C.c_int], C.c_char_p),

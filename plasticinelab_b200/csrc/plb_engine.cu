@@ -126,6 +126,8 @@ struct plb_engine {
     virtual int slab_ipc_export(int side, void* handle64) = 0;
     virtual int slab_ipc_import(int side, const void* handle64) = 0;
     virtual int slab_ipc_close() = 0;
+    virtual int slab_ipc_export_grid(int which, void* handle64) = 0;
+    virtual int slab_ipc_import_grid(int side, int which, const void* handle64) = 0;
     virtual int set_stream(void* s) = 0;
     virtual int synchronize() = 0;
     long long launches = 0;
@@ -185,7 +187,10 @@ struct Engine : plb_engine {
                   // peer-memory halo: my inboxes (neighbours write here), the neighbours' inboxes mapped through CUDA IPC
                   char* inbox[2] = {nullptr, nullptr}; char* peer[2] = {nullptr, nullptr}; HaloGeom geom[2]; size_t inbox_bytes = 0;
                   int* seq = nullptr; int* listed_stamp = nullptr; int* err = nullptr; unsigned* done = nullptr; bool peer_ready = false; bool exported = false, ipc_closed = false;
-                  bool fused = true; } slab;      // fused: env-step block list + one push launch per exchange, receive inside the grid kernels (PLB_SLAB_FUSED=0: the per-substep chain)
+                  bool fused = true;
+                  // direct halo (PLB_SLAB_DIRECT=0 disables): scatter kernels RED their zone contributions into the neighbours' grids
+                  // (CUDA-IPC mappings of grid_in x2 and g_out x2, alternating by substep parity); an exchange is a completion flag
+                  bool direct = true; Vec4<T>* g_out2 = nullptr; Vec4<T>* peer_grid[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}; } slab;      // fused: env-step block list + one push launch per exchange, receive inside the grid kernels (PLB_SLAB_FUSED=0: the per-substep chain)
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     bool fuse = true;               // fused G2P+P2G / P2G.grad+G2P.grad particle kernels inside env-step graphs (PLB_FUSE=0 disables)
     bool fwd_plane = false;         // plane (9-node) tile in the forward scatter kernels: 1/3 shared memory (PLB_FWD_PLANE)
@@ -259,6 +264,7 @@ struct Engine : plb_engine {
             for (int which = 0; which < 3; which++) cudaFree(slab.recv[which][side]);
         }
         cudaFree(slab.seq); cudaFree(slab.err); cudaFree(slab.listed_stamp); cudaFree(slab.done);
+        if (slab.ipc_closed || !slab.exported) cudaFree(slab.g_out2);
         for (cudaEvent_t e : cap_events) cudaEventDestroy(e);
         if (side_stream) cudaStreamDestroy(side_stream);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -405,6 +411,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_SVD_WARM")) svd_warm = atoi(v) != 0;
         if (const char* v = getenv("PLB_TILE_BWD")) tile_bwd = atoi(v) != 0;
         if (const char* v = getenv("PLB_SLAB_FUSED")) slab.fused = atoi(v) != 0;
+        if (const char* v = getenv("PLB_SLAB_DIRECT")) slab.direct = atoi(v) != 0;
         if (const char* v = getenv("PLB_TILE_FWD_MINB")) tile_fwd_minb = atoi(v);
         tile_mode = tile_mode && tile_scatter && sparse && fuse;
         tile_bwd = tile_bwd && tile_mode;
@@ -720,10 +727,40 @@ struct Engine : plb_engine {
     // forward graphs in env-list mode: single GPU, forward-grid store present
     bool slab_fused() const { return slab.peer_ready && slab.fused && env_list && store.vals; }
     bool env_list_mode() const { return env_list && sparse && tile_scatter && store.vals && (!slab.on || slab_fused()); }
-    HaloIn halo_in(bool on) const {
+    // mode: 0 none, 1 fused receive (wait + add the inbox data), 2 direct halo (wait only)
+    HaloIn halo_in(int mode) const {
         HaloIn h;
-        for (int side = 0; side < 2; side++) { h.inbox[side] = (on && slab.has[side]) ? slab.inbox[side] : nullptr; h.g[side] = slab.geom[side]; }
-        h.seq = slab.seq; h.err = slab.err; h.on = on ? 1 : 0;
+        for (int side = 0; side < 2; side++) { h.inbox[side] = (mode && slab.has[side]) ? slab.inbox[side] : nullptr; h.g[side] = slab.geom[side]; }
+        h.seq = slab.seq; h.err = slab.err; h.on = mode;
+        return h;
+    }
+    bool slab_direct() const {
+        if (!(slab_fused() && slab.direct && tile_mode && !tile_bwd && flush_mode == 0 && !bwd_plane && cta == kBlock && grid_bwd_v2 && sets[1].in && slab.g_out2)) return false;
+        for (int side = 0; side < 2; side++)
+            if (slab.has[side]) for (int w = 0; w < 4; w++) if (!slab.peer_grid[side][w]) return false;
+        return true;
+    }
+    // adjoint-of-grid_out buffer the backward scatter of substep j goes into (and its grid adjoint consumes): g_out, or with the
+    // direct halo the parity-j buffer whose copies on the neighbours receive the zone contributions
+    Vec4<T>* cur_gout = nullptr; int cur_gout_which = -1;
+    void select_gout(int j, bool direct) {
+        if (direct) { cur_gout_which = 2 + (j & 1); cur_gout = local_grid(cur_gout_which); }
+        else { cur_gout_which = -1; cur_gout = g_out; }
+    }
+    PeerHalo<Vec4<T>> gout_peers() const { return cur_gout_which >= 0 ? peer_halo(cur_gout_which) : no_peers<Vec4<T>>(); }
+    HaloOut gout_publish() const { return cur_gout_which >= 0 ? halo_out() : halo_out_none(); }
+    Vec4<T>* local_grid(int which) const { return which == 0 ? sets[0].in : which == 1 ? sets[1].in : which == 2 ? g_out : slab.g_out2; }
+    // which: 0/1 grid_in of even/odd substeps, 2/3 g_out of even/odd substeps
+    PeerHalo<Vec4<T>> peer_halo(int which) const {
+        PeerHalo<Vec4<T>> p = no_peers<Vec4<T>>();
+        for (int side = 0; side < 2; side++)
+            if (slab.has[side]) { p.grid[side] = slab.peer_grid[side][which]; p.lo[side] = slab.zlo[side]; p.hi[side] = slab.zhi[side]; }
+        return p;
+    }
+    HaloOut halo_out() const {
+        HaloOut h;
+        for (int side = 0; side < 2; side++) h.peer[side] = slab.has[side] ? slab.peer[side] : nullptr;
+        h.seq = slab.seq; h.done = slab.done;
         return h;
     }
     // one launch: my listed zone blocks of `grid` -> both neighbours' inboxes, published by the last CTA (k_halo_push2)
@@ -737,12 +774,22 @@ struct Engine : plb_engine {
         const int nbx = cfg.n_grid / 4, nb = (n_blocks + 255) / 256;
         cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
         k_mark_slot<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, slot, d_flags);
+        if (slab_direct()) {
+            // the neighbours add into my zone planes directly; what they put into blocks outside my list (the far edge of a zone,
+            // which only their material reaches) is never consumed or cleared by my grid kernels: wipe the zones once per env step,
+            // before my flags go out (the neighbours scatter again only after they have received them)
+            const size_t plane = (size_t)cfg.n_grid * cfg.n_grid * sizeof(Vec4<T>);
+            for (int side = 0; side < 2; side++)
+                if (slab.has[side])
+                    for (int w = 0; w < 4; w++)
+                        cudaMemsetAsync((char*)local_grid(w) + (size_t)slab.zlo[side] * plane, 0, (size_t)(slab.zhi[side] - slab.zlo[side]) * plane, stream);
+        }
         if (slab_fused()) {
             // the neighbours' particles scatter into the zones too: exchange the zone flags once per env step, so that both sides
             // list (and push / receive) the same zone blocks for all of its substeps
             k_halo_push_flags<<<32, 256, 0, stream>>>(cfg.n_grid, d_flags, slab.has[0] ? slab.peer[0] : nullptr, slab.has[1] ? slab.peer[1] : nullptr,
                                                       slab.geom[0], slab.geom[1], slab.seq, slab.done);
-            k_halo_or_flags<<<32, 256, 0, stream>>>(cfg.n_grid, d_flags, halo_in(true));
+            k_halo_or_flags<<<32, 256, 0, stream>>>(cfg.n_grid, d_flags, halo_in(1));
             launches += 2;
         }
         k_dilate_flags<<<nb, 256, 0, stream>>>(nbx, d_flags, d_flags2);
@@ -760,14 +807,17 @@ struct Engine : plb_engine {
             launches++;
         }
     }
-    void enqueue_grid_fwd_stage(SlotRef si, SlotRef pf, bool fixed_list = false) {
+    // gin: the buffer the substep's scatter went into (direct halo alternates between the two grid sets' by substep parity)
+    void enqueue_grid_fwd_stage(SlotRef si, SlotRef pf, bool fixed_list = false, Vec4<T>* gin = nullptr) {
+        if (!gin) gin = grid_in;
         prof_begin(K_GRID_FWD);
         if (sparse) {
             if (fixed_list) {
                 // (the list in d_list / d_nactive was built by enqueue_env_list for the whole env step)
                 if (slab_fused()) {
-                    halo_push_fused(grid_in, d_list, d_nactive);
-                    k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si, halo_in(true));
+                    const bool direct = slab_direct();
+                    if (!direct) halo_push_fused(gin, d_list, d_nactive);
+                    k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gin, grid_out, 1, d_list, d_nactive, store, si, halo_in(direct ? 2 : 1));
                     prof_end();
                     launches++;
                     return;
@@ -792,7 +842,7 @@ struct Engine : plb_engine {
             } else {
                 compact_blocks();
             }
-            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si, halo_in(false));
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si, halo_in(0));
         } else {
             k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
         }
@@ -819,23 +869,27 @@ struct Engine : plb_engine {
             // chunked kernels: one CTA per <= 128 particles of one grid block, grid_out window by TMA (plb_tile.cuh)
             const size_t sm = chunk_smem_bytes(kFwdTiles);
             const SlotRef none = abs_ref(0);
+            const bool direct = fixed_list && slab_direct();          // scatter of substep i -> grid set i & 1, mirrored into the neighbours' copies
+            const HaloOut ho = direct ? halo_out() : halo_out_none();
+            auto gin = [&](int i) { return direct ? sets[i & 1].in : grid_in; };
+            auto ph = [&](int i) { return direct ? peer_halo(i & 1) : no_peers<Vec4<T>>(); };
             prof_begin(K_P2G);
             k_fwd_chunk<T, FWD_P2G, TileOcc<T>::fwd><<<chunk_grid, kBlock, sm, stream>>>(tm_out[0], P, frames, n_pad, mk(this, 0, 0), none, mk(this, 1, 0), material(),
-                                                                                      chunk_table(), grid_out, grid_in, fl, svd_store, 0);
+                                                                                      chunk_table(), grid_out, gin(0), fl, svd_store, 0, ph(0), ho);
             prof_end();
-            enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0), fixed_list);
+            enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0), fixed_list, gin(0));
             for (int i = 1; i < n; i++) {
                 prof_begin(K_G2P_P2G);
                 auto kern = tile_fwd_minb >= 6 ? k_fwd_chunk<T, FWD_G2P | FWD_P2G, TileOcc<T>::fwd_hi> : k_fwd_chunk<T, FWD_G2P | FWD_P2G, TileOcc<T>::fwd>;
                 kern<<<chunk_grid, kBlock, sm, stream>>>(tm_out[0], P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), chunk_table(),
-                                                         grid_out, grid_in, fl, svd_store, svd_warm ? 1 : 0);
+                                                         grid_out, gin(i), fl, svd_store, svd_warm ? 1 : 0, ph(i), ho);
                 prof_end();
-                enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i), fixed_list);
+                enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i), fixed_list, gin(i));
                 launches++;
             }
             prof_begin(K_G2P);
             k_fwd_chunk<T, FWD_G2P, TileOcc<T>::fwd><<<chunk_grid, kBlock, sm, stream>>>(tm_out[0], P, frames, n_pad, mk(this, 0, n - 1), none, mk(this, 1, n - 1), material(),
-                                                                                      chunk_table(), grid_out, grid_in, nullptr, (T*)nullptr, 0);
+                                                                                      chunk_table(), grid_out, grid_in, nullptr, (T*)nullptr, 0, no_peers<Vec4<T>>(), halo_out_none());
             prof_end();
             launches += 2;
             if (fixed_list) enqueue_env_list_check(mk(this, 1, n - 1));
@@ -875,7 +929,7 @@ struct Engine : plb_engine {
         }
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE, st);
         if (sparse)
-            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, gs.list, gs.count, nostore, si, halo_in(false));
+            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, gs.list, gs.count, nostore, si, halo_in(0));
         else
             k_grid_fwd<T><<<ng, kBlock, 0, st>>>(P, prims, d_traj, pf, gs.in, gs.out, 0, n_nodes);
         prof_end();
@@ -884,9 +938,11 @@ struct Engine : plb_engine {
     void enqueue_bwd_grid_adj(SlotRef pf, const GridSet& gs) {               // (halo of g_out) + grid_op.grad
         const int ng = blocks(n_nodes);
         prof_begin(K_GRID_BWD);
+        Vec4<T>* g_out = cur_gout ? cur_gout : this->g_out;
         if (slab_fused() && sparse && grid_bwd_v2) {
-            halo_push_fused(g_out, gs.list, gs.count);
-            k_grid_bwd_sparse_v2<T><<<sparse_ctas(148 * 5), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(true));
+            const bool direct = cur_gout_which >= 0;
+            if (!direct) halo_push_fused(g_out, gs.list, gs.count);
+            k_grid_bwd_sparse_v2<T><<<sparse_ctas(148 * 5), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(direct ? 2 : 1));
             prof_end();
             launches++;
             return;
@@ -898,7 +954,7 @@ struct Engine : plb_engine {
             launches += 6;
         }
         if (sparse && grid_bwd_v2 && !slab.on)         // (slab runs keep the array form: the register form was validated on one GPU only)
-            k_grid_bwd_sparse_v2<T><<<sparse_ctas(148 * 5), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(false));
+            k_grid_bwd_sparse_v2<T><<<sparse_ctas(148 * 5), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(0));
         else if (sparse)
             k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());
         else
@@ -910,6 +966,7 @@ struct Engine : plb_engine {
     const CUtensorMap& tm_of(const GridSet& gs) const { return gs.out == sets[1].out ? tm_out[1] : tm_out[0]; }
     // s_next: the successor frame of si (only dereferenced when next_ok)
     void launch_g2p_bwd(SlotRef si, T* a_next, T* a_cur, const GridSet& gs, bool next_ok, bool chunked = false, SlotRef s_next = SlotRef{nullptr, 0, 0}) {
+        Vec4<T>* g_out = cur_gout ? cur_gout : this->g_out;
         prof_begin(K_G2P_BWD);
         if (chunked) {
             k_bwd_chunk<T, BWD_G2P, TileOcc<T>::bwd_lo, false><<<chunk_grid, kBlock, chunk_smem_bytes(kBwdTiles), stream>>>(
@@ -917,8 +974,8 @@ struct Engine : plb_engine {
         } else if (tile_scatter) {
             const int nbc = blocks(cfg.n_particles, cta);
             const size_t sm = tile_smem_bytes(bwd_plane, cta);
-            if (bwd_plane) k_g2p_bwd_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode);
-            else k_g2p_bwd_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode);
+            if (bwd_plane) k_g2p_bwd_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode, no_peers<Vec4<T>>(), halo_out_none());
+            else k_g2p_bwd_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode, gout_peers(), gout_publish());
         } else {
             k_g2p_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, gs.out, g_out);
         }
@@ -943,6 +1000,7 @@ struct Engine : plb_engine {
     void launch_bwd_fused(SlotRef s_cur, SlotRef s_prev, T* a_next, T* a_cur, const GridSet& gs, bool svd) {
         const int nbc = blocks(cfg.n_particles, cta);
         const size_t sm = tile_smem_bytes(bwd_plane, cta);
+        Vec4<T>* g_out = cur_gout ? cur_gout : this->g_out;
         prof_begin(K_P2G_BWD_G2P_BWD);
         if (tile_bwd) {
             if (svd && bwd_minb >= 4)
@@ -959,7 +1017,8 @@ struct Engine : plb_engine {
         auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo, false>)
                     : svd     ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>)
                               : (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, false>);
-        kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode, svd_store);
+        kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode, svd_store,
+                                       bwd_plane ? no_peers<Vec4<T>>() : gout_peers(), bwd_plane ? halo_out_none() : gout_publish());
         prof_end();
         launches++;
     }
@@ -978,16 +1037,20 @@ struct Engine : plb_engine {
     //   Pre(j) -> K(j) = [p2g.grad(j+1) +] g2p.grad(j) -> A(j) = grid adjoint(j) -> K(j-1);   Pre(j-2) waits for A(j) (same set).
     void enqueue_bwd_fused(int n, bool restore, bool next_ok, bool svd, int c, SlotRef (*mk)(const Engine*, int, int), bool overlap) {
         svd = svd && !bwd_plane;
+        const bool direct = restore && slab_direct();          // (direct halo: the scatter of substep j and its grid adjoint use the parity-j buffer)
         if (!overlap) {
             enqueue_bwd_grid_pre(mk(this, 0, n - 1), mk(this, 2, n - 1), restore, sets[0], stream);
+            select_gout(n - 1, direct);
             launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[0], next_ok, tile_bwd, mk(this, 1, n - 1));
             enqueue_bwd_grid_adj(mk(this, 2, n - 1), sets[0]);
             for (int i = n - 1; i >= 1; i--) {
                 enqueue_bwd_grid_pre(mk(this, 0, i - 1), mk(this, 2, i - 1), restore, sets[0], stream);
+                select_gout(i - 1, direct);
                 launch_bwd_fused(mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1], sets[0], svd);
                 c ^= 1;
                 enqueue_bwd_grid_adj(mk(this, 2, i - 1), sets[0]);
             }
+            select_gout(0, false);
             launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1], svd, tile_bwd);
             return;
         }
@@ -1000,6 +1063,7 @@ struct Engine : plb_engine {
         cudaEvent_t ev_pre = next_event();
         enqueue_bwd_grid_pre(mk(this, 0, n - 2), mk(this, 2, n - 2), true, sets[(n - 2) & 1], side_stream);
         cudaEventRecord(ev_pre, side_stream);
+        select_gout(n - 1, direct);
         launch_g2p_bwd(mk(this, 0, n - 1), adj[c], adj[c ^ 1], sets[(n - 1) & 1], next_ok, tile_bwd, mk(this, 1, n - 1));
         enqueue_bwd_grid_adj(mk(this, 2, n - 1), sets[(n - 1) & 1]);
         cudaEvent_t ev_adj = next_event();              // A(i) done, for the i of the coming iteration
@@ -1012,12 +1076,14 @@ struct Engine : plb_engine {
                 ev_pre = next_event();
                 cudaEventRecord(ev_pre, side_stream);
             }
+            select_gout(i - 1, direct);
             launch_bwd_fused(mk(this, 0, i), mk(this, 0, i - 1), adj[c], adj[c ^ 1], sets[(i - 1) & 1], svd);
             c ^= 1;
             enqueue_bwd_grid_adj(mk(this, 2, i - 1), sets[(i - 1) & 1]);
             ev_adj = next_event();
             cudaEventRecord(ev_adj, stream);
         }
+        select_gout(0, false);
         launch_p2g_bwd(mk(this, 0, 0), adj[c], adj[c ^ 1], svd, tile_bwd);
     }
     // push my listed zone blocks of `grid` into the neighbours' inboxes, publish, wait for theirs
@@ -1179,6 +1245,11 @@ struct Engine : plb_engine {
                 PLB_CUDA(cudaMalloc(&slab.recv[which][side], bytes));
             }
         }
+        if (slab.direct && !slab.g_out2) {
+            const size_t gb = (size_t)n_nodes * sizeof(Vec4<T>);
+            if (cudaMalloc(&slab.g_out2, gb) == cudaSuccess) cudaMemset(slab.g_out2, 0, gb);
+            else { cudaGetLastError(); slab.g_out2 = nullptr; }
+        }
         use_graphs = false;                    // phases are host-driven
         return PLB_OK;
     }
@@ -1222,7 +1293,7 @@ struct Engine : plb_engine {
             }
         compact_blocks();
         halo_add(grid_in, 0);
-        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 1, d_list, d_nactive, store, abs_ref(si), halo_in(false));
+        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 1, d_list, d_nactive, store, abs_ref(si), halo_in(0));
         prof_end(); prof_begin(K_G2P);
         k_g2p<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, abs_ref(si), abs_ref(so), grid_out);
         prof_end();
@@ -1240,7 +1311,7 @@ struct Engine : plb_engine {
         prof_begin(K_P2G_RECOMPUTE);
         k_restore_blocks<T><<<sparse_ctas(), kBlock, 0, stream>>>(cfg.n_grid, grid_in, d_list, d_nactive, store, abs_ref(si));
         prof_end(); prof_begin(K_GRID_FWD_RECOMPUTE);
-        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 0, d_list, d_nactive, nostore, abs_ref(si), halo_in(false));
+        k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, abs_ref(pf), grid_in, grid_out, 0, d_list, d_nactive, nostore, abs_ref(si), halo_in(0));
         prof_end();
         launch_g2p_bwd(abs_ref(si), adj[cur], adj[cur ^ 1], sets[0], fwd_ok[si] != 0);
         launches += 2;
@@ -1360,11 +1431,33 @@ struct Engine : plb_engine {
         }
         return PLB_OK;
     }
+    // direct halo: which = 0/1 grid_in of even/odd substeps, 2/3 adjoint of grid_out of even/odd substeps
+    int slab_ipc_export_grid(int which, void* handle64) override {
+        PLB_REQUIRE(slab.on && which >= 0 && which < 4, "no such grid");
+        PLB_REQUIRE(local_grid(which) != nullptr, "direct halo buffers are not allocated (PLB_SLAB_DIRECT=0 or PLB_BWD_OVERLAP=0)");
+        cudaIpcMemHandle_t h;
+        PLB_CUDA(cudaIpcGetMemHandle(&h, local_grid(which)));
+        std::memcpy(handle64, &h, 64);
+        return PLB_OK;
+    }
+    int slab_ipc_import_grid(int side, int which, const void* handle64) override {
+        PLB_REQUIRE(slab.on && side >= 0 && side < 2 && slab.has[side] && which >= 0 && which < 4, "no neighbour on that side");
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, 64);
+        void* ptr = nullptr;
+        PLB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        slab.peer_grid[side][which] = (Vec4<T>*)ptr;
+        drop_graphs();
+        return PLB_OK;
+    }
     int slab_ipc_close() override {
         PLB_CUDA(cudaStreamSynchronize(stream));
         drop_graphs();                         // (they hold the peer pointers by value)
         for (int side = 0; side < 2; side++)
             if (slab.peer[side]) { cudaIpcCloseMemHandle(slab.peer[side]); slab.peer[side] = nullptr; }
+        for (int side = 0; side < 2; side++)
+            for (int w = 0; w < 4; w++)
+                if (slab.peer_grid[side][w]) { cudaIpcCloseMemHandle(slab.peer_grid[side][w]); slab.peer_grid[side][w] = nullptr; }
         slab.peer_ready = false; slab.ipc_closed = true;
         use_graphs = false;
         return PLB_OK;
@@ -1732,6 +1825,8 @@ int plb_device_buffer(plb_engine* e, int which, void** ptr, long long* bytes) { 
 int plb_slab_ipc_export(plb_engine* e, int side, void* handle64) { return e->slab_ipc_export(side, handle64); }
 int plb_slab_ipc_import(plb_engine* e, int side, const void* handle64) { return e->slab_ipc_import(side, handle64); }
 int plb_slab_ipc_close(plb_engine* e) { return e->slab_ipc_close(); }
+int plb_slab_ipc_export_grid(plb_engine* e, int which, void* handle64) { return e->slab_ipc_export_grid(which, handle64); }
+int plb_slab_ipc_import_grid(plb_engine* e, int side, int which, const void* handle64) { return e->slab_ipc_import_grid(side, which, handle64); }
 int plb_debug_get_grid(plb_engine* e, double* in4, double* out4) { return e->debug_get_grid(in4, out4); }
 long long plb_launch_count(const plb_engine* e) { return e->launches; }
 int plb_profile_enable(plb_engine* e, int on) {

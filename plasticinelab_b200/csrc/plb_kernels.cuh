@@ -192,7 +192,7 @@ struct HaloGeom { int zone_lo, zone_hi, nzb; long long stamps_off, data_off, fla
 // What a grid kernel needs to take the neighbours' partial sums itself (fused receive): my two inboxes, their geometry, the
 // exchange counter.  on == 0: no halo (single GPU, or the stage reads an already summed grid).
 struct HaloIn { const char* inbox[2]; HaloGeom g[2]; const int* seq; int* err; int on; };
-__device__ __forceinline__ HaloIn halo_none() { HaloIn h; h.inbox[0] = h.inbox[1] = nullptr; h.seq = nullptr; h.err = nullptr; h.on = 0; return h; }
+__host__ __device__ __forceinline__ HaloIn halo_none() { HaloIn h; h.inbox[0] = h.inbox[1] = nullptr; h.seq = nullptr; h.err = nullptr; h.on = 0; return h; }
 
 // thread 0 of the CTA spins until both neighbours have published exchange `s` in MY inboxes (local memory: the neighbour wrote
 // it over NVLink), then the CTA may read what they pushed.  ~4 s timeout -> *err = 1 (reported by the next readback).
@@ -289,20 +289,32 @@ __global__ void k_halo_next_seq(int* seq_ptr) { *seq_ptr += 1; }
 // Exchange number s = *seq + 1.  Every CTA copies its share of my listed zone blocks into the neighbours' inboxes (parity
 // s & 1) and stamps them; every thread fences its stores; the LAST CTA to finish publishes s in both neighbours' flags and
 // stores it to *seq (the consumer kernel launched next reads it there).
-__device__ __forceinline__ void halo_publish_last_cta(char* peer0, char* peer1, int* seq_ptr, unsigned* done, int s) {
-    __threadfence_system();
+__device__ __forceinline__ void halo_publish_last_cta(char* peer0, char* peer1, int* seq_ptr, unsigned* done, int s, bool fence = true) {
+    if (fence) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned t = atomicAdd(done, 1u);
         if (t == gridDim.x - 1) {
             *done = 0u;
             __threadfence_system();
+            if (s < 0) s = *seq_ptr + 1;
             if (peer0) { volatile int* f = reinterpret_cast<volatile int*>(peer0); f[0] = s; }
             if (peer1) { volatile int* f = reinterpret_cast<volatile int*>(peer1); f[0] = s; }
             __threadfence_system();
             *seq_ptr = s;
         }
     }
+}
+// Direct halo: the scatter kernels add their zone contributions straight into the neighbours' grids (PeerHalo, plb_warp.cuh), so
+// an exchange is only a completion signal: every warp that issued remote REDs fences them, the last CTA of the scatter kernel
+// publishes the next exchange number in the neighbours' flags.  seq == nullptr: nothing to publish (single GPU).
+struct HaloOut { char* peer[2]; int* seq; unsigned* done; };
+__host__ __device__ __forceinline__ HaloOut halo_out_none() { HaloOut h; h.peer[0] = h.peer[1] = nullptr; h.seq = nullptr; h.done = nullptr; return h; }
+// every thread of the CTA calls this once, at the end of the kernel (sent: this thread issued a RED into a neighbour's grid)
+__device__ __forceinline__ void halo_publish_scatter(const HaloOut& ho, bool sent) {
+    if (!ho.seq) return;
+    if (__any_sync(0xffffffffu, sent)) __threadfence_system();
+    halo_publish_last_cta(ho.peer[0], ho.peer[1], ho.seq, ho.done, -1, false);
 }
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_halo_push2(int n_grid, const Vec4<T>* __restrict__ grid, const int* __restrict__ list,
@@ -456,13 +468,15 @@ __global__ void __launch_bounds__(kBlock, kMinB) k_g2p_p2g_warp(SimConst<T> P, T
 // g2p.grad; next_ok: slot_in + 1 holds the frame G2P produced from slot_in (clamp masks and gather sum are read from it)
 template <class T, bool kPlane>
 __global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, int next_ok,
-                                                                           T* adj_next, T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode) {
+                                                                           T* adj_next, T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode,
+                                                                           PeerHalo<Vec4<T>> ph, HaloOut ho) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int si = slot_in.get();
     FramePtr<T> fnext = frame_at(frames, si + 1, n_pad);
-    t_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+    const bool sent = t_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                          frame_at(frames, si, n_pad), next_ok ? &fnext : nullptr, frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad),
-                         grid_out, g_out, flush_mode);
+                         grid_out, g_out, flush_mode, ph.any() ? &ph : nullptr);
+    halo_publish_scatter(ho, sent);
 }
 
 // p2g.grad of substep s + g2p.grad of substep s-1 (inside env-step graphs; frame s was produced by G2P(s-1) there)
@@ -470,13 +484,15 @@ __global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_warp(SimCon
 template <class T, bool kPlane, int kMinB, bool kSvd>
 __global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
                                                                                    SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
-                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode, T* svd_base) {
+                                                                                   const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode, T* svd_base,
+                                                                                   PeerHalo<Vec4<T>> ph, HaloOut ho) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SvdPtr<T> sp = svd_at(svd_base, slot_s.get(), n_pad);
     // tight register cap + SVD store: run the (then cheap) forward particle math twice instead of keeping it across the gather
-    t_p2g_bwd_g2p_bwd<T, kPlane, kSvd, (kSvd && kMinB >= 4)>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+    const bool sent = t_p2g_bwd_g2p_bwd<T, kPlane, kSvd, (kSvd && kMinB >= 4)>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
                                        frame_at(frames, slot_s.get(), n_pad), frame_at(frames, slot_prev.get(), n_pad), frame_at(adj_next, 0, n_pad),
-                                       frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out, flush_mode, &sp);
+                                       frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out, flush_mode, &sp, ph.any() ? &ph : nullptr);
+    halo_publish_scatter(ho, sent);
 }
 
 template <class T>
@@ -502,7 +518,7 @@ __global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimS
     for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
         const int blk = list[e];
         const long long node = block_node(P.n_grid, blk, local);
-        if (halo.on) {
+        if (halo.on == 1) {                                     // (2: direct halo, the neighbours' sums are already in grid_in)
             Vec4<T> r;
             if (halo_fetch<T>(halo, P.n_grid, blk, local, hs, r)) {
                 const Vec4<T> v = grid_in[node];
@@ -638,7 +654,7 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse_v2(SimConst<T> P, Pr
             node = block_node(P.n_grid, blk, local);
             const int plane = (int)(node / ((long long)P.n_grid * P.n_grid));
             owned = plane >= own_lo && plane < own_hi;
-            if (halo.on) {
+            if (halo.on == 1) {
                 Vec4<T> q;
                 if (halo_fetch<T>(halo, P.n_grid, blk, local, hs, q)) {
                     const Vec4<T> v = g_out[node];

@@ -103,8 +103,10 @@ __device__ __forceinline__ Vec4<double> add4(Vec4<double> a, Vec4<double> b) { r
 // key: packed base cell of this lane's particle (< 0: none).  All 32 lanes must call.  A run = maximal stretch of consecutive
 // lanes with one key; lane q < 27 sums node q over each run and adds it to the grid with one vector RED.  Columns of lanes
 // without a particle are read but land in a run of their own that is dropped.
+// ph: direct halo (plb_warp.cuh) -- returns true if this lane issued a RED into a neighbour's grid
 template <class T>
-__device__ __forceinline__ void flush_runs(const Vec4<T>* tile, int lane, int key, int n_grid, Vec4<T>* grid) {
+__device__ __forceinline__ bool flush_runs(const Vec4<T>* tile, int lane, int key, int n_grid, Vec4<T>* grid, const PeerHalo<Vec4<T>>& ph) {
+    bool sent = false;
     __syncwarp();
     const int next = __shfl_sync(0xffffffffu, key, (lane + 1) & 31);
     const unsigned ends = __ballot_sync(0xffffffffu, lane == 31 || next != key);
@@ -124,14 +126,18 @@ __device__ __forceinline__ void flush_runs(const Vec4<T>* tile, int lane, int ke
                 acc = add4(acc, v[j]);
                 if ((m >> j) & 1u) {
                     const int rkey = __shfl_sync(0xffffffffu, key, 4 * g + j);
-                    if (lane < 27 && rkey >= 0)
-                        scatter_add4(grid + node_index(n_grid, (rkey >> 20) + oi, ((rkey >> 10) & 1023) + oj, (rkey & 1023) + ok), acc);
+                    if (lane < 27 && rkey >= 0) {
+                        const long long node = node_index(n_grid, (rkey >> 20) + oi, ((rkey >> 10) & 1023) + oj, (rkey & 1023) + ok);
+                        scatter_add4(grid + node, acc);
+                        sent = pay_red_peers(ph, node, (rkey >> 20) + oi, acc) || sent;
+                    }
                     acc = mk4<T>(T(0), T(0), T(0), T(0));
                 }
             }
         }
     }
     __syncwarp();
+    return sent;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -143,13 +149,14 @@ constexpr int kFwdTiles = 2, kBwdTiles = 4;
 template <class T, int kMode, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB)
 k_fwd_chunk(const __grid_constant__ CUtensorMap tm_out, SimConst<T> P, T* frames, long long n_pad, SlotRef s_in, SlotRef s_mid, SlotRef s_out,
-            Material<T> mat, ChunkTable sg, const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags, T* svd_base, int svd_warm) {
+            Material<T> mat, ChunkTable sg, const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags, T* svd_base, int svd_warm,
+            PeerHalo<Vec4<T>> ph, HaloOut ho) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3];          // [0] TMA window, [1..2] scatter-tile hand-off
     unsigned long long& mbar = bars[0];
     const int n_chunks = *sg.n_chunks;
     const Chunk ch = sg.chunks[blockIdx.x];             // (the table has room for the whole launch grid: both loads are in flight together)
-    if ((int)blockIdx.x >= n_chunks) return;
+    if ((int)blockIdx.x >= n_chunks) { halo_publish_scatter(ho, false); return; }
     const int tid = threadIdx.x, lane = tid & 31;
     // warm start of the Jacobi SVD from V of the previous substep (record of slot s_in, written by the previous kernel)
     const bool warm = kMode == (FWD_G2P | FWD_P2G) && svd_base != nullptr && svd_warm != 0;
@@ -219,8 +226,9 @@ k_fwd_chunk(const __grid_constant__ CUtensorMap tm_out, SimConst<T> P, T* frames
             WarpTileScatter<T> sc{stile, lane};
             p2g_scatter<T>(P, st, v, affine, sc);
         }
-        flush_runs<T>(stile, lane, key, P.n_grid, grid_in);
+        const bool sent = flush_runs<T>(stile, lane, key, P.n_grid, grid_in, ph);
         shared_tile_release<kFwdTiles>(&bars[1], tid >> 5, lane);
+        halo_publish_scatter(ho, sent);
     }
 }
 
@@ -315,7 +323,7 @@ k_bwd_chunk(const __grid_constant__ CUtensorMap tm_gin, const __grid_constant__ 
             WarpTileScatter<T> sc{stile, lane};
             g2p_bwd_scatter<T>(stp, carry, sc);
         }
-        flush_runs<T>(stile, lane, key, P.n_grid, g_out);
+        flush_runs<T>(stile, lane, key, P.n_grid, g_out, no_peers<Vec4<T>>());
         shared_tile_release<kBwdTiles>(nullptr, tid >> 5, lane);
     }
 }

@@ -88,6 +88,25 @@ template <class Pay> PLB_D Pay tile_row_sum(const Pay* row, unsigned g) {
     return a0;
 }
 
+// ------------------------------------------------------------------------------------------------ direct halo (multi-GPU slabs)
+// The neighbours' copies of the grid this kernel scatters into, mapped through CUDA IPC (NVLink peer memory).  A reduced
+// contribution to a node whose plane lies in the zone shared with a neighbour is added to the neighbour's grid as well (one more
+// RED, over NVLink), so that after the scatter kernels of both ranks the zone holds the full sums on both sides and no separate
+// push / add pass is needed.  grid[side] == nullptr: no neighbour on that side (or single-GPU run: both null).
+template <class Pay> struct PeerHalo {
+    Pay* grid[2]; int lo[2], hi[2];
+    PLB_HD bool any() const { return grid[0] != nullptr || grid[1] != nullptr; }
+};
+template <class Pay> PLB_HD PeerHalo<Pay> no_peers() { PeerHalo<Pay> p; p.grid[0] = p.grid[1] = nullptr; p.lo[0] = p.lo[1] = p.hi[0] = p.hi[1] = 0; return p; }
+// plane = first grid index of the node; returns true if a remote RED was issued
+template <class Pay> PLB_D bool pay_red_peers(const PeerHalo<Pay>& ph, long long node, int plane, const Pay& a) {
+    bool sent = false;
+#pragma unroll
+    for (int side = 0; side < 2; side++)
+        if (ph.grid[side] && plane >= ph.lo[side] && plane < ph.hi[side]) { pay_red(ph.grid[side] + node, a); sent = true; }
+    return sent;
+}
+
 // ------------------------------------------------------------------------------------------------ full tile
 template <class T> struct WarpTileScatter {
     Vec4<T>* tile;     // this warp's tile
@@ -103,12 +122,14 @@ template <class Pay> PLB_D void tile_init(Pay* tile, int lane) {
 
 // key: packed base cell of this lane's particle (< 0: none).  All 32 lanes must call.  Loop over the distinct cells of
 // the warp; lane q < 27 sums node q over the lanes of the cell and adds it to the grid with one (vector) RED.
+// ph (optional): direct halo -- returns true if this lane issued a RED into a neighbour's grid
 template <class Pay>
-PLB_D void warp_tile_flush(const Pay* tile, int lane, int key, int n_grid, Pay* grid) {
+PLB_D bool warp_tile_flush(const Pay* tile, int lane, int key, int n_grid, Pay* grid, const PeerHalo<Pay>* ph = nullptr) {
     warp_sync();
     unsigned remaining = warp_ballot(key >= 0);
     const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;       // node offset owned by this lane (lane < 27)
     const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
+    bool sent = false;
     while (remaining) {
         const int leader = ctz32(remaining);
         const int lkey = warp_shfl(key, leader);
@@ -116,10 +137,13 @@ PLB_D void warp_tile_flush(const Pay* tile, int lane, int key, int n_grid, Pay* 
         remaining &= ~group;
         if (lane < 27) {
             const Pay acc = tile_row_sum(row, group);
-            pay_red(grid + node_index(n_grid, (lkey >> 20) + oi, ((lkey >> 10) & 1023) + oj, (lkey & 1023) + ok), acc);
+            const long long node = node_index(n_grid, (lkey >> 20) + oi, ((lkey >> 10) & 1023) + oj, (lkey & 1023) + ok);
+            pay_red(grid + node, acc);
+            if (ph) sent = pay_red_peers(*ph, node, (lkey >> 20) + oi, acc) || sent;
         }
     }
     warp_sync();
+    return sent;
 }
 
 // Paired-group flush: like warp_tile_flush, but two cells are taken per round and their column walks are interleaved, so
@@ -202,7 +226,8 @@ template <class Pay> PLB_D void tile_zero_column(Pay* tile, int lane) {
 }
 // mode 0: per-cell groups, mode 1: runs, mode 2: per-cell groups, two cells per round
 template <class Pay>
-PLB_D void warp_tile_flush_sel(Pay* tile, int lane, int key, int n_grid, Pay* grid, int mode) {
+PLB_D bool warp_tile_flush_sel(Pay* tile, int lane, int key, int n_grid, Pay* grid, int mode, const PeerHalo<Pay>* ph = nullptr) {
+    if (ph) return warp_tile_flush(tile, lane, key, n_grid, grid, ph);          // (direct halo: per-cell group flush only)
     if (mode == 1) {
         if (key < 0) tile_zero_column(tile, lane);
         warp_tile_flush_runs(tile, lane, key, n_grid, grid);
@@ -211,6 +236,7 @@ PLB_D void warp_tile_flush_sel(Pay* tile, int lane, int key, int n_grid, Pay* gr
     } else {
         warp_tile_flush(tile, lane, key, n_grid, grid);
     }
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------------ plane tile
@@ -355,8 +381,9 @@ PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
 
 // g2p.grad of one substep (state frame fin; fnext = the frame G2P produced, or null pointers => recompute the gather sum)
 template <class T, bool kPlane>
-PLB_D void t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>* fnext,
-                     const FramePtr<T>& adj_next, const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0) {
+PLB_D bool t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>* fnext,
+                     const FramePtr<T>& adj_next, const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0,
+                     const PeerHalo<Vec4<T>>* ph = nullptr) {
     const bool valid = p < P.n_particles;
     if (kPlane) {
         if (!valid) p = P.n_particles - 1;
@@ -391,16 +418,18 @@ PLB_D void t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const
             adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
             key = cell_key(x, P.inv_dx);
         }
-        warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode);
+        return warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode, ph);
     }
+    return false;
 }
 
 // p2g.grad of substep s (frame fs) + g2p.grad of substep s-1 (frame fprev); the adjoint of (x,v,C)[s] stays in registers and
 // the state (x,v)[s] this thread loaded anyway is what G2P(s-1) produced (clamp masks + gather sum come from it)
 template <class T, bool kPlane, bool kSvdGiven = false, bool kTwoPhase = false>
-PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fs, const FramePtr<T>& fprev,
+PLB_D bool t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fs, const FramePtr<T>& fprev,
                              const FramePtr<T>& next, const FramePtr<T>& cur, const Material<T>& mat, const Vec4<T>* g_in,
-                             const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0, const SvdPtr<T>* svd_kept = nullptr) {
+                             const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0, const SvdPtr<T>* svd_kept = nullptr,
+                             const PeerHalo<Vec4<T>>* ph = nullptr) {
     const bool valid = p < P.n_particles;
     if (valid) prefetch_frame_rest(fprev, p);          // for the next backward kernel (p2g.grad of substep s-1)
     if (kPlane) {
@@ -444,8 +473,9 @@ PLB_D void t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& 
             next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
             key = cell_key(xp, P.inv_dx);
         }
-        warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode);
+        return warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode, ph);
     }
+    return false;
 }
 
 // mass-only scatter of the loss (scalar payload, full tile of scalars)

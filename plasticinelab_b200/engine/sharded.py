@@ -8,6 +8,7 @@ the contact minimum and the pose gradients are all-reduced.  See include/plb_b20
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -71,7 +72,7 @@ class ShardedEnv:
         self.prim_grad = _tensor(ptr.value, nb.value, self.device, f64=True)
         self.records = []
         self.cur = 0
-        import os
+        self.direct = False
         self.peer = (os.environ.get("PLB_SLAB_PEER", "1") != "0") if peer is None else bool(peer)
         if self.peer and self.world > 1:
             self._setup_peer()
@@ -93,6 +94,20 @@ class ShardedEnv:
             peer = self.rank - 1 if side == 0 else self.rank + 1
             h = gathered[peer][1 - side]          # the neighbour's inbox that faces me
             eng.call("plb_slab_ipc_import", side, C.create_string_buffer(h, 64))
+        # direct halo: map the neighbours' scatter targets too (grid_in / adjoint of grid_out, even and odd substeps)
+        self.direct = os.environ.get("PLB_SLAB_DIRECT", "1") != "0" and os.environ.get("PLB_BWD_OVERLAP", "1") != "0"
+        if self.direct:
+            grids = []
+            for which in range(4):
+                buf = C.create_string_buffer(64)
+                eng.call("plb_slab_ipc_export_grid", which, buf)
+                grids.append(buf.raw)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, grids, group=self.group)
+            for side in self.sides:
+                peer = self.rank - 1 if side == 0 else self.rank + 1
+                for which in range(4):
+                    eng.call("plb_slab_ipc_import_grid", side, which, C.create_string_buffer(gathered[peer][which], 64))
         dist.barrier(group=self.group)
 
     def close(self):

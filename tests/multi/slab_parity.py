@@ -80,9 +80,10 @@ def main():
         el = abs(loss - rloss) / abs(rloss)
         eg = np.linalg.norm(grad - rgrad) / np.linalg.norm(rgrad)
         ex = np.abs(x_local - xr[senv.index]).max()
-        print(f'[slab parity] peer={int(senv.peer)} world={world} bounds={senv.bounds} local={len(senv.index)}/{senv.n_global} loss {loss:.10f} vs {rloss:.10f} '
+        print(f'[slab parity] peer={int(senv.peer)} direct={int(senv.direct)} world={world} bounds={senv.bounds} local={len(senv.index)}/{senv.n_global} loss {loss:.10f} vs {rloss:.10f} '
               f'(rel {el:.2e}) grad rel {eg:.2e} |grad| {np.linalg.norm(rgrad):.3e} x err {ex:.2e}')
         ok = el < tol_l and eg < tol_g and ex < tol_x
+    senv.close()
     flag = torch.tensor([1 if ok else 0], device='cuda')
     dist.broadcast(flag, 0)
     if rank != 0:

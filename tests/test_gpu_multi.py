@@ -10,14 +10,20 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('peer', [1, 0])
+# halo paths: direct (scatter kernels add into the neighbours' grids over NVLink, default), push (zone blocks pushed into the
+# neighbour's inbox, one launch per exchange), chain (the per-substep launch chain of round 1), host (NCCL send/recv from the host)
+MODES = {'direct': (1, {}), 'push': (1, {'PLB_SLAB_DIRECT': '0'}), 'chain': (1, {'PLB_SLAB_FUSED': '0'}), 'host': (0, {})}
+
+
+@pytest.mark.parametrize('mode', sorted(MODES))
 @pytest.mark.parametrize('dtype', ['float64', 'float32'])
-def test_slab_parity_two_ranks(dtype, peer):
+def test_slab_parity_two_ranks(dtype, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
+    peer, extra = MODES[mode]
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
            '--master-port', '29611', os.path.join(ROOT, 'tests', 'multi', 'slab_parity.py'), '--dtype', dtype, '--peer', str(peer)]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=dict(os.environ, **extra))
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
 
