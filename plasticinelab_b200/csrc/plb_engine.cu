@@ -50,6 +50,21 @@ struct plb_engine {
     long long prof_cnt[K_COUNT] = {0};
     cudaStream_t prof_stream = 0;
     cudaStream_t prof_cur = 0;
+    // Programmatic dependent launch of the kernels chained inside the env-step graphs (plb_types.cuh, pdl_wait / pdl_launch):
+    // the launch may become resident while the kernel ahead of it in the stream drains.  Off while profiling (the event pairs
+    // around single kernels should not overlap) and in slab runs (PLB_PDL=0 switches it off altogether).
+    bool pdl_enable = true, pdl_inhibit = false;          // (inhibit: slab runs whose halo needs a launch without pdl_wait between the chained kernels)
+    bool pdl_on() const { return pdl_enable && !prof_on && !pdl_inhibit; }
+    template <class... KArgs, class... Args>
+    void launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+        cudaLaunchKernelEx(&lc, kern, KArgs(std::forward<Args>(args))...);
+    }
     void prof_begin(int kid, cudaStream_t st = nullptr) {
         if (!prof_on) return;
         prof_cur = st ? st : prof_stream;
@@ -190,14 +205,14 @@ struct Engine : plb_engine {
                   bool fused = true;
                   // direct halo (PLB_SLAB_DIRECT=0 disables): scatter kernels RED their zone contributions into the neighbours' grids
                   // (CUDA-IPC mappings of grid_in x2 and g_out x2, alternating by substep parity); an exchange is a completion flag
-                  bool direct = true; Vec4<T>* g_out2 = nullptr; Vec4<T>* peer_grid[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}; } slab;      // fused: env-step block list + one push launch per exchange, receive inside the grid kernels (PLB_SLAB_FUSED=0: the per-substep chain)
+                  bool direct = false; Vec4<T>* g_out2 = nullptr; Vec4<T>* peer_grid[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}; } slab;      // fused: env-step block list + one push launch per exchange, receive inside the grid kernels (PLB_SLAB_FUSED=0: the per-substep chain)
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     bool fuse = true;               // fused G2P+P2G / P2G.grad+G2P.grad particle kernels inside env-step graphs (PLB_FUSE=0 disables)
     bool fwd_plane = false;         // plane (9-node) tile in the forward scatter kernels: 1/3 shared memory (PLB_FWD_PLANE)
     bool bwd_plane = false;         // same for the backward scatter kernels (PLB_BWD_PLANE)
     int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
     int fwd_minb = 5, bwd_minb = 4; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 selects the tighter forward cap, PLB_BWD_MINB=3 the looser backward one)
-    int flush_mode = 0;             // full-tile flush: 0 = per-cell groups, 1 = runs of consecutive lanes (PLB_FLUSH_RUNS=1), 2 = two cells per round (PLB_FLUSH_PAIRS=1)
+    int flush_mode = 3;             // full-tile flush of the per-warp kernels: 3 = runs of consecutive lanes, unrolled (flush_runs, default), 0 = per-cell groups, 1 = runs (first version, PLB_FLUSH_RUNS=1), 2 = two cells per round (PLB_FLUSH_PAIRS=1); PLB_FLUSH_MODE=n
     bool grid_bwd_v2 = true;        // grid adjoint with register-resident pose gradients (k_grid_bwd_sparse_v2); PLB_GRID_BWD_V2=0: array form
     bool env_list = true;           // active-block list built once per env step (dilated by one block) instead of per substep (PLB_ENV_LIST=0: per substep)
     unsigned char* d_flags2 = nullptr; unsigned char* d_listed = nullptr;
@@ -338,6 +353,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_ENV_LIST")) env_list = atoi(v) != 0;
         if (const char* v = getenv("PLB_FLUSH_RUNS")) flush_mode = atoi(v) != 0 ? 1 : 0;
         if (const char* v = getenv("PLB_FLUSH_PAIRS")) flush_mode = atoi(v) != 0 ? 2 : flush_mode;
+        if (const char* v = getenv("PLB_FLUSH_MODE")) flush_mode = std::min(std::max(atoi(v), 0), 3);
         if (const char* v = getenv("PLB_GRID_BWD_V2")) grid_bwd_v2 = atoi(v) != 0;
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
         if (tile_scatter) {
@@ -413,6 +429,8 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_SLAB_FUSED")) slab.fused = atoi(v) != 0;
         if (const char* v = getenv("PLB_SLAB_DIRECT")) slab.direct = atoi(v) != 0;
         if (const char* v = getenv("PLB_TILE_FWD_MINB")) tile_fwd_minb = atoi(v);
+        if (const char* v = getenv("PLB_PDL")) pdl_enable = atoi(v) != 0;
+        if (const char* v = getenv("PLB_SLAB_PUSH_INSIDE")) push_inside = atoi(v) != 0;
         tile_mode = tile_mode && tile_scatter && sparse && fuse;
         tile_bwd = tile_bwd && tile_mode;
         if (tile_mode) {
@@ -727,15 +745,18 @@ struct Engine : plb_engine {
     // forward graphs in env-list mode: single GPU, forward-grid store present
     bool slab_fused() const { return slab.peer_ready && slab.fused && env_list && store.vals; }
     bool env_list_mode() const { return env_list && sparse && tile_scatter && store.vals && (!slab.on || slab_fused()); }
-    // mode: 0 none, 1 fused receive (wait + add the inbox data), 2 direct halo (wait only)
+    // mode: 0 none, 1 fused receive (wait + add the inbox data), 2 direct halo (wait only), 3 send + receive inside the grid kernel
+    bool push_inside = true;        // PLB_SLAB_PUSH_INSIDE=0: separate k_halo_push2 launch ahead of the grid kernel (mode 1)
     HaloIn halo_in(int mode) const {
         HaloIn h;
         for (int side = 0; side < 2; side++) { h.inbox[side] = (mode && slab.has[side]) ? slab.inbox[side] : nullptr; h.g[side] = slab.geom[side]; }
         h.seq = slab.seq; h.err = slab.err; h.on = mode;
+        for (int side = 0; side < 2; side++) { h.peer[side] = (mode == 3 && slab.has[side]) ? slab.peer[side] : nullptr; h.pg[side] = slab.geom[side]; }
+        h.seq_w = slab.seq; h.done = slab.done;
         return h;
     }
     bool slab_direct() const {
-        if (!(slab_fused() && slab.direct && tile_mode && !tile_bwd && flush_mode == 0 && !bwd_plane && cta == kBlock && grid_bwd_v2 && sets[1].in && slab.g_out2)) return false;
+        if (!(slab_fused() && slab.direct && tile_mode && !tile_bwd && (flush_mode == 0 || flush_mode == 3) && !bwd_plane && cta == kBlock && grid_bwd_v2 && sets[1].in && slab.g_out2)) return false;
         for (int side = 0; side < 2; side++)
             if (slab.has[side]) for (int w = 0; w < 4; w++) if (!slab.peer_grid[side][w]) return false;
         return true;
@@ -816,8 +837,8 @@ struct Engine : plb_engine {
                 // (the list in d_list / d_nactive was built by enqueue_env_list for the whole env step)
                 if (slab_fused()) {
                     const bool direct = slab_direct();
-                    if (!direct) halo_push_fused(gin, d_list, d_nactive);
-                    k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gin, grid_out, 1, d_list, d_nactive, store, si, halo_in(direct ? 2 : 1));
+                    if (!direct && !push_inside) halo_push_fused(gin, d_list, d_nactive);
+                    launch_k(pdl_on(), k_grid_fwd_sparse<T>, sparse_ctas(), kBlock, 0, stream, P, prims, d_traj, pf, gin, grid_out, 1, d_list, d_nactive, store, si, halo_in(direct ? 2 : push_inside ? 3 : 1));
                     prof_end();
                     launches++;
                     return;
@@ -842,7 +863,7 @@ struct Engine : plb_engine {
             } else {
                 compact_blocks();
             }
-            k_grid_fwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si, halo_in(0));
+            launch_k(fixed_list && pdl_on(), k_grid_fwd_sparse<T>, sparse_ctas(), kBlock, 0, stream, P, prims, d_traj, pf, grid_in, grid_out, 1, d_list, d_nactive, store, si, halo_in(0));
         } else {
             k_grid_fwd<T><<<blocks(n_nodes), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, 1, n_nodes);
         }
@@ -861,7 +882,9 @@ struct Engine : plb_engine {
         launches += 2;
     }
     // n >= 2 forward substeps with G2P(i-1) and P2G(i) fused into one particle kernel (refs are cursor-relative or absolute)
+    void set_pdl_inhibit() { pdl_inhibit = slab.on && !(slab_fused() && push_inside && !slab_direct()); }
     void enqueue_fwd_fused(int n, SlotRef (*mk)(const Engine*, int, int), bool fixed_list = false) {
+        set_pdl_inhibit();
         const int nb = blocks(cfg.n_particles);
         unsigned char* fl = (sparse && !fixed_list) ? d_flags : nullptr;
         if (fixed_list) enqueue_env_list(mk(this, 0, 0));
@@ -881,15 +904,15 @@ struct Engine : plb_engine {
             for (int i = 1; i < n; i++) {
                 prof_begin(K_G2P_P2G);
                 auto kern = tile_fwd_minb >= 6 ? k_fwd_chunk<T, FWD_G2P | FWD_P2G, TileOcc<T>::fwd_hi> : k_fwd_chunk<T, FWD_G2P | FWD_P2G, TileOcc<T>::fwd>;
-                kern<<<chunk_grid, kBlock, sm, stream>>>(tm_out[0], P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), chunk_table(),
-                                                         grid_out, gin(i), fl, svd_store, svd_warm ? 1 : 0, ph(i), ho);
+                launch_k(fixed_list && pdl_on(), kern, chunk_grid, kBlock, sm, stream, tm_out[0], P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(),
+                         chunk_table(), grid_out, gin(i), fl, svd_store, svd_warm ? 1 : 0, ph(i), ho);
                 prof_end();
                 enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i), fixed_list, gin(i));
                 launches++;
             }
             prof_begin(K_G2P);
-            k_fwd_chunk<T, FWD_G2P, TileOcc<T>::fwd><<<chunk_grid, kBlock, sm, stream>>>(tm_out[0], P, frames, n_pad, mk(this, 0, n - 1), none, mk(this, 1, n - 1), material(),
-                                                                                      chunk_table(), grid_out, grid_in, nullptr, (T*)nullptr, 0, no_peers<Vec4<T>>(), halo_out_none());
+            launch_k(fixed_list && pdl_on(), k_fwd_chunk<T, FWD_G2P, TileOcc<T>::fwd>, chunk_grid, kBlock, sm, stream, tm_out[0], P, frames, n_pad, mk(this, 0, n - 1), none,
+                     mk(this, 1, n - 1), material(), chunk_table(), grid_out, grid_in, (unsigned char*)nullptr, (T*)nullptr, 0, no_peers<Vec4<T>>(), halo_out_none());
             prof_end();
             launches += 2;
             if (fixed_list) enqueue_env_list_check(mk(this, 1, n - 1));
@@ -935,14 +958,15 @@ struct Engine : plb_engine {
         prof_end();
         launches += 2;
     }
+    bool pdl_bwd = false;          // set by enqueue_bwd_fused around the launches that follow a kernel with pdl_launch() in the stream
     void enqueue_bwd_grid_adj(SlotRef pf, const GridSet& gs) {               // (halo of g_out) + grid_op.grad
         const int ng = blocks(n_nodes);
         prof_begin(K_GRID_BWD);
         Vec4<T>* g_out = cur_gout ? cur_gout : this->g_out;
         if (slab_fused() && sparse && grid_bwd_v2) {
             const bool direct = cur_gout_which >= 0;
-            if (!direct) halo_push_fused(g_out, gs.list, gs.count);
-            k_grid_bwd_sparse_v2<T><<<sparse_ctas(148 * 5), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(direct ? 2 : 1));
+            if (!direct && !push_inside) halo_push_fused(g_out, gs.list, gs.count);
+            launch_k(pdl_bwd && pdl_on(), k_grid_bwd_sparse_v2<T>, sparse_ctas(148 * 5), kBlock, 0, stream, P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(direct ? 2 : push_inside ? 3 : 1));
             prof_end();
             launches++;
             return;
@@ -954,7 +978,7 @@ struct Engine : plb_engine {
             launches += 6;
         }
         if (sparse && grid_bwd_v2 && !slab.on)         // (slab runs keep the array form: the register form was validated on one GPU only)
-            k_grid_bwd_sparse_v2<T><<<sparse_ctas(148 * 5), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(0));
+            launch_k(pdl_bwd && pdl_on(), k_grid_bwd_sparse_v2<T>, sparse_ctas(148 * 5), kBlock, 0, stream, P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(0));
         else if (sparse)
             k_grid_bwd_sparse<T><<<sparse_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi());
         else
@@ -1017,8 +1041,8 @@ struct Engine : plb_engine {
         auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo, false>)
                     : svd     ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>)
                               : (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, false>);
-        kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode, svd_store,
-                                       bwd_plane ? no_peers<Vec4<T>>() : gout_peers(), bwd_plane ? halo_out_none() : gout_publish());
+        launch_k(pdl_bwd && pdl_on() && !bwd_plane, kern, nbc, cta, sm, stream, P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode, svd_store,
+                 bwd_plane ? no_peers<Vec4<T>>() : gout_peers(), bwd_plane ? halo_out_none() : gout_publish());
         prof_end();
         launches++;
     }
@@ -1038,6 +1062,8 @@ struct Engine : plb_engine {
     void enqueue_bwd_fused(int n, bool restore, bool next_ok, bool svd, int c, SlotRef (*mk)(const Engine*, int, int), bool overlap) {
         svd = svd && !bwd_plane;
         const bool direct = restore && slab_direct();          // (direct halo: the scatter of substep j and its grid adjoint use the parity-j buffer)
+        struct PdlScope { bool& f; PdlScope(bool& f_) : f(f_) { f = true; } ~PdlScope() { f = false; } } pdl_scope(pdl_bwd);
+        set_pdl_inhibit();
         if (!overlap) {
             enqueue_bwd_grid_pre(mk(this, 0, n - 1), mk(this, 2, n - 1), restore, sets[0], stream);
             select_gout(n - 1, direct);

@@ -191,13 +191,17 @@ struct HaloGeom { int zone_lo, zone_hi, nzb; long long stamps_off, data_off, fla
 
 // What a grid kernel needs to take the neighbours' partial sums itself (fused receive): my two inboxes, their geometry, the
 // exchange counter.  on == 0: no halo (single GPU, or the stage reads an already summed grid).
-struct HaloIn { const char* inbox[2]; HaloGeom g[2]; const int* seq; int* err; int on; };
-__host__ __device__ __forceinline__ HaloIn halo_none() { HaloIn h; h.inbox[0] = h.inbox[1] = nullptr; h.seq = nullptr; h.err = nullptr; h.on = 0; return h; }
+// on == 3: the grid kernel also SENDS (halo_push_share): peer = the neighbours' inboxes (mapped through CUDA IPC), pg = their geometry,
+// seq_w / done = the exchange counter and the CTA counter of the last-CTA publication.
+struct HaloIn { const char* inbox[2]; HaloGeom g[2]; const int* seq; int* err; int on; char* peer[2]; HaloGeom pg[2]; int* seq_w; unsigned* done; };
+__host__ __device__ __forceinline__ HaloIn halo_none() {
+    HaloIn h; h.inbox[0] = h.inbox[1] = nullptr; h.seq = nullptr; h.err = nullptr; h.on = 0; h.peer[0] = h.peer[1] = nullptr; h.seq_w = nullptr; h.done = nullptr; return h;
+}
 
 // thread 0 of the CTA spins until both neighbours have published exchange `s` in MY inboxes (local memory: the neighbour wrote
 // it over NVLink), then the CTA may read what they pushed.  ~4 s timeout -> *err = 1 (reported by the next readback).
-__device__ __forceinline__ int halo_wait_cta(const HaloIn& h) {
-    const int s = *h.seq;
+__device__ __forceinline__ int halo_wait_cta(const HaloIn& h, int s_given = -1) {
+    const int s = s_given >= 0 ? s_given : *h.seq;
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         for (int side = 0; side < 2; side++) {
@@ -338,6 +342,37 @@ __global__ void __launch_bounds__(kBlock) k_halo_push2(int n_grid, const Vec4<T>
         }
     }
     halo_publish_last_cta(peer0, peer1, seq_ptr, done, s);
+}
+// The same push from inside the consuming grid kernel (HaloIn.on == 3): every CTA copies its share of my listed zone blocks of
+// `grid` into the neighbours' inboxes, the last CTA to finish publishes exchange s = *seq + 1 (every CTA read *seq before it
+// counted itself done, so the publisher's update of *seq cannot be seen early).  One launch less per exchange than k_halo_push2 +
+// grid kernel, and the kernel runs its interior blocks while the neighbours' pushes are in flight.
+__device__ __forceinline__ bool halo_zone_block(const HaloIn& h, int n_grid, int blk) {
+    const int nbx = n_grid >> kBlkShift;
+    const int i0 = (blk / (nbx * nbx)) << kBlkShift;
+    return (h.inbox[0] && i0 >= h.g[0].zone_lo && i0 + 4 <= h.g[0].zone_hi) || (h.inbox[1] && i0 >= h.g[1].zone_lo && i0 + 4 <= h.g[1].zone_hi);
+}
+template <class T>
+__device__ __forceinline__ int halo_push_share(const HaloIn& h, int n_grid, const Vec4<T>* grid, const int* __restrict__ list, int n) {
+    const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1), s = *h.seq + 1, par = s & 1;
+    const int nbx = n_grid >> kBlkShift;
+    for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
+        const int blk = list[e];
+        const int i0 = (blk / (nbx * nbx)) << kBlkShift;
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            char* peer = h.peer[side];
+            const HaloGeom& g = h.pg[side];
+            if (!peer || i0 < g.zone_lo || i0 + 4 > g.zone_hi) continue;
+            const int zb = zone_block_index(n_grid, blk, g.zone_lo);
+            int* stamps = reinterpret_cast<int*>(peer + g.stamps_off) + (long long)par * g.nzb;
+            Vec4<T>* data = reinterpret_cast<Vec4<T>*>(peer + g.data_off) + (long long)par * g.nzb * kBlkNodes;
+            data[(long long)zb * kBlkNodes + local] = grid[block_node(n_grid, blk, local)];
+            if (local == 0) stamps[zb] = s;
+        }
+    }
+    halo_publish_last_cta(h.peer[0], h.peer[1], h.seq_w, h.done, s);
+    return s;
 }
 // env-step list exchange: my block flags inside the zones -> the neighbours' inboxes (one byte per zone block), published like a push
 __global__ void k_halo_push_flags(int n_grid, const unsigned char* __restrict__ flags, char* peer0, char* peer1, HaloGeom g0, HaloGeom g1,
@@ -487,6 +522,7 @@ __global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst
                                                                                    const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode, T* svd_base,
                                                                                    PeerHalo<Vec4<T>> ph, HaloOut ho) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_launch();                                              // (the grid adjoint behind this kernel waits for its completion itself)
     SvdPtr<T> sp = svd_at(svd_base, slot_s.get(), n_pad);
     // tight register cap + SVD store: run the (then cheap) forward particle math twice instead of keeping it across the gather
     const bool sent = t_p2g_bwd_g2p_bwd<T, kPlane, kSvd, (kSvd && kMinB >= 4)>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
@@ -504,7 +540,11 @@ __global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimS
     load_poses_smem<T>(traj, pf.get(), P.n_prim, s0, s1);
     const int per_cta = kBlock / kBlkNodes, n = *count;
     const int local = threadIdx.x & (kBlkNodes - 1);
-    const int hs = halo.on ? halo_wait_cta(halo) : 0;          // fused receive: the neighbours' partial sums of this exchange
+    pdl_wait();                                                // the scatter into grid_in is complete
+    pdl_launch();                                              // the next particle kernel may load its particles meanwhile
+    int hs = 0;
+    if (halo.on == 3) hs = halo_push_share<T>(halo, P.n_grid, grid_in, list, n);      // send first; the wait comes after the interior blocks
+    else if (halo.on) hs = halo_wait_cta(halo);                // fused receive: the neighbours' partial sums of this exchange
     Vec4<T>* svals = nullptr; int* sids = nullptr;
     if (store.vals) {
         const long long sl = slot.get();
@@ -515,10 +555,14 @@ __global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimS
             if (n > store.cap) *store.overflow = 1;
         }
     }
+    // on == 3: pass 0 = blocks outside the zones (while the neighbours' pushes arrive), then wait, pass 1 = zone blocks
+    for (int pass = 0; pass < (halo.on == 3 ? 2 : 1); pass++) {
+    if (pass == 1) halo_wait_cta(halo, hs);
     for (int e = blockIdx.x * per_cta + threadIdx.x / kBlkNodes; e < n; e += gridDim.x * per_cta) {
         const int blk = list[e];
+        if (halo.on == 3 && halo_zone_block(halo, P.n_grid, blk) != (pass == 1)) continue;
         const long long node = block_node(P.n_grid, blk, local);
-        if (halo.on == 1) {                                     // (2: direct halo, the neighbours' sums are already in grid_in)
+        if (halo.on == 1 || (halo.on == 3 && pass == 1)) {      // (2: direct halo, the neighbours' sums are already in grid_in)
             Vec4<T> r;
             if (halo_fetch<T>(halo, P.n_grid, blk, local, hs, r)) {
                 const Vec4<T> v = grid_in[node];
@@ -530,6 +574,7 @@ __global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimS
             if (local == 0) sids[e] = blk;
         }
         grid_fwd_body<T>(node, P, prims, s0, s1, grid_in, grid_out, clear_in != 0);
+    }
     }
 }
 
@@ -643,18 +688,25 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse_v2(SimConst<T> P, Pr
     load_poses_smem<T>(traj, pf, P.n_prim, s0, s1);
     const int per_cta = kBlock / kBlkNodes, n = *count;
     const int rounds = (n + gridDim.x * per_cta - 1) / (gridDim.x * per_cta);
-    const int hs = halo.on ? halo_wait_cta(halo) : 0;          // fused receive of the neighbours' adjoint of grid_out
+    pdl_wait();                                                // the scatter into g_out is complete
+    pdl_launch();
+    int hs = 0;
+    if (halo.on == 3) hs = halo_push_share<T>(halo, P.n_grid, g_out, list, n);
+    else if (halo.on) hs = halo_wait_cta(halo);                // fused receive of the neighbours' adjoint of grid_out
+    for (int pass = 0; pass < (halo.on == 3 ? 2 : 1); pass++) {
+    if (pass == 1) halo_wait_cta(halo, hs);
     for (int r = 0; r < rounds; r++) {              // uniform trip count: warp collectives inside
         const int e = (r * gridDim.x + blockIdx.x) * per_cta + threadIdx.x / kBlkNodes;
-        const bool act = e < n;
+        bool act = e < n;
         long long node = 0;
         bool owned = false;
+        if (act && halo.on == 3 && halo_zone_block(halo, P.n_grid, list[e]) != (pass == 1)) act = false;
         if (act) {
             const int blk = list[e], local = threadIdx.x & (kBlkNodes - 1);
             node = block_node(P.n_grid, blk, local);
             const int plane = (int)(node / ((long long)P.n_grid * P.n_grid));
             owned = plane >= own_lo && plane < own_hi;
-            if (halo.on == 1) {
+            if (halo.on == 1 || (halo.on == 3 && pass == 1)) {
                 Vec4<T> q;
                 if (halo_fetch<T>(halo, P.n_grid, blk, local, hs, q)) {
                     const Vec4<T> v = g_out[node];
@@ -663,6 +715,7 @@ __global__ void __launch_bounds__(kBlock) k_grid_bwd_sparse_v2(SimConst<T> P, Pr
             }
         }
         t_grid_bwd_node<T>(act, owned, node, threadIdx.x & 31, P, prims, s0, s1, grid_in, g_out, g_in, clear != 0, prim_grad, pf);
+    }
     }
 }
 

@@ -47,10 +47,12 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    // (with a suspend-time hint: the waiting warp sleeps in the barrier unit instead of re-issuing the poll -- the polls of the
+    //  tile hand-off were 8.7 % of the forward kernel's issued instructions, profiles/r2c_summary.md)
     unsigned ok = 0;
     while (!ok)
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase), "r"(0x989680u) : "memory");
 }
 // box copy of a 4-D tensor (component, k, j, i) into shared memory; completion (bytes) is signalled on `bar`
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, unsigned long long* bar, int c0, int c1, int c2, int c3) {
@@ -92,53 +94,7 @@ __device__ __forceinline__ GridView<T> pick_view(const Vec4<T>* tile, const int 
     return v;
 }
 
-// ------------------------------------------------------------------------------------------------ run-based flush
-__device__ __forceinline__ Vec4<float> add4(Vec4<float> a, Vec4<float> b) {          // two packed FADD2 (sm_100)
-    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
-    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
-    return mk4<float>(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ Vec4<double> add4(Vec4<double> a, Vec4<double> b) { return mk4<double>(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-
-// key: packed base cell of this lane's particle (< 0: none).  All 32 lanes must call.  A run = maximal stretch of consecutive
-// lanes with one key; lane q < 27 sums node q over each run and adds it to the grid with one vector RED.  Columns of lanes
-// without a particle are read but land in a run of their own that is dropped.
-// ph: direct halo (plb_warp.cuh) -- returns true if this lane issued a RED into a neighbour's grid
-template <class T>
-__device__ __forceinline__ bool flush_runs(const Vec4<T>* tile, int lane, int key, int n_grid, Vec4<T>* grid, const PeerHalo<Vec4<T>>& ph) {
-    bool sent = false;
-    __syncwarp();
-    const int next = __shfl_sync(0xffffffffu, key, (lane + 1) & 31);
-    const unsigned ends = __ballot_sync(0xffffffffu, lane == 31 || next != key);
-    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
-    const Vec4<T>* row = tile + (lane < 27 ? lane : 0) * kTileStride;
-    Vec4<T> acc = mk4<T>(T(0), T(0), T(0), T(0));
-#pragma unroll 2
-    for (int g = 0; g < 8; g++) {
-        const Vec4<T> v0 = row[4 * g], v1 = row[4 * g + 1], v2 = row[4 * g + 2], v3 = row[4 * g + 3];
-        const unsigned m = (ends >> (4 * g)) & 0xFu;          // warp-uniform
-        if (m == 0u) {
-            acc = add4(acc, add4(add4(v0, v1), add4(v2, v3)));
-        } else {
-            const Vec4<T> v[4] = {v0, v1, v2, v3};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                acc = add4(acc, v[j]);
-                if ((m >> j) & 1u) {
-                    const int rkey = __shfl_sync(0xffffffffu, key, 4 * g + j);
-                    if (lane < 27 && rkey >= 0) {
-                        const long long node = node_index(n_grid, (rkey >> 20) + oi, ((rkey >> 10) & 1023) + oj, (rkey & 1023) + ok);
-                        scatter_add4(grid + node, acc);
-                        sent = pay_red_peers(ph, node, (rkey >> 20) + oi, acc) || sent;
-                    }
-                    acc = mk4<T>(T(0), T(0), T(0), T(0));
-                }
-            }
-        }
-    }
-    __syncwarp();
-    return sent;
-}
+// (the run-based flush of the scatter tiles, flush_runs, lives in plb_warp.cuh: the per-warp kernels use it too)
 
 // ------------------------------------------------------------------------------------------------ forward
 // kMode = FWD_P2G: P2G of the first substep of a graph (frame s_in -> F' into s_out, scatter)
@@ -154,6 +110,7 @@ k_fwd_chunk(const __grid_constant__ CUtensorMap tm_out, SimConst<T> P, T* frames
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3];          // [0] TMA window, [1..2] scatter-tile hand-off
     unsigned long long& mbar = bars[0];
+    pdl_launch();                                       // (the grid kernel behind this one waits for its completion itself)
     const int n_chunks = *sg.n_chunks;
     const Chunk ch = sg.chunks[blockIdx.x];             // (the table has room for the whole launch grid: both loads are in flight together)
     if ((int)blockIdx.x >= n_chunks) { halo_publish_scatter(ho, false); return; }
@@ -168,12 +125,6 @@ k_fwd_chunk(const __grid_constant__ CUtensorMap tm_out, SimConst<T> P, T* frames
         if (kMode & FWD_P2G) { mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); }
     }
     __syncthreads();
-    if (kMode & FWD_G2P) {
-        if (tid == 0) {
-            mbar_expect_tx(&mbar, (unsigned)(kTileNodes * sizeof(Vec4<T>)));
-            tma_load_4d(gtile, &tm_out, &mbar, 0, o[2], o[1], o[0]);
-        }
-    }
     const bool valid = tid < ch.count;
     const int p = ch.start + tid;
     const FramePtr<T> fin = frame_at(frames, s_in.get(), n_pad);
@@ -195,7 +146,14 @@ k_fwd_chunk(const __grid_constant__ CUtensorMap tm_out, SimConst<T> P, T* frames
         }
         if (kMode & FWD_P2G) load_material(P, mat, p, mu, lam, ys);
     }
+    // everything above reads what the particle kernel two launches back produced (complete: the grid kernel between the two
+    // released this launch only after its own wait) and is in flight now; grid_out / grid_in belong to the grid kernel ahead
+    pdl_wait();
     if (kMode & FWD_G2P) {
+        if (tid == 0) {
+            mbar_expect_tx(&mbar, (unsigned)(kTileNodes * sizeof(Vec4<T>)));
+            tma_load_4d(gtile, &tm_out, &mbar, 0, o[2], o[1], o[0]);
+        }
         mbar_wait(&mbar, 0);
         if (valid) {
             const Stencil<T> st = make_stencil(x, P.inv_dx);

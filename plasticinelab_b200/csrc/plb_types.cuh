@@ -24,6 +24,20 @@
 
 namespace plb {
 
+// Programmatic dependent launch (sm_90+).  Inside the env-step graphs consecutive kernels are chained with programmatic edges
+// (plb_engine.cu, launch_k): a kernel calls pdl_launch() once its dependent may become resident (the dependent then sets up --
+// poses, block list, particle loads -- while this kernel's last wave drains) and pdl_wait() before it first touches anything
+// the kernels ahead of it in the chain produce.  A grid kernel calls pdl_launch() only AFTER its own pdl_wait(), so the
+// particle kernel behind it never starts before the particle kernel ahead of it has completed (its frames are final).
+// Both are no-ops in a kernel launched without the attribute (and on the host).
+#if defined(__CUDA_ARCH__)
+PLB_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PLB_D void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+PLB_D void pdl_wait() {}
+PLB_D void pdl_launch() {}
+#endif
+
 template <class T> struct V3 {
     T x, y, z;
     PLB_HD T& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }

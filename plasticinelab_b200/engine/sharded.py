@@ -94,8 +94,10 @@ class ShardedEnv:
             peer = self.rank - 1 if side == 0 else self.rank + 1
             h = gathered[peer][1 - side]          # the neighbour's inbox that faces me
             eng.call("plb_slab_ipc_import", side, C.create_string_buffer(h, 64))
-        # direct halo: map the neighbours' scatter targets too (grid_in / adjoint of grid_out, even and odd substeps)
-        self.direct = os.environ.get("PLB_SLAB_DIRECT", "1") != "0" and os.environ.get("PLB_BWD_OVERLAP", "1") != "0"
+        # direct halo (opt-in, PLB_SLAB_DIRECT=1): map the neighbours' scatter targets too (grid_in / adjoint of grid_out, even and
+        # odd substeps).  Measured slower than the pushed zone blocks on 2 B200s (4.91e9 vs 5.84e9 particle-substeps/s at slab1m,
+        # profiles/r2c_multi2_timeline.txt): with 8-plane zones 57 % of a 28-plane slab's scatter is duplicated as remote REDs.
+        self.direct = os.environ.get("PLB_SLAB_DIRECT", "0") != "0" and os.environ.get("PLB_BWD_OVERLAP", "1") != "0"
         if self.direct:
             grids = []
             for which in range(4):

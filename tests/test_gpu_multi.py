@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-# halo paths: direct (scatter kernels add into the neighbours' grids over NVLink, default), push (zone blocks pushed into the
-# neighbour's inbox, one launch per exchange), chain (the per-substep launch chain of round 1), host (NCCL send/recv from the host)
-MODES = {'direct': (1, {}), 'push': (1, {'PLB_SLAB_DIRECT': '0'}), 'chain': (1, {'PLB_SLAB_FUSED': '0'}), 'host': (0, {})}
+# halo paths: push (zone blocks pushed into the neighbour's inbox, one launch per exchange, default), direct (scatter kernels add
+# into the neighbours' grids over NVLink, opt-in), chain (the per-substep launch chain of round 1), host (NCCL send/recv from the host)
+MODES = {'direct': (1, {'PLB_SLAB_DIRECT': '1'}), 'push': (1, {}), 'chain': (1, {'PLB_SLAB_FUSED': '0'}), 'host': (0, {})}
 
 
 @pytest.mark.parametrize('mode', sorted(MODES))
