@@ -57,6 +57,10 @@ WORKLOADS = {
     # BASELINE.json configs[0] (the reference's own CPU-runnable case), here as fwd+bwd
     "move10k": dict(scene="move.yml", n=10_000, quality=1, horizon=50,
                     desc="Move-v1 stock, 10k particles, 64^3 grid, 50 env steps x 19 substeps, fwd+bwd"),
+    # a translating body (every particle starts with velocity (2, 0, 2): ~0.5 cells per env step, 5 cells over the episode):
+    # exercises the TMA windows that follow the material (k_chunk_origins; PLB_WINDOW_FOLLOW=0 pins them to the sort-time blocks)
+    "fly1m": dict(scene="move.yml", n=1_000_000, quality=2, horizon=10, v0=(2.0, 0.0, 2.0),
+                  desc="Move-v1 geometry with initial velocity (2, 0, 2), 1M particles, 128^3 grid, 10 env steps x 39 substeps, fwd+bwd"),
     # weak scaling (north_star / BASELINE configs[4]-style): an elastic-plastic bar along the slab axis, 1M particles and
     # 0.109 of the domain (28 planes of 256) per GPU; --gpus N decomposes the N-times-longer bar into N slabs
     "slab1m": dict(scene="slab", n=1_000_000, quality=4, horizon=2,
@@ -297,7 +301,7 @@ class Job:
         self.senv = None
         if self.slab:
             from plasticinelab_b200.engine.sharded import ShardedEnv
-            self.senv = ShardedEnv(self.cfg, dtype=args.dtype, device=local_rank, halo_w=w.get("halo_w", 8),
+            self.senv = ShardedEnv(self.cfg, dtype=args.dtype, device=local_rank, halo_w=int(os.environ.get("PLB_BENCH_HALO_W", w.get("halo_w", 8))),
                                    materials=split_materials if w.get("materials") else None)
             self.env = self.senv.env
         else:
@@ -307,6 +311,10 @@ class Job:
                 self.env.simulator.set_materials(*split_materials(self.env.init_particles))
         env = self.env
         env.loss.set_weights(10, 10, 1, False)
+        if w.get("v0") and not self.slab:
+            st = [np.array(a) for a in env.get_state()["state"]]
+            st[1][:] = np.asarray(w["v0"])
+            env.set_state(st, 666.0, False)
         self.eng = env.engine
         self.ckpt = None
         if w.get("checkpoint"):
@@ -417,7 +425,10 @@ class Job:
             env.loss.set_weights(10, 10, 1, False)
             solver = Solver(env, None, None, n_iters=1, softness=666.0, horizon=Hp)
             solver.total_steps = 0
-            loss, grad = solver.forward(env.get_state()["state"], acts)
+            st = [np.array(a) for a in env.get_state()["state"]]
+            if w.get("v0"):
+                st[1][:] = np.asarray(w["v0"])
+            loss, grad = solver.forward(st, acts)
             x = env.simulator.get_x(env.simulator.cur)
             out[dtype] = (loss, np.array(grad), x)
             env.engine.close()
@@ -542,7 +553,7 @@ def slab_parity(args, wname, rank, world, local_rank, dist):
     for dtype in ("float64", args.dtype):
         cfg, S = build_cfg(w, world)
         mats = split_materials if w.get("materials") else None
-        senv = ShardedEnv(cfg, dtype=dtype, device=local_rank, halo_w=w.get("halo_w", 8), materials=mats)
+        senv = ShardedEnv(cfg, dtype=dtype, device=local_rank, halo_w=int(os.environ.get("PLB_BENCH_HALO_W", w.get("halo_w", 8))), materials=mats)
         senv.env.loss.set_weights(10, 10, 1, False)
         A = senv.env.primitives.action_dim
         acts = actions_for(w, A, 1)
@@ -616,7 +627,10 @@ def main():
         if world == 1:
             par = job.parity()
         else:
-            par = slab_parity(args, args.workload, rank, world, local_rank, dist)
+            try:
+                par = slab_parity(args, args.workload, rank, world, local_rank, dist)
+            except Exception as e:  # noqa: BLE001  (the throughput line is still worth printing; the failure is part of it)
+                par = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -243,6 +243,7 @@ struct Engine : plb_engine {
     // backward chunk kernels (PLB_TILE_BWD=1): measured slower than the per-thread-gather backward kernel on a B200 (171 vs 159 us
     // at 1M particles: the chunk -> TMA -> wait chain at CTA start and instruction-fetch stalls outweigh the shared-memory
     // gathers in a kernel that registers cap at 16 warps per SM either way), so the default backward path keeps the latter
+    bool window_follow = true;      // chunk window origins recomputed from the first frame of every env step (PLB_WINDOW_FOLLOW=0: fixed at the sort)
     bool tile_bwd = false;
     int tile_fwd_minb = 6;          // chunked forward kernel: 6 resident CTAs per SM (80 registers, no spills) | 5 (96 registers): PLB_TILE_FWD_MINB
     bool svd_warm = true;           // Jacobi SVD of substep s+1 started from V of substep s (needs the SVD store; PLB_SVD_WARM=0: from the identity)
@@ -431,6 +432,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_TILE_FWD_MINB")) tile_fwd_minb = atoi(v);
         if (const char* v = getenv("PLB_PDL")) pdl_enable = atoi(v) != 0;
         if (const char* v = getenv("PLB_SLAB_PUSH_INSIDE")) push_inside = atoi(v) != 0;
+        if (const char* v = getenv("PLB_WINDOW_FOLLOW")) window_follow = atoi(v) != 0;
         tile_mode = tile_mode && tile_scatter && sparse && fuse;
         tile_bwd = tile_bwd && tile_mode;
         if (tile_mode) {
@@ -747,6 +749,24 @@ struct Engine : plb_engine {
     bool env_list_mode() const { return env_list && sparse && tile_scatter && store.vals && (!slab.on || slab_fused()); }
     // mode: 0 none, 1 fused receive (wait + add the inbox data), 2 direct halo (wait only), 3 send + receive inside the grid kernel
     bool push_inside = true;        // PLB_SLAB_PUSH_INSIDE=0: separate k_halo_push2 launch ahead of the grid kernel (mode 1)
+    // A grid kernel that sends AND waits (mode 3) must have all its CTAs co-resident: a CTA spinning on the neighbour's flag
+    // would otherwise hold the slot of a CTA of its own kernel that has not pushed yet, and the neighbour -- waiting for that push --
+    // does the same (seen on 2 GPUs with the float64 kernels, whose 194 registers allow 2 CTAs per SM where the launch assumed 5).
+    // The launch is therefore capped by the occupancy the runtime reports for the instantiation.
+    int occ_grid_fwd = 0, occ_grid_bwd = 0;
+    int coresident_cap(bool bwd) {
+        int& occ = bwd ? occ_grid_bwd : occ_grid_fwd;
+        if (occ == 0) {
+            int o = 0;
+            cudaError_t e = bwd ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_grid_bwd_sparse_v2<T>, kBlock, 0)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_grid_fwd_sparse<T>, kBlock, 0);
+            if (e != cudaSuccess) { cudaGetLastError(); o = 1; }
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+            occ = std::max(1, o) * std::max(1, sms);
+        }
+        return occ;
+    }
     HaloIn halo_in(int mode) const {
         HaloIn h;
         for (int side = 0; side < 2; side++) { h.inbox[side] = (mode && slab.has[side]) ? slab.inbox[side] : nullptr; h.g[side] = slab.geom[side]; }
@@ -838,7 +858,7 @@ struct Engine : plb_engine {
                 if (slab_fused()) {
                     const bool direct = slab_direct();
                     if (!direct && !push_inside) halo_push_fused(gin, d_list, d_nactive);
-                    launch_k(pdl_on(), k_grid_fwd_sparse<T>, sparse_ctas(), kBlock, 0, stream, P, prims, d_traj, pf, gin, grid_out, 1, d_list, d_nactive, store, si, halo_in(direct ? 2 : push_inside ? 3 : 1));
+                    launch_k(pdl_on(), k_grid_fwd_sparse<T>, sparse_ctas(std::min(148 * 8, coresident_cap(false))), kBlock, 0, stream, P, prims, d_traj, pf, gin, grid_out, 1, d_list, d_nactive, store, si, halo_in(direct ? 2 : push_inside ? 3 : 1));
                     prof_end();
                     launches++;
                     return;
@@ -888,6 +908,10 @@ struct Engine : plb_engine {
         const int nb = blocks(cfg.n_particles);
         unsigned char* fl = (sparse && !fixed_list) ? d_flags : nullptr;
         if (fixed_list) enqueue_env_list(mk(this, 0, 0));
+        if (tile_mode && window_follow) {          // TMA windows follow the material (k_chunk_origins)
+            k_chunk_origins<T><<<chunk_grid, kBlock, 0, stream>>>(P, frames, n_pad, mk(this, 0, 0), d_chunks, d_nchunks);
+            launches++;
+        }
         if (tile_mode) {
             // chunked kernels: one CTA per <= 128 particles of one grid block, grid_out window by TMA (plb_tile.cuh)
             const size_t sm = chunk_smem_bytes(kFwdTiles);
@@ -966,7 +990,7 @@ struct Engine : plb_engine {
         if (slab_fused() && sparse && grid_bwd_v2) {
             const bool direct = cur_gout_which >= 0;
             if (!direct && !push_inside) halo_push_fused(g_out, gs.list, gs.count);
-            launch_k(pdl_bwd && pdl_on(), k_grid_bwd_sparse_v2<T>, sparse_ctas(148 * 5), kBlock, 0, stream, P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(direct ? 2 : push_inside ? 3 : 1));
+            launch_k(pdl_bwd && pdl_on(), k_grid_bwd_sparse_v2<T>, sparse_ctas(std::min(148 * 5, coresident_cap(true))), kBlock, 0, stream, P, prims, d_traj, pf, gs.in, g_out, g_in, 1, d_prim_grad, gs.list, gs.count, own_lo(), own_hi(), halo_in(direct ? 2 : push_inside ? 3 : 1));
             prof_end();
             launches++;
             return;

@@ -204,10 +204,12 @@ __device__ __forceinline__ int halo_wait_cta(const HaloIn& h, int s_given = -1) 
     const int s = s_given >= 0 ? s_given : *h.seq;
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
+        const volatile int* e = h.err;
         for (int side = 0; side < 2; side++) {
             if (!h.inbox[side]) continue;
             const volatile int* f = reinterpret_cast<const volatile int*>(h.inbox[side]);
             while (f[0] < s) {
+                if (*e == 1) break;                   // an earlier wait of this run timed out: do not spin again (the run is reported invalid)
                 if (clock64() - t0 > 8000000000LL) { *h.err = 1; break; }
             }
         }

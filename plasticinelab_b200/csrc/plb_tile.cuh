@@ -321,6 +321,41 @@ __global__ void k_trivial_chunks(int n, Chunk* chunks, int* n_chunks) {
     if (c == 0) *n_chunks = nch;
     if (c < nch) { Chunk ch; ch.origin = 0; ch.start = c * kChunk; ch.count = min(kChunk, n - c * kChunk); ch.pad = 0; chunks[c] = ch; }
 }
+// Window origins from the particles' CURRENT positions (first frame of an env step): origin = (smallest base cell of the chunk's
+// particles) - 1 per axis.  Right after the sort that is the block's 4 b - 1; later the material has moved, but the particles
+// of a chunk move together, so their base cells still span a few cells and the 8^3 window follows them (spans up to 4 cells
+// plus one cell of drift either way within the env step stay inside; what does not fit reads the dense grid, pick_view).
+// Without this the windows stay where the blocks were at the sort and a translating body leaves them after a few env steps.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_chunk_origins(SimConst<T> P, T* frames, long long n_pad, SlotRef slot, Chunk* chunks, const int* n_chunks) {
+    if ((int)blockIdx.x >= *n_chunks) return;
+    __shared__ int smin[3][kBlock / 32];
+    const Chunk ch = chunks[blockIdx.x];
+    int b[3] = {1 << 20, 1 << 20, 1 << 20};
+    if ((int)threadIdx.x < ch.count) {
+        const V3<T> x = load_x(frame_at(frames, slot.get(), n_pad), ch.start + threadIdx.x);
+#pragma unroll
+        for (int d = 0; d < 3; d++) b[d] = (int)(x[d] * P.inv_dx - T(0.5));
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b[d] = min(b[d], __shfl_xor_sync(0xffffffffu, b[d], o));
+        if ((threadIdx.x & 31) == 0) smin[d][threadIdx.x >> 5] = b[d];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int o[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            int m = smin[d][0];
+#pragma unroll
+            for (int w = 1; w < kBlock / 32; w++) m = min(m, smin[d][w]);
+            o[d] = min(max(m, 0), 1022);          // (origin + 1 is packed into 10 bits per axis; positions are clamped to the domain)
+        }
+        chunks[blockIdx.x].origin = (o[0] << 20) | (o[1] << 10) | o[2];          // (o - 1) + 1 per axis
+    }
+}
 #endif   // __CUDACC__
 
 }  // namespace plb
