@@ -63,7 +63,9 @@ WORKLOADS = {
                   desc="Move-v1 geometry with initial velocity (2, 0, 2), 1M particles, 128^3 grid, 10 env steps x 39 substeps, fwd+bwd"),
     # weak scaling (north_star / BASELINE configs[4]-style): an elastic-plastic bar along the slab axis, 1M particles and
     # 0.109 of the domain (28 planes of 256) per GPU; --gpus N decomposes the N-times-longer bar into N slabs
-    "slab1m": dict(scene="slab", n=1_000_000, quality=4, horizon=2,
+    # (slab runs: 4-plane halo zones -- the material moves less than a plane per env step here; every env step checks that all
+    #  stencils stay inside the slab +- halo, k_check_margin)
+    "slab1m": dict(scene="slab", n=1_000_000, quality=4, horizon=2, halo_w=4,
                    desc="bar (0.109*N) x 0.1 x 0.1 on the ground pressed by two spheres, 1M particles per GPU, 256^3 grid, "
                         "2 env steps x 79 substeps, fwd+bwd"),
     # BASELINE.json configs[2]
