@@ -243,6 +243,17 @@ struct Engine : plb_engine {
     // backward chunk kernels (PLB_TILE_BWD=1): measured slower than the per-thread-gather backward kernel on a B200 (171 vs 159 us
     // at 1M particles: the chunk -> TMA -> wait chain at CTA start and instruction-fetch stalls outweigh the shared-memory
     // gathers in a kernel that registers cap at 16 warps per SM either way), so the default backward path keeps the latter
+    // Env-step re-sort (PLB_RESORT=1): plb_step_fwd re-sorts the particles of its first frame by (block, cell) when that frame was
+    // produced by an earlier env step, so that a moving body keeps few distinct cells per warp (the scatter cost) and fresh TMA
+    // windows.  The permutation q of every re-sorted frame is kept; plb_step_bwd, once it has produced the adjoint of that frame,
+    // puts the adjoint frame, the frame itself and the materials back into the previous env step's order.  order_perm[k] = caller-side
+    // index map of ordering k (0 = the ordering of the last plb_sort_particles), slot_order[s] = ordering frame s is stored in.
+    bool resort = false;
+    std::map<int, int*> resort_q;
+    std::vector<int*> q_spent;
+    std::vector<int*> order_perm;
+    std::vector<int> slot_order;
+    int cur_order = 0;
     bool window_follow = true;      // chunk window origins recomputed from the first frame of every env step (PLB_WINDOW_FOLLOW=0: fixed at the sort)
     bool tile_bwd = false;
     int tile_fwd_minb = 6;          // chunked forward kernel: 6 resident CTAs per SM (80 registers, no spills) | 5 (96 registers): PLB_TILE_FWD_MINB
@@ -268,6 +279,9 @@ struct Engine : plb_engine {
         cudaFree(d_flags); cudaFree(d_list); cudaFree(d_nactive); cudaFree(d_perm); cudaFree(d_perm2); cudaFree(d_keys);
         cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_cub); cudaFree(frame_tmp);
         cudaFree(d_chunks); cudaFree(d_nchunks);
+        for (auto& kv : resort_q) cudaFree(kv.second);
+        for (int* p : q_spent) cudaFree(p);
+        for (int* p : order_perm) cudaFree(p);
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         cudaFree(store.vals); cudaFree(store.ids); cudaFree(store.cnt); cudaFree(store.overflow); cudaFree(d_cursor);
         cudaFree(d_flags2); cudaFree(d_listed);
@@ -433,6 +447,7 @@ struct Engine : plb_engine {
         if (const char* v = getenv("PLB_PDL")) pdl_enable = atoi(v) != 0;
         if (const char* v = getenv("PLB_SLAB_PUSH_INSIDE")) push_inside = atoi(v) != 0;
         if (const char* v = getenv("PLB_WINDOW_FOLLOW")) window_follow = atoi(v) != 0;
+        if (const char* v = getenv("PLB_RESORT")) resort = atoi(v) != 0;
         tile_mode = tile_mode && tile_scatter && sparse && fuse;
         tile_bwd = tile_bwd && tile_mode;
         if (tile_mode) {
@@ -501,7 +516,96 @@ struct Engine : plb_engine {
     int synchronize() override { PLB_CUDA(cudaStreamSynchronize(stream)); return PLB_OK; }
 
     // frame `s` was overwritten from outside a forward substep: its stored grid and the "successor frame" links are stale
-    void slot_written(int s) { stored[s] = 0; fwd_ok[s] = 0; svd_ok[s] = 0; if (s > 0) fwd_ok[s - 1] = 0; }
+    void slot_written(int s) { stored[s] = 0; fwd_ok[s] = 0; svd_ok[s] = 0; if (s > 0) fwd_ok[s - 1] = 0; if (!slot_order.empty()) slot_order[s] = cur_order; }
+    // caller-side index map of the ordering frame `slot` is stored in
+    const int* perm_of_slot(int slot) const {
+        if (slot_order.empty() || order_perm.empty()) return d_perm;
+        const int k = slot_order[slot];
+        return (k == cur_order || k < 0 || k >= (int)order_perm.size()) ? d_perm : order_perm[k];
+    }
+    void clear_orders() {
+        for (auto& kv : resort_q) cudaFree(kv.second);
+        resort_q.clear();
+        for (int* p : q_spent) cudaFree(p);
+        q_spent.clear();
+        for (int* p : order_perm) cudaFree(p);
+        order_perm.clear();
+        cur_order = 0;
+        slot_order.assign(cfg.max_frames, 0);
+    }
+    int push_order() {          // remember the current d_perm as ordering cur_order
+        int* copy = nullptr;
+        PLB_CUDA(cudaMalloc(&copy, n_pad * sizeof(int)));
+        PLB_CUDA(cudaMemcpyAsync(copy, d_perm, n_pad * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        if ((int)order_perm.size() <= cur_order) order_perm.resize(cur_order + 1, nullptr);
+        cudaFree(order_perm[cur_order]);
+        order_perm[cur_order] = copy;
+        return PLB_OK;
+    }
+    bool resort_applies(int slot0) const {
+        return resort && slot0 > 0 && use_graphs && sparse && tile_scatter && !slab.on && !tile_bwd && d_keys && fwd_ok[slot0 - 1] && !resort_q.count(slot0);
+    }
+    // re-sort frame `slot` (produced by the previous env step) in place; nothing is read back to the host
+    int resort_frame(int slot) {
+        const int n = cfg.n_particles;
+        if (order_perm.empty()) { if (int r = push_order()) return r; }          // ordering 0 = what the last plb_sort_particles left
+        k_sort_keys<T><<<blocks(n), kBlock, 0, stream>>>(P, frame_base(slot), n_pad, d_keys, d_vals);
+        int bits = 1;
+        while (bits < 32 && (1ull << bits) < (unsigned long long)n_blocks * 64ull) bits++;
+        PLB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, bits, stream));
+        k_permute_frame<T><<<blocks(n), kBlock, 0, stream>>>(n, n_pad, frame_base(slot), frame_tmp, d_vals2, d_perm, d_perm2);
+        PLB_CUDA(cudaMemcpyAsync(frame_base(slot), frame_tmp, (size_t)24 * n_pad * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        T* mats[3] = {mat_mu, mat_lam, mat_ys};
+        for (int i = 0; i < 3; i++) {
+            if (!mats[i]) continue;
+            k_permute_scalar<T><<<blocks(n), kBlock, 0, stream>>>(n, mats[i], frame_tmp, d_vals2);
+            PLB_CUDA(cudaMemcpyAsync(mats[i], frame_tmp, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        }
+        std::swap(d_perm, d_perm2);
+        inv_perm_valid = false;
+        int* q = nullptr;
+        PLB_CUDA(cudaMalloc(&q, (size_t)n * sizeof(int)));
+        PLB_CUDA(cudaMemcpyAsync(q, d_vals2, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        resort_q[slot] = q;
+        cur_order++;
+        if (int r = push_order()) return r;
+        slot_order[slot] = cur_order;
+        launches += 3;
+        if (tile_mode) {          // chunk table of the new order; its size is checked on the device against the launch grid
+            PLB_CUDA(cudaMemsetAsync(d_nchunks, 0, sizeof(int), stream));
+            k_build_chunks<<<blocks(n), kBlock, 0, stream>>>(n, cfg.n_grid, d_keys2, d_chunks, d_nchunks, chunk_grid, store.overflow);
+            launches++;
+        }
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
+    // after plb_step_bwd has produced the adjoint of frame `slot`: adjoint frame, frame and materials back to the previous ordering
+    int unsort_frame(int slot) {
+        auto it = resort_q.find(slot);
+        if (it == resort_q.end()) return PLB_OK;
+        const int n = cfg.n_particles;
+        const size_t fb = (size_t)24 * n_pad * sizeof(T);
+        k_unpermute_frame<T><<<blocks(n), kBlock, 0, stream>>>(n, n_pad, adj[cur], frame_tmp, it->second);
+        PLB_CUDA(cudaMemcpyAsync(adj[cur], frame_tmp, fb, cudaMemcpyDeviceToDevice, stream));
+        k_unpermute_frame<T><<<blocks(n), kBlock, 0, stream>>>(n, n_pad, frame_base(slot), frame_tmp, it->second);
+        PLB_CUDA(cudaMemcpyAsync(frame_base(slot), frame_tmp, fb, cudaMemcpyDeviceToDevice, stream));
+        T* mats[3] = {mat_mu, mat_lam, mat_ys};
+        for (int i = 0; i < 3; i++) {
+            if (!mats[i]) continue;
+            k_unpermute_scalar<T><<<blocks(n), kBlock, 0, stream>>>(n, mats[i], frame_tmp, it->second);
+            PLB_CUDA(cudaMemcpyAsync(mats[i], frame_tmp, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        }
+        launches += 2;
+        PLB_REQUIRE(cur_order > 0 && cur_order - 1 < (int)order_perm.size() && order_perm[cur_order - 1], "env-step re-sort: ordering stack underflow");
+        cur_order--;
+        PLB_CUDA(cudaMemcpyAsync(d_perm, order_perm[cur_order], n_pad * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        inv_perm_valid = false;
+        slot_order[slot] = cur_order;
+        q_spent.push_back(it->second);          // (still read by the kernels just enqueued: freed at the next plb_sort_particles)
+        resort_q.erase(it);
+        PLB_CUDA(cudaGetLastError());
+        return PLB_OK;
+    }
     int check_slot(int s) { PLB_REQUIRE(s >= 0 && s < cfg.max_frames, "frame slot out of range"); return PLB_OK; }
     int check_pf(int pf, int extra = 0) { PLB_REQUIRE(pf >= 0 && pf + extra < cfg.max_prim_frames, "primitive frame out of range"); return PLB_OK; }
 
@@ -529,11 +633,11 @@ struct Engine : plb_engine {
         if (C) PLB_CUDA(cudaMemcpyAsync(*dC, C, 9 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
         return PLB_OK;
     }
-    int download_aos(T* frame, double* x, double* v, double* F, double* C) {
+    int download_aos(T* frame, double* x, double* v, double* F, double* C, const int* perm = nullptr) {
         size_t n = cfg.n_particles;
         double *dx = x ? d_stage : nullptr, *dv = v ? d_stage + 3 * n : nullptr, *dF = F ? d_stage + 6 * n : nullptr,
                *dC = C ? d_stage + 15 * n : nullptr;
-        k_unpack_frame<T><<<blocks(n), kBlock, 0, stream>>>((int)n, n_pad, frame, d_perm, dx, dv, dF, dC);
+        k_unpack_frame<T><<<blocks(n), kBlock, 0, stream>>>((int)n, n_pad, frame, perm ? perm : d_perm, dx, dv, dF, dC);
         launches++;
         if (x) PLB_CUDA(cudaMemcpyAsync(x, dx, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
         if (v) PLB_CUDA(cudaMemcpyAsync(v, dv, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -555,7 +659,7 @@ struct Engine : plb_engine {
     }
     int get_frame(int slot, double* x, double* v, double* F, double* C) override {
         if (int r = check_slot(slot)) return r;
-        return download_aos(frame_base(slot), x, v, F, C);
+        return download_aos(frame_base(slot), x, v, F, C, perm_of_slot(slot));
     }
     int copy_frame(int src, int dst) override {
         if (int r = check_slot(src)) return r;
@@ -592,6 +696,7 @@ struct Engine : plb_engine {
         }
         std::swap(d_perm, d_perm2);
         inv_perm_valid = false;
+        clear_orders();
         launches += 3;
         if (tile_mode) {
             PLB_CUDA(cudaMemsetAsync(d_nchunks, 0, sizeof(int), stream));
@@ -601,8 +706,11 @@ struct Engine : plb_engine {
             PLB_CUDA(cudaMemcpyAsync(&nch, d_nchunks, sizeof(int), cudaMemcpyDeviceToHost, stream));
             PLB_CUDA(cudaStreamSynchronize(stream));
             PLB_REQUIRE(nch > 0 && nch <= chunk_cap, "chunk table overflow");
-            if (nch > chunk_grid) {                 // (captured graphs hold the launch geometry)
-                chunk_grid = std::min(chunk_cap, nch + nch / 16 + 64);
+            // (captured graphs hold the launch geometry; with the env-step re-sort the table is rebuilt without a read-back, so
+            //  the grid keeps a margin for the block count growing as the body spreads)
+            const int want_grid = std::min(chunk_cap, resort ? nch + nch / 4 + 256 : nch + nch / 16 + 64);
+            if (nch > chunk_grid || (resort && chunk_grid < want_grid)) {
+                chunk_grid = want_grid;
                 drop_graphs();
             }
         }
@@ -1249,8 +1357,10 @@ struct Engine : plb_engine {
             for (int i = 0; i < n; i++) if (int r = substep_fwd(slot0 + i, slot0 + i + 1, pf0 + i)) return r;
             return PLB_OK;
         }
+        if (resort_applies(slot0)) { if (int r = resort_frame(slot0)) return r; }
         GraphKey key{0, n, 0, (store.vals != nullptr ? 1 : 0) | (scan_mode() ? 2 : 0) | (env_list_mode() ? 4 : 0)};
         if (int r = launch_graph(key, slot0, pf0)) return r;
+        if (!slot_order.empty()) for (int i = 1; i <= n; i++) slot_order[slot0 + i] = cur_order;
         for (int i = 0; i < n; i++) { stored[slot0 + i] = store.vals != nullptr; fwd_ok[slot0 + i] = 1; svd_ok[slot0 + i] = svd_store != nullptr; }
         stored[slot0 + n] = 0; fwd_ok[slot0 + n] = 0; svd_ok[slot0 + n] = 0;
         return PLB_OK;
@@ -1265,11 +1375,13 @@ struct Engine : plb_engine {
         bool uniform = (n_stored == 0 || n_stored == n) && n_ok == n;
         if (!use_graphs || !sparse || !uniform) {
             for (int i = n - 1; i >= 0; i--) if (int r = substep_bwd(slot0 + i, pf0 + i)) return r;
+            if (resort_q.count(slot0)) return unsort_frame(slot0);
             return PLB_OK;
         }
         GraphKey key{1, n, cur, ((n_stored == n && store.vals) ? 1 : 0) | 2 | ((n_svd == n && svd_store) ? 4 : 0)};
         if (int r = launch_graph(key, slot0, pf0)) return r;
         cur ^= (n & 1);
+        if (resort_q.count(slot0)) return unsort_frame(slot0);
         return PLB_OK;
     }
 
@@ -1565,6 +1677,12 @@ struct Engine : plb_engine {
                 return PLB_ERR_INVALID;
             }
             if (he) { cudaMemset(slab.err, 0, sizeof(int)); err = "slab halo: timed out waiting for a neighbour's push"; return PLB_ERR_CUDA; }
+        }
+        if (ov == 3) {
+            PLB_CUDA(cudaMemsetAsync(store.overflow, 0, sizeof(int), stream));
+            err = "env-step re-sort: the chunk table outgrew the launch grid of the captured graphs (the body spread over many more 4^3 blocks "
+                  "than at plb_sort_particles); results of this episode are invalid -- run with PLB_RESORT=0";
+            return PLB_ERR_NOMEM;
         }
         if (ov == 2) {
             PLB_CUDA(cudaMemsetAsync(store.overflow, 0, sizeof(int), stream));

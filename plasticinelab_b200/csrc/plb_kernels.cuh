@@ -1005,6 +1005,23 @@ template <class T> __global__ void k_permute_scalar(int n, const T* src, T* dst,
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) dst[j] = src[order[j]];
 }
+// the inverse: dst[order[j]] = src[j] (env-step re-sort: the adjoint frame and the boundary frame go back to the previous env step's order)
+template <class T>
+__global__ void k_unpermute_frame(int n, long long n_pad, const T* src, T* dst, const int* __restrict__ order) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int o = order[j];
+    FramePtr<T> fs = frame_at(const_cast<T*>(src), 0, n_pad), fd = frame_at(dst, 0, n_pad);
+    V3<T> x, v; M3<T> C;
+    load_xvC(fs, j, x, v, C);
+    M3<T> F = load_F(fs, j);
+    store_xvC(fd, o, x, v, C);
+    store_F(fd, o, F);
+}
+template <class T> __global__ void k_unpermute_scalar(int n, const T* src, T* dst, const int* __restrict__ order) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[order[j]] = src[j];
+}
 // ---- policy path: observation gather / observation-adjoint scatter for a handful of particles (caller-order indices)
 __global__ void k_invert_perm(int n, const int* __restrict__ perm, int* inv) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -17,7 +17,7 @@ from test_gpu_parity import _episode_cfg, _target32
 
 pytestmark = pytest.mark.gpu
 
-KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST", "PLB_TILE", "PLB_TILE_BWD", "PLB_TILE_FWD_MINB", "PLB_SVD_WARM", "PLB_FLUSH_MODE", "PLB_PDL", "PLB_WINDOW_FOLLOW"]
+KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST", "PLB_TILE", "PLB_TILE_BWD", "PLB_TILE_FWD_MINB", "PLB_SVD_WARM", "PLB_FLUSH_MODE", "PLB_PDL", "PLB_WINDOW_FOLLOW", "PLB_RESORT"]
 VARIANTS = {
     "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3,
                          PLB_GRID_BWD_V2=0, PLB_FLUSH_RUNS=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_TILE=0),
@@ -51,7 +51,9 @@ VARIANTS.update({
     "svd_cold": dict(PLB_SVD_WARM=0),
     "no_pdl": dict(PLB_PDL=0),                             # env-step graphs without programmatic dependent launch edges
     "window_fixed": dict(PLB_WINDOW_FOLLOW=0),             # TMA windows fixed at the sort (default: re-centred on the material every env step)
-    "flush_groups": dict(PLB_FLUSH_MODE=0),                # per-cell group flush in the per-warp kernels (default: unrolled runs, mode 3)
+    "flush_groups": dict(PLB_FLUSH_MODE=0),
+    "resort": dict(PLB_RESORT=1),                          # particles re-sorted at every env-step boundary, adjoint un-permuted on the way back
+    "resort_no_tile": dict(PLB_RESORT=1, PLB_TILE=0),                # per-cell group flush in the per-warp kernels (default: unrolled runs, mode 3)
     "substep_list_no_svd_pairs": dict(PLB_ENV_LIST=0, PLB_SVD_STORE=0, PLB_BWD_MINB=3, PLB_FLUSH_PAIRS=1),
 })
 
