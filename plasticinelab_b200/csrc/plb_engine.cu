@@ -208,15 +208,12 @@ struct Engine : plb_engine {
                   bool direct = false; Vec4<T>* g_out2 = nullptr; Vec4<T>* peer_grid[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}; } slab;      // fused: env-step block list + one push launch per exchange, receive inside the grid kernels (PLB_SLAB_FUSED=0: the per-substep chain)
     bool tile_scatter = true;       // warp-tile pre-reduced scatters (kernel_variant 0); variant 2 = sparse grid + direct atomics
     bool fuse = true;               // fused G2P+P2G / P2G.grad+G2P.grad particle kernels inside env-step graphs (PLB_FUSE=0 disables)
-    bool fwd_plane = false;         // plane (9-node) tile in the forward scatter kernels: 1/3 shared memory (PLB_FWD_PLANE)
-    bool bwd_plane = false;         // same for the backward scatter kernels (PLB_BWD_PLANE)
-    int cta = kBlock;               // threads per CTA of the scatter kernels, 64 or 128 (PLB_CTA)
+    static constexpr int cta = kBlock;          // threads per CTA of the per-warp scatter kernels
     int fwd_minb = 5, bwd_minb = 4; // register caps of the fused particle kernels (OccSel; PLB_FWD_MINB=6 selects the tighter forward cap, PLB_BWD_MINB=3 the looser backward one)
-    int flush_mode = 3;             // full-tile flush of the per-warp kernels: 3 = runs of consecutive lanes, unrolled (flush_runs, default), 0 = per-cell groups, 1 = runs (first version, PLB_FLUSH_RUNS=1), 2 = two cells per round (PLB_FLUSH_PAIRS=1); PLB_FLUSH_MODE=n
+    int flush_mode = 3;             // full-tile flush of the per-warp kernels: 3 = runs of consecutive lanes (flush_runs, default), 0 = per-cell groups (PLB_FLUSH_MODE=0)
     bool grid_bwd_v2 = true;        // grid adjoint with register-resident pose gradients (k_grid_bwd_sparse_v2); PLB_GRID_BWD_V2=0: array form
     bool env_list = true;           // active-block list built once per env step (dilated by one block) instead of per substep (PLB_ENV_LIST=0: per substep)
     unsigned char* d_flags2 = nullptr; unsigned char* d_listed = nullptr;
-    bool grid_scan = false;         // forward grid stage as one kernel (flag scan + store + grid operator), PLB_GRID_SCAN=1
     bool bwd_overlap = true;        // backward graphs: restore + grid recompute of substep s-1 on a forked branch, overlapping the
                                     // particle kernel and grid adjoint of substep s (needs the second grid set; PLB_BWD_OVERLAP=0 disables)
     // grid set: forward grid (momentum+mass), grid operator output, active-block list.  Set 0 is the working set of the
@@ -301,7 +298,7 @@ struct Engine : plb_engine {
     }
 
     int blocks(long long n, int b = kBlock) const { return (int)((n + b - 1) / b); }
-    static size_t tile_smem_bytes(bool plane, int threads) { return (size_t)(threads / 32) * (plane ? kPlaneVec4 : kTileVec4) * sizeof(Vec4<T>); }
+    static size_t tile_smem_bytes(int threads) { return (size_t)(threads / 32) * kTileVec4 * sizeof(Vec4<T>); }
     Material<T> material() const { Material<T> m; m.mu = mat_mu; m.lam = mat_lam; m.ys = mat_ys; return m; }
     T* frame_base(int slot) const { return frames + (long long)slot * 24 * n_pad; }
 
@@ -357,41 +354,35 @@ struct Engine : plb_engine {
         PLB_REQUIRE(c.n_grid <= 1024, "n_grid above 1024 is not supported (cell keys pack 10 bits per axis)");
         sparse = c.kernel_variant != 1;
         tile_scatter = c.kernel_variant == 0;
-        if (const char* v = getenv("PLB_FWD_PLANE")) fwd_plane = atoi(v) != 0;
-        if (const char* v = getenv("PLB_BWD_PLANE")) bwd_plane = atoi(v) != 0;
-        if (const char* v = getenv("PLB_CTA")) cta = atoi(v) == 64 ? 64 : kBlock;
         if (const char* v = getenv("PLB_FWD_MINB")) fwd_minb = atoi(v);
         if (const char* v = getenv("PLB_BWD_MINB")) bwd_minb = atoi(v);
         if (const char* v = getenv("PLB_BWD_OVERLAP")) bwd_overlap = atoi(v) != 0;
-        if (const char* v = getenv("PLB_GRID_SCAN")) grid_scan = atoi(v) != 0;
         if (const char* v = getenv("PLB_SVD_STORE")) svd_enable = atoi(v) != 0;
         if (const char* v = getenv("PLB_ENV_LIST")) env_list = atoi(v) != 0;
-        if (const char* v = getenv("PLB_FLUSH_RUNS")) flush_mode = atoi(v) != 0 ? 1 : 0;
-        if (const char* v = getenv("PLB_FLUSH_PAIRS")) flush_mode = atoi(v) != 0 ? 2 : flush_mode;
-        if (const char* v = getenv("PLB_FLUSH_MODE")) flush_mode = std::min(std::max(atoi(v), 0), 3);
+        if (const char* v = getenv("PLB_FLUSH_MODE")) flush_mode = atoi(v) == 0 ? 0 : 3;
         if (const char* v = getenv("PLB_GRID_BWD_V2")) grid_bwd_v2 = atoi(v) != 0;
         fuse = c.kernel_variant == 0 && !(getenv("PLB_FUSE") && atoi(getenv("PLB_FUSE")) == 0);
         if (tile_scatter) {
-            const int full = (int)tile_smem_bytes(false, kBlock);
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_warp<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            const int full = (int)tile_smem_bytes(kBlock);
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, OccSel<T>::fwd_lo>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, OccSel<T>::fwd_hi>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_lo, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_hi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_lo, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_hi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, full));
             // the full tiles want the whole shared-memory carve-out (4 x 57 KB per SM); the driver's default choice left the
             // backward kernel at 3 CTAs per SM by shared memory (ncu launch__occupancy_limit_shared_mem)
             const int carve = cudaSharedmemCarveoutMaxShared;
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_warp<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_warp<T>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, OccSel<T>::fwd_lo>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_p2g_warp<T, OccSel<T>::fwd_hi>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_g2p_bwd_warp<T>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_lo, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_hi, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_lo, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PLB_CUDA(cudaFuncSetAttribute(k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_hi, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         }
         n_blocks = (c.n_grid / 4) * (c.n_grid / 4) * (c.n_grid / 4);
         PLB_CUDA(cudaMalloc(&d_flags, n_blocks));
@@ -839,11 +830,6 @@ struct Engine : plb_engine {
         const int want = (listed_est + listed_est / 4 + 1) / 2;
         return std::min(std::max((want + 147) / 148 * 148, 148), wave_cap);
     }
-    int scan_ctas() const { return std::min(std::max((n_blocks + kBlock - 1) / kBlock, 1), 148 * 8); }
-    // forward grid stage as one kernel (k_grid_fwd_scan): single GPU, forward-grid store present, per-CTA list capacity suffices
-    bool scan_mode() const {
-        return grid_scan && !env_list && sparse && tile_scatter && store.vals && !slab.on && (long long)scan_ctas() * kScanCap >= n_blocks;
-    }
     void compact_blocks() {
         cudaMemsetAsync(d_nactive, 0, sizeof(int), stream);
         k_compact<<<(n_blocks + 255) / 256, 256, 0, stream>>>(n_blocks, d_flags, d_list, d_nactive);
@@ -884,7 +870,7 @@ struct Engine : plb_engine {
         return h;
     }
     bool slab_direct() const {
-        if (!(slab_fused() && slab.direct && tile_mode && !tile_bwd && (flush_mode == 0 || flush_mode == 3) && !bwd_plane && cta == kBlock && grid_bwd_v2 && sets[1].in && slab.g_out2)) return false;
+        if (!(slab_fused() && slab.direct && tile_mode && !tile_bwd && grid_bwd_v2 && sets[1].in && slab.g_out2)) return false;
         for (int side = 0; side < 2; side++)
             if (slab.has[side]) for (int w = 0; w < 4; w++) if (!slab.peer_grid[side][w]) return false;
         return true;
@@ -982,12 +968,6 @@ struct Engine : plb_engine {
                                                               slab.listed_stamp, d_list, d_nactive);
                 halo_add_inbox(grid_in);
                 launches += 8;
-            } else if (scan_mode()) {
-                // one kernel: flag scan + store + grid operator (the slot's store counter was zeroed by the caller)
-                k_grid_fwd_scan<T><<<scan_ctas(), kBlock, 0, stream>>>(P, prims, d_traj, pf, grid_in, grid_out, d_flags, n_blocks, store, si);
-                prof_end();
-                launches++;
-                return;
             } else {
                 compact_blocks();
             }
@@ -1055,11 +1035,10 @@ struct Engine : plb_engine {
         prof_end();
         enqueue_grid_fwd_stage(mk(this, 0, 0), mk(this, 2, 0), fixed_list);
         const int nbc = blocks(cfg.n_particles, cta);
-        const size_t sm = tile_smem_bytes(fwd_plane, cta);
+        const size_t sm = tile_smem_bytes(cta);
         for (int i = 1; i < n; i++) {
             prof_begin(K_G2P_P2G);
-            auto kern = fwd_plane ? (fwd_minb >= 6 ? k_g2p_p2g_warp<T, true, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, true, OccSel<T>::fwd_lo>)
-                                  : (fwd_minb >= 6 ? k_g2p_p2g_warp<T, false, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, false, OccSel<T>::fwd_lo>);
+            auto kern = fwd_minb >= 6 ? k_g2p_p2g_warp<T, OccSel<T>::fwd_hi> : k_g2p_p2g_warp<T, OccSel<T>::fwd_lo>;
             kern<<<nbc, cta, sm, stream>>>(P, frames, n_pad, mk(this, 0, i - 1), mk(this, 0, i), mk(this, 1, i), material(), grid_out, grid_in, fl, flush_mode, svd_store);
             prof_end();
             enqueue_grid_fwd_stage(mk(this, 0, i), mk(this, 2, i), fixed_list);
@@ -1129,9 +1108,8 @@ struct Engine : plb_engine {
                 tm_gin, tm_of(gs), P, frames, n_pad, s_next, si, next_ok ? 1 : 0, a_next, a_cur, material(), chunk_table(), g_in, gs.out, g_out, (T*)nullptr);
         } else if (tile_scatter) {
             const int nbc = blocks(cfg.n_particles, cta);
-            const size_t sm = tile_smem_bytes(bwd_plane, cta);
-            if (bwd_plane) k_g2p_bwd_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode, no_peers<Vec4<T>>(), halo_out_none());
-            else k_g2p_bwd_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode, gout_peers(), gout_publish());
+            const size_t sm = tile_smem_bytes(cta);
+            k_g2p_bwd_warp<T><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, next_ok ? 1 : 0, a_next, a_cur, gs.out, g_out, flush_mode, gout_peers(), gout_publish());
         } else {
             k_g2p_bwd<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, a_next, a_cur, gs.out, g_out);
         }
@@ -1155,7 +1133,7 @@ struct Engine : plb_engine {
     }
     void launch_bwd_fused(SlotRef s_cur, SlotRef s_prev, T* a_next, T* a_cur, const GridSet& gs, bool svd) {
         const int nbc = blocks(cfg.n_particles, cta);
-        const size_t sm = tile_smem_bytes(bwd_plane, cta);
+        const size_t sm = tile_smem_bytes(cta);
         Vec4<T>* g_out = cur_gout ? cur_gout : this->g_out;
         prof_begin(K_P2G_BWD_G2P_BWD);
         if (tile_bwd) {
@@ -1169,12 +1147,10 @@ struct Engine : plb_engine {
             launches++;
             return;
         }
-        // (the plane-tile variants are instantiated without the SVD-store form: they lost at every size measured)
-        auto kern = bwd_plane ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, true, OccSel<T>::bwd_lo, false>)
-                    : svd     ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, true> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, true>)
-                              : (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, false, OccSel<T>::bwd_lo, false>);
-        launch_k(pdl_bwd && pdl_on() && !bwd_plane, kern, nbc, cta, sm, stream, P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode, svd_store,
-                 bwd_plane ? no_peers<Vec4<T>>() : gout_peers(), bwd_plane ? halo_out_none() : gout_publish());
+        auto kern = svd ? (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_hi, true> : k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_lo, true>)
+                        : (bwd_minb >= 4 ? k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_hi, false> : k_p2g_bwd_g2p_bwd_warp<T, OccSel<T>::bwd_lo, false>);
+        launch_k(pdl_bwd && pdl_on(), kern, nbc, cta, sm, stream, P, frames, n_pad, s_cur, s_prev, a_next, a_cur, material(), g_in, gs.out, g_out, flush_mode, svd_store,
+                 gout_peers(), gout_publish());
         prof_end();
         launches++;
     }
@@ -1192,7 +1168,6 @@ struct Engine : plb_engine {
     // and runs beside the particle kernel and grid adjoint of substep i; the two grid sets alternate by substep parity:
     //   Pre(j) -> K(j) = [p2g.grad(j+1) +] g2p.grad(j) -> A(j) = grid adjoint(j) -> K(j-1);   Pre(j-2) waits for A(j) (same set).
     void enqueue_bwd_fused(int n, bool restore, bool next_ok, bool svd, int c, SlotRef (*mk)(const Engine*, int, int), bool overlap) {
-        svd = svd && !bwd_plane;
         const bool direct = restore && slab_direct();          // (direct halo: the scatter of substep j and its grid adjoint use the parity-j buffer)
         struct PdlScope { bool& f; PdlScope(bool& f_) : f(f_) { f = true; } ~PdlScope() { f = false; } } pdl_scope(pdl_bwd);
         set_pdl_inhibit();
@@ -1263,9 +1238,8 @@ struct Engine : plb_engine {
         unsigned char* fl = (sparse && mark) ? d_flags : nullptr;
         if (tile_scatter) {
             const int nbc = blocks(cfg.n_particles, cta);
-            const size_t sm = tile_smem_bytes(fwd_plane, cta);
-            if (fwd_plane) k_p2g_warp<T, true><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode, svd_store);
-            else k_p2g_warp<T, false><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode, svd_store);
+            const size_t sm = tile_smem_bytes(cta);
+            k_p2g_warp<T><<<nbc, cta, sm, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, flush_mode, svd_store);
         } else {
             k_p2g<T><<<blocks(cfg.n_particles), kBlock, 0, stream>>>(P, frames, n_pad, si, so, store_F, material(), grid_in, fl, svd_store);
         }
@@ -1280,7 +1254,6 @@ struct Engine : plb_engine {
         if (int r = check_slot(so)) return r;
         if (int r = check_pf(pf, 1)) return r;
         PLB_REQUIRE(si != so, "in-place substep");
-        if (scan_mode()) PLB_CUDA(cudaMemsetAsync(store.cnt + si, 0, sizeof(int), stream));
         enqueue_fwd(abs_ref(si), abs_ref(so), abs_ref(pf));
         slot_written(so);
         stored[si] = store.vals != nullptr;
@@ -1316,8 +1289,7 @@ struct Engine : plb_engine {
         if (prof_on) {
             // profiling (bench.py's live per-kernel times): the SAME kernel sequence as the graph, launched one by one with a
             // CUDA-event pair around every kernel, on the streams the graph's branches were captured from
-            if (key.dir == 0 && scan_mode()) k_set_cursor_zero<<<1, 256, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0, store.cnt, key.n);
-            else k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
+            k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
             launches++;
             enqueue_step(key);
             cudaEvent_t join = next_event();            // (the overlapped backward leaves work on the side stream)
@@ -1341,8 +1313,7 @@ struct Engine : plb_engine {
             cudaGraphDestroy(g);
             it = graphs.emplace(key, ge).first;
         }
-        if (key.dir == 0 && scan_mode()) k_set_cursor_zero<<<1, 256, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0, store.cnt, key.n);
-        else k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
+        k_set_cursor<<<1, 1, 0, stream>>>(d_cursor, slot0, slot0 + 1, pf0);
         PLB_CUDA(cudaGraphLaunch(it->second, stream));
         // kernels + memset nodes inside the replayed graph (the capture counted them once into graph_nodes[key])
         launches += graph_nodes[key] + 1;
@@ -1358,7 +1329,7 @@ struct Engine : plb_engine {
             return PLB_OK;
         }
         if (resort_applies(slot0)) { if (int r = resort_frame(slot0)) return r; }
-        GraphKey key{0, n, 0, (store.vals != nullptr ? 1 : 0) | (scan_mode() ? 2 : 0) | (env_list_mode() ? 4 : 0)};
+        GraphKey key{0, n, 0, (store.vals != nullptr ? 1 : 0) | (env_list_mode() ? 4 : 0)};
         if (int r = launch_graph(key, slot0, pf0)) return r;
         if (!slot_order.empty()) for (int i = 1; i <= n; i++) slot_order[slot0 + i] = cur_order;
         for (int i = 0; i < n; i++) { stored[slot0 + i] = store.vals != nullptr; fwd_ok[slot0 + i] = 1; svd_ok[slot0 + i] = svd_store != nullptr; }

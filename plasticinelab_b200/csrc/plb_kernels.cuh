@@ -471,46 +471,44 @@ __global__ void __launch_bounds__(kBlock) k_p2g(SimConst<T> P, T* frames, long l
     if (flags) mark_blocks<T>(P, load_x(fin, p), flags);
 }
 
-// ---- scatter kernels with the warp tile (plb_warp.cuh); dynamic shared memory = (blockDim / 32) tiles.
-// kPlane: plane tile (4.75 KB / warp) instead of the full tile (14.25 KB / warp).  kCta = threads per CTA (64 or 128): at
-// small particle counts the 64-thread CTAs let one wave hold every warp of the launch.
-template <class T, bool kPlane> __device__ __forceinline__ Vec4<T>* warp_tile_ptr(unsigned char* smem_raw) {
-    return reinterpret_cast<Vec4<T>*>(smem_raw) + (threadIdx.x >> 5) * (kPlane ? kPlaneVec4 : kTileVec4);
+// ---- scatter kernels with the warp tile (plb_warp.cuh); dynamic shared memory = (blockDim / 32) tiles of 14.25 KB.
+template <class T> __device__ __forceinline__ Vec4<T>* warp_tile_ptr(unsigned char* smem_raw) {
+    return reinterpret_cast<Vec4<T>*>(smem_raw) + (threadIdx.x >> 5) * kTileVec4;
 }
 
-template <class T, bool kPlane>
+template <class T>
 __global__ void __launch_bounds__(kBlock) k_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, SlotRef slot_out,
                                                      int store_F_out, Material<T> mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode, T* svd_base) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SvdPtr<T> sp = svd_at(svd_base, slot_in.get(), n_pad);
-    t_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+    t_p2g<T>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T>(smem_raw), P,
                      frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_out.get(), n_pad), store_F_out != 0, mat, grid_in, flags, flush_mode,
                      svd_base ? &sp : nullptr);
 }
 
 // G2P of substep s + P2G of substep s+1 in one pass over the particles (inside env-step graphs)
 // kMinB: resident CTAs per SM requested from ptxas (register cap 65536 / (128 kMinB)): 5 -> 96 registers (what ptxas picks
-// unprompted), 6 -> 80 registers (24 resident warps with the plane tile)
-template <class T, bool kPlane, int kMinB>
+// unprompted), 6 -> 80 registers
+template <class T, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB) k_g2p_p2g_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in,
                                                                            SlotRef slot_mid, SlotRef slot_out, Material<T> mat,
                                                                            const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags, int flush_mode, T* svd_base) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SvdPtr<T> sp = svd_at(svd_base, slot_mid.get(), n_pad);          // the P2G half decomposes F_tmp of frame `mid`
-    t_g2p_p2g<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+    t_g2p_p2g<T>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T>(smem_raw), P,
                          frame_at(frames, slot_in.get(), n_pad), frame_at(frames, slot_mid.get(), n_pad),
                          frame_at(frames, slot_out.get(), n_pad), mat, grid_out, grid_in, flags, flush_mode, svd_base ? &sp : nullptr);
 }
 
 // g2p.grad; next_ok: slot_in + 1 holds the frame G2P produced from slot_in (clamp masks and gather sum are read from it)
-template <class T, bool kPlane>
+template <class T>
 __global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_in, int next_ok,
                                                                            T* adj_next, T* adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode,
                                                                            PeerHalo<Vec4<T>> ph, HaloOut ho) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int si = slot_in.get();
     FramePtr<T> fnext = frame_at(frames, si + 1, n_pad);
-    const bool sent = t_g2p_bwd<T, kPlane>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+    const bool sent = t_g2p_bwd<T>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T>(smem_raw), P,
                          frame_at(frames, si, n_pad), next_ok ? &fnext : nullptr, frame_at(adj_next, 0, n_pad), frame_at(adj_cur, 0, n_pad),
                          grid_out, g_out, flush_mode, ph.any() ? &ph : nullptr);
     halo_publish_scatter(ho, sent);
@@ -518,7 +516,7 @@ __global__ void __launch_bounds__(kBlock, Occ<T>::g2p_bwd) k_g2p_bwd_warp(SimCon
 
 // p2g.grad of substep s + g2p.grad of substep s-1 (inside env-step graphs; frame s was produced by G2P(s-1) there)
 // kSvd: the decomposition of F_tmp(s) comes from the SVD store (written by the forward pass) instead of the Jacobi iteration
-template <class T, bool kPlane, int kMinB, bool kSvd>
+template <class T, int kMinB, bool kSvd>
 __global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst<T> P, T* frames, long long n_pad, SlotRef slot_s,
                                                                                    SlotRef slot_prev, T* adj_next, T* adj_cur, Material<T> mat,
                                                                                    const Vec4<T>* g_in, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode, T* svd_base,
@@ -527,7 +525,7 @@ __global__ void __launch_bounds__(kBlock, kMinB) k_p2g_bwd_g2p_bwd_warp(SimConst
     pdl_launch();                                              // (the grid adjoint behind this kernel waits for its completion itself)
     SvdPtr<T> sp = svd_at(svd_base, slot_s.get(), n_pad);
     // tight register cap + SVD store: run the (then cheap) forward particle math twice instead of keeping it across the gather
-    const bool sent = t_p2g_bwd_g2p_bwd<T, kPlane, kSvd, (kSvd && kMinB >= 4)>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T, kPlane>(smem_raw), P,
+    const bool sent = t_p2g_bwd_g2p_bwd<T, kSvd, (kSvd && kMinB >= 4)>(blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31, warp_tile_ptr<T>(smem_raw), P,
                                        frame_at(frames, slot_s.get(), n_pad), frame_at(frames, slot_prev.get(), n_pad), frame_at(adj_next, 0, n_pad),
                                        frame_at(adj_cur, 0, n_pad), mat, g_in, grid_out, g_out, flush_mode, &sp, ph.any() ? &ph : nullptr);
     halo_publish_scatter(ho, sent);
@@ -578,56 +576,6 @@ __global__ void __launch_bounds__(kBlock) k_grid_fwd_sparse(SimConst<T> P, PrimS
         grid_fwd_body<T>(node, P, prims, s0, s1, grid_in, grid_out, clear_in != 0);
     }
     }
-}
-
-// Forward grid stage in ONE kernel (single-GPU path with the forward-grid store): no separate compaction.  CTA c owns the
-// block ids c, c + G, c + 2G, ... ; it collects its flagged blocks in shared memory (clearing the flags), reserves store
-// entries for them with one atomic on the slot's counter (zeroed beforehand by k_set_cursor_zero / a memset), and runs the
-// grid operator on them.  The active-block list of the substep then exists only in the store (ids), which is all the backward
-// pass reads.  Replaces memset + k_compact + k_grid_fwd_sparse (3 graph nodes per forward substep) by one.
-constexpr int kScanCap = 2048;                  // flagged blocks one CTA can hold
-template <class T>
-__global__ void __launch_bounds__(kBlock) k_grid_fwd_scan(SimConst<T> P, PrimSet<T> prims, const double* traj, SlotRef pf,
-                                                          Vec4<T>* grid_in, Vec4<T>* grid_out, unsigned char* flags, int n_blocks,
-                                                          GridStore<T> store, SlotRef slot) {
-    __shared__ Pose<T> s0[PLB_MAX_PRIM], s1[PLB_MAX_PRIM];
-    __shared__ int s_blk[kScanCap];
-    __shared__ int s_n, s_base;
-    if (threadIdx.x == 0) s_n = 0;
-    load_poses_smem<T>(traj, pf.get(), P.n_prim, s0, s1);          // (ends with __syncthreads)
-    for (int b = blockIdx.x + threadIdx.x * gridDim.x; b < n_blocks; b += gridDim.x * blockDim.x)
-        if (flags[b]) {
-            flags[b] = 0;
-            s_blk[atomicAdd(&s_n, 1)] = b;
-        }
-    __syncthreads();
-    const int n = s_n;
-    if (n == 0) return;
-    const long long sl = slot.get();
-    if (threadIdx.x == 0) {
-        s_base = atomicAdd(store.cnt + sl, n);
-        if (s_base + n > store.cap) *store.overflow = 1;
-    }
-    __syncthreads();
-    const int base = s_base;
-    Vec4<T>* svals = store.vals + sl * store.cap * kBlkNodes;
-    int* sids = store.ids + sl * store.cap;
-    const int per_cta = kBlock / kBlkNodes, local = threadIdx.x & (kBlkNodes - 1);
-    for (int e = threadIdx.x / kBlkNodes; e < n; e += per_cta) {
-        const int blk = s_blk[e];
-        const long long node = block_node(P.n_grid, blk, local);
-        const int idx = base + e;
-        if (idx < store.cap) {
-            svals[(long long)idx * kBlkNodes + local] = grid_in[node];
-            if (local == 0) sids[idx] = blk;
-        }
-        grid_fwd_body<T>(node, P, prims, s0, s1, grid_in, grid_out, true);
-    }
-}
-// cursor + zeroed store counters of the n slots the coming forward graph fills
-__global__ void k_set_cursor_zero(int* cur, int a, int b, int c, int* cnt, int n) {
-    if (threadIdx.x == 0) { cur[0] = a; cur[1] = b; cur[2] = c; }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) cnt[a + i] = 0;
 }
 
 // backward: re-install the stored forward grid of `slot` (values + active list) instead of recomputing P2G

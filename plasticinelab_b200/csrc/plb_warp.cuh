@@ -6,12 +6,9 @@
 // for each group one lane per node sums the group's columns and issues ONE vector RED: atomics drop from
 // 27 x 32 per warp to 27 x (#cells in the warp).
 //
-// Two tile shapes:
-//   * full tile  [27][33] Vec4 (14.25 KB / warp): one flush per particle, lane q < 27 owns node q;
-//   * plane tile [ 9][33] Vec4 ( 4.75 KB / warp): the stencil is produced plane by plane (i = 0,1,2) and flushed after
-//     each plane; lanes 0..26 = (node q = lane % 9, part r = lane / 9), part r sums the group members sitting in lanes
-//     [11 r, 11 r + 11), the three partial sums meet in lanes 0..8 through two shuffles.  A third of the shared memory,
-//     so the scatter kernels are limited by registers, not by shared memory, in resident warps per SM.
+// Tile shape: [27][33] Vec4 (14.25 KB / warp), one flush per particle, lane q < 27 owns node q.  (A 9-node plane tile flushed after
+// every stencil plane, 64-thread CTAs, a paired-cell flush and a one-kernel forward grid stage were measured in round 1 and
+// lost at every size; they were removed in round 2, profiles/r1b_ab_results.md has the numbers.)
 // Column 32 of every row (the padding that makes the transposed read conflict-free) is kept at zero and serves as the
 // "no member" column: the member walk is unrolled by four with independent LDS.
 //
@@ -53,7 +50,6 @@ template <class T> PLB_D void prefetch_frame_rest(const FramePtr<T>& f, int p) {
 constexpr int kTileStride = 33;
 constexpr int kNullCol = 32;
 constexpr int kTileVec4 = 27 * kTileStride;
-constexpr int kPlaneVec4 = 9 * kTileStride;
 
 // base cell packed into one int, 10 bits per axis (n_grid <= 1024); negative = the lane carries no particle
 PLB_HD int pack_cell(int i, int j, int k) { return (i << 20) | (j << 10) | k; }
@@ -146,103 +142,29 @@ PLB_D bool warp_tile_flush(const Pay* tile, int lane, int key, int n_grid, Pay* 
     return sent;
 }
 
-// Paired-group flush: like warp_tile_flush, but two cells are taken per round and their column walks are interleaved, so
-// that the dependent chains of one cell (find member -> LDS -> add) overlap with the other's.  With several cells per warp
-// (6.4 on average at 100k particles / 128^3 once the particles have drifted from their sorted order) the flush is a chain of
-// short latency-bound loops; pairing halves the number of serial rounds.  Same result up to summation order.
-template <class Pay>
-PLB_D void warp_tile_flush_pairs(const Pay* tile, int lane, int key, int n_grid, Pay* grid) {
-    warp_sync();
-    unsigned remaining = warp_ballot(key >= 0);
-    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
-    const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
-    while (remaining) {
-        const int ka = warp_shfl(key, ctz32(remaining));
-        const unsigned ga = warp_ballot(key == ka);
-        remaining &= ~ga;
-        int kb = -1;
-        unsigned gb = 0u;
-        if (remaining) {                                   // warp-uniform
-            kb = warp_shfl(key, ctz32(remaining));
-            gb = warp_ballot(key == kb);
-            remaining &= ~gb;
-        }
-        if (lane < 27) {
-            Pay a, b;
-            pay_zero(a); pay_zero(b);
-            unsigned ua = ga, ub = gb;
-            while (ua | ub) {                              // ub == 0 reads the zero column
-                const int a0 = ctz32(ua); ua &= ua - 1;
-                const int b0 = ctz32(ub); ub &= ub - 1;
-                const int a1 = ctz32(ua); ua &= ua - 1;
-                const int b1 = ctz32(ub); ub &= ub - 1;
-                const Pay va0 = row[a0], vb0 = row[b0], va1 = row[a1], vb1 = row[b1];
-                pay_acc(a, va0); pay_acc(b, vb0); pay_acc(a, va1); pay_acc(b, vb1);
-            }
-            pay_red(grid + node_index(n_grid, (ka >> 20) + oi, ((ka >> 10) & 1023) + oj, (ka & 1023) + ok), a);
-            if (gb) pay_red(grid + node_index(n_grid, (kb >> 20) + oi, ((kb >> 10) & 1023) + oj, (kb & 1023) + ok), b);
-        }
-    }
-    warp_sync();
-}
-
-// Run-based flush: one pass over the 32 columns in lane order; a run = maximal stretch of consecutive lanes with the same
-// cell (after the spatial sort a warp is a few runs; for arbitrary order the result is still correct, the runs just get
-// short).  Lane q < 27 accumulates node q and adds the run's sum to the grid at the run's last column.  No per-cell
-// gather loop: ~7 instructions per column + ~15 per run.  Every column must be defined (lanes without a particle zero theirs).
-template <class Pay>
-PLB_D void warp_tile_flush_runs(const Pay* tile, int lane, int key, int n_grid, Pay* grid) {
-    warp_sync();
-    const int next = warp_shfl(key, (lane + 1) & 31);
-    const unsigned run_end = warp_ballot(lane == 31 || next != key);
-    const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
-    const Pay* row = tile + (lane < 27 ? lane : 0) * kTileStride;
-    Pay acc;
-    pay_zero(acc);
-#pragma unroll 2
-    for (int c = 0; c < 32; c += 4) {
-        Pay v[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = row[c + j];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            pay_acc(acc, v[j]);
-            if ((run_end >> (c + j)) & 1u) {                          // warp-uniform
-                const int rkey = warp_shfl(key, c + j);
-                if (lane < 27 && rkey >= 0)
-                    pay_red(grid + node_index(n_grid, (rkey >> 20) + oi, ((rkey >> 10) & 1023) + oj, (rkey & 1023) + ok), acc);
-                pay_zero(acc);
-            }
-        }
-    }
-    warp_sync();
-}
-// zero this lane's column (lanes without a particle, for the run-based flush)
-template <class Pay> PLB_D void tile_zero_column(Pay* tile, int lane) {
-    Pay z;
-    pay_zero(z);
-#pragma unroll
-    for (int q = 0; q < 27; q++) tile[q * kTileStride + lane] = z;
-}
-#if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------------------ run-based flush
-__device__ __forceinline__ Vec4<float> add4(Vec4<float> a, Vec4<float> b) {          // two packed FADD2 (sm_100)
+#if defined(__CUDA_ARCH__)
+PLB_D Vec4<float> add4(Vec4<float> a, Vec4<float> b) {          // two packed FADD2 (sm_100)
     const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
     const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
     return mk4<float>(lo.x, lo.y, hi.x, hi.y);
 }
-__device__ __forceinline__ Vec4<double> add4(Vec4<double> a, Vec4<double> b) { return mk4<double>(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+#else
+PLB_D Vec4<float> add4(Vec4<float> a, Vec4<float> b) { return mk4<float>(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+#endif
+PLB_D Vec4<double> add4(Vec4<double> a, Vec4<double> b) { return mk4<double>(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // key: packed base cell of this lane's particle (< 0: none).  All 32 lanes must call.  A run = maximal stretch of consecutive
-// lanes with one key; lane q < 27 sums node q over each run and adds it to the grid with one vector RED.  Columns of lanes
-// without a particle are read but land in a run of their own that is dropped.
-// ph: direct halo (plb_warp.cuh) -- returns true if this lane issued a RED into a neighbour's grid
+// lanes with one key (after the spatial sort a warp is a few runs; for an arbitrary order the result is still correct, the runs
+// just get short); lane q < 27 walks the 32 columns of node q once, four LDS.128 at a time, and adds each run's sum to the grid
+// with one vector RED.  Columns of lanes without a particle are read but land in a run of their own that is dropped.
+// ph: direct halo -- returns true if this lane issued a RED into a neighbour's grid
 template <class T>
-__device__ __forceinline__ bool flush_runs(const Vec4<T>* tile, int lane, int key, int n_grid, Vec4<T>* grid, const PeerHalo<Vec4<T>>& ph) {
+PLB_D bool flush_runs(const Vec4<T>* tile, int lane, int key, int n_grid, Vec4<T>* grid, const PeerHalo<Vec4<T>>& ph) {
     bool sent = false;
-    __syncwarp();
-    const int next = __shfl_sync(0xffffffffu, key, (lane + 1) & 31);
-    const unsigned ends = __ballot_sync(0xffffffffu, lane == 31 || next != key);
+    warp_sync();
+    const int next = warp_shfl(key, (lane + 1) & 31);
+    const unsigned ends = warp_ballot(lane == 31 || next != key);
     const int oi = lane / 9, oj = (lane / 3) % 3, ok = lane % 3;
     const Vec4<T>* row = tile + (lane < 27 ? lane : 0) * kTileStride;
     Vec4<T> acc = mk4<T>(T(0), T(0), T(0), T(0));
@@ -258,7 +180,7 @@ __device__ __forceinline__ bool flush_runs(const Vec4<T>* tile, int lane, int ke
             for (int j = 0; j < 4; j++) {
                 acc = add4(acc, v[j]);
                 if ((m >> j) & 1u) {
-                    const int rkey = __shfl_sync(0xffffffffu, key, 4 * g + j);
+                    const int rkey = warp_shfl(key, 4 * g + j);
                     if (lane < 27 && rkey >= 0) {
                         const long long node = node_index(n_grid, (rkey >> 20) + oi, ((rkey >> 10) & 1023) + oj, (rkey & 1023) + ok);
                         scatter_add4(grid + node, acc);
@@ -269,69 +191,23 @@ __device__ __forceinline__ bool flush_runs(const Vec4<T>* tile, int lane, int ke
             }
         }
     }
-    __syncwarp();
+    warp_sync();
     return sent;
 }
-#endif
 
-// mode 0: per-cell groups, mode 1: runs, mode 2: per-cell groups, two cells per round, mode 3: runs, unrolled (flush_runs)
+// mode 3 (default): runs of consecutive lanes (flush_runs: 297 instead of 615 warp instructions per flush in the fused backward
+// kernel, profiles/r2c_summary.md); mode 0: per-cell groups (warp_tile_flush)
 template <class Pay>
 PLB_D bool warp_tile_flush_sel(Pay* tile, int lane, int key, int n_grid, Pay* grid, int mode, const PeerHalo<Pay>* ph = nullptr) {
-#if defined(__CUDACC__)
-    // mode 3 (default on the device): one pass over the columns, four LDS.128 at a time, one RED per run of equal cells
-    // (297 instead of 615 warp instructions per flush in the fused backward kernel, profiles/r2c_summary.md)
-    if (mode == 3) return ph ? flush_runs(tile, lane, key, n_grid, grid, *ph) : flush_runs(tile, lane, key, n_grid, grid, no_peers<Pay>());
-#endif
-    if (ph) return warp_tile_flush(tile, lane, key, n_grid, grid, ph);          // (direct halo: per-cell group flush, or mode 3)
-    if (mode == 1) {
-        if (key < 0) tile_zero_column(tile, lane);
-        warp_tile_flush_runs(tile, lane, key, n_grid, grid);
-    } else if (mode == 2) {
-        warp_tile_flush_pairs(tile, lane, key, n_grid, grid);
-    } else {
-        warp_tile_flush(tile, lane, key, n_grid, grid);
-    }
-    return false;
+    if (mode != 0) return ph ? flush_runs(tile, lane, key, n_grid, grid, *ph) : flush_runs(tile, lane, key, n_grid, grid, no_peers<Pay>());
+    return warp_tile_flush(tile, lane, key, n_grid, grid, ph);
 }
-
-// ------------------------------------------------------------------------------------------------ plane tile
-template <class T> struct WarpPlaneScatter {
-    Vec4<T>* tile; Vec4<T>* grid;
-    int lane, key, n_grid;          // key < 0: this lane carries no particle
-    PLB_D void init() const {       // zero the padding column; the first end_plane() synchronises before any read
-        if (lane < 9) pay_zero(tile[lane * kTileStride + kNullCol]);
-    }
-    PLB_D void add(int slot, int, int, int, Vec4<T> v) const { tile[(slot % 9) * kTileStride + lane] = v; }
-    PLB_D void end_plane(int plane) const {
-        warp_sync();
-        unsigned remaining = warp_ballot(key >= 0);
-        const int q = lane % 9, r = lane / 9;
-        const unsigned part_mask = r == 0 ? 0x000007ffu : (r == 1 ? 0x003ff800u : (r == 2 ? 0xffc00000u : 0u));
-        const Vec4<T>* row = tile + q * kTileStride;
-        while (remaining) {
-            const int leader = ctz32(remaining);
-            const int lkey = warp_shfl(key, leader);
-            const unsigned group = warp_ballot(key == lkey);
-            remaining &= ~group;
-            Vec4<T> acc = tile_row_sum(row, group & part_mask);
-            acc.x += warp_shfl_down(acc.x, 9) + warp_shfl_down(acc.x, 18);
-            acc.y += warp_shfl_down(acc.y, 9) + warp_shfl_down(acc.y, 18);
-            acc.z += warp_shfl_down(acc.z, 9) + warp_shfl_down(acc.z, 18);
-            acc.w += warp_shfl_down(acc.w, 9) + warp_shfl_down(acc.w, 18);
-            if (lane < 9)
-                scatter_add4(grid + node_index(n_grid, (lkey >> 20) + plane, ((lkey >> 10) & 1023) + q / 3, (lkey & 1023) + q % 3), acc);
-        }
-        warp_sync();                // the next plane overwrites the columns
-    }
-};
 
 
 // ================================================================================================
 // Thread-level scatter kernels: what ONE thread of a scatter kernel does, given its particle index, its lane and its warp's
 // tile.  The __global__ wrappers in plb_kernels.cuh only derive (p, lane, tile) from the launch geometry; the host warp
-// emulation (tests/host) calls the same functions.  kPlane selects the plane tile; with it every lane runs the particle
-// math (lanes past the end redo the last particle with key = -1 and store nothing) because the per-plane flush is
-// warp-collective.  With the full tile, lanes past the end skip the math and only take part in the flush.
+// emulation (tests/host) calls the same functions.  Lanes past the end skip the math and only take part in the flush.
 // ================================================================================================
 namespace detail {
 constexpr int kBlkShiftW = 2;          // 4 nodes per active-block edge (same constant as plb_kernels.cuh)
@@ -362,133 +238,87 @@ PLB_HD void mark_blocks(const SimConst<T>& P, V3<T> x, unsigned char* flags) {
 }
 
 // P2G of one substep
-template <class T, bool kPlane>
+template <class T>
 PLB_D void t_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>& fout, bool store_F,
                  const Material<T>& mat, Vec4<T>* grid_in, unsigned char* flags, int flush_mode = 0, const SvdPtr<T>* svd_keep = nullptr) {
     const bool valid = p < P.n_particles;
-    if (kPlane) {
-        if (!valid) p = P.n_particles - 1;
+    tile_init(tile, lane);
+    int key = -1;
+    if (valid) {
+        WarpTileScatter<T> sc{tile, lane};
+        p2g_body<T, WarpTileScatter<T>>(p, P, fin, fout, store_F, mat, sc, svd_keep);
         V3<T> x = load_x(fin, p);
-        WarpPlaneScatter<T> sc{tile, grid_in, lane, valid ? cell_key(x, P.inv_dx) : -1, P.n_grid};
-        sc.init();
-        p2g_body<T, WarpPlaneScatter<T>>(p, P, fin, fout, store_F && valid, mat, sc, svd_keep);
-        if (flags && valid) mark_blocks<T>(P, x, flags);
-    } else {
-        tile_init(tile, lane);
-        int key = -1;
-        if (valid) {
-            WarpTileScatter<T> sc{tile, lane};
-            p2g_body<T, WarpTileScatter<T>>(p, P, fin, fout, store_F, mat, sc, svd_keep);
-            V3<T> x = load_x(fin, p);
-            key = cell_key(x, P.inv_dx);
-            if (flags) mark_blocks<T>(P, x, flags);
-        }
-        warp_tile_flush_sel(tile, lane, key, P.n_grid, grid_in, flush_mode);
+        key = cell_key(x, P.inv_dx);
+        if (flags) mark_blocks<T>(P, x, flags);
     }
+    warp_tile_flush_sel(tile, lane, key, P.n_grid, grid_in, flush_mode);
 }
 
 // G2P of substep s (frame fin -> fmid) + P2G of substep s+1 (F from fmid, F' to fout), keyed on the ADVECTED position
-template <class T, bool kPlane>
+template <class T>
 PLB_D void t_g2p_p2g(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>& fmid,
                      const FramePtr<T>& fout, const Material<T>& mat, const Vec4<T>* grid_out, Vec4<T>* grid_in, unsigned char* flags,
                      int flush_mode = 0, const SvdPtr<T>* svd_keep = nullptr) {
     const bool valid = p < P.n_particles;
-    if (kPlane) {
-        if (!valid) p = P.n_particles - 1;
-        M3<T> F = load_F(fmid, p);                 // issued before the gather: the stores below may alias for the compiler
+    tile_init(tile, lane);
+    int key = -1;
+    if (valid) {
+        M3<T> F = load_F(fmid, p);             // issued before the gather: the stores below may alias for the compiler
         T mu, lam, ys;
         load_material(P, mat, p, mu, lam, ys);
         V3<T> nx, nv; M3<T> nC;
         g2p_core<T>(P, load_x(fin, p), grid_out, nx, nv, nC);
-        if (valid) store_xvC(fmid, p, nx, nv, nC);
-        WarpPlaneScatter<T> sc{tile, grid_in, lane, valid ? cell_key(nx, P.inv_dx) : -1, P.n_grid};
-        sc.init();
+        store_xvC(fmid, p, nx, nv, nC);
         M3<T> new_F;
+        WarpTileScatter<T> sc{tile, lane};
         SvdRec<T> rec;
-        p2g_core<T, WarpPlaneScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc, svd_keep ? &rec : nullptr);
-        if (valid) {
-            store_F(fout, p, new_F);
-            if (svd_keep) store_svd(*svd_keep, p, rec);
-            if (flags) mark_blocks<T>(P, nx, flags);
-        }
-    } else {
-        tile_init(tile, lane);
-        int key = -1;
-        if (valid) {
-            M3<T> F = load_F(fmid, p);             // issued before the gather: the stores below may alias for the compiler
-            T mu, lam, ys;
-            load_material(P, mat, p, mu, lam, ys);
-            V3<T> nx, nv; M3<T> nC;
-            g2p_core<T>(P, load_x(fin, p), grid_out, nx, nv, nC);
-            store_xvC(fmid, p, nx, nv, nC);
-            M3<T> new_F;
-            WarpTileScatter<T> sc{tile, lane};
-            SvdRec<T> rec;
-            p2g_core<T, WarpTileScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc, svd_keep ? &rec : nullptr);
-            store_F(fout, p, new_F);
-            if (svd_keep) store_svd(*svd_keep, p, rec);
-            key = cell_key(nx, P.inv_dx);
-            if (flags) mark_blocks<T>(P, nx, flags);
-        }
-        warp_tile_flush_sel(tile, lane, key, P.n_grid, grid_in, flush_mode);
+        p2g_core<T, WarpTileScatter<T>>(P, nx, nv, nC, F, mu, lam, ys, new_F, sc, svd_keep ? &rec : nullptr);
+        store_F(fout, p, new_F);
+        if (svd_keep) store_svd(*svd_keep, p, rec);
+        key = cell_key(nx, P.inv_dx);
+        if (flags) mark_blocks<T>(P, nx, flags);
     }
+    warp_tile_flush_sel(tile, lane, key, P.n_grid, grid_in, flush_mode);
 }
 
 // g2p.grad of one substep (state frame fin; fnext = the frame G2P produced, or null pointers => recompute the gather sum)
-template <class T, bool kPlane>
+template <class T>
 PLB_D bool t_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fin, const FramePtr<T>* fnext,
                      const FramePtr<T>& adj_next, const FramePtr<T>& adj_cur, const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0,
                      const PeerHalo<Vec4<T>>* ph = nullptr) {
     const bool valid = p < P.n_particles;
-    if (kPlane) {
-        if (!valid) p = P.n_particles - 1;
+    tile_init(tile, lane);
+    int key = -1;
+    if (valid) {
         V3<T> x = load_x(fin, p);
-        WarpPlaneScatter<T> sc{tile, g_out, lane, valid ? cell_key(x, P.inv_dx) : -1, P.n_grid};
-        sc.init();
+        WarpTileScatter<T> sc{tile, lane};
         V3<T> gxn, gvn; M3<T> gCn;
         load_xvC(adj_next, p, gxn, gvn, gCn);
         V3<T> gx;
         if (fnext) {
             Vec4<T> q0 = fnext->A0[p], q1 = fnext->A1[p];
-            gx = g2p_bwd_core<T, WarpPlaneScatter<T>, true>(P, x, gxn, gvn, gCn, grid_out, sc, mk3<T>(q0.x, q0.y, q0.z), mk3<T>(q0.w, q1.x, q1.y));
+            gx = g2p_bwd_core<T, WarpTileScatter<T>, true>(P, x, gxn, gvn, gCn, grid_out, sc, mk3<T>(q0.x, q0.y, q0.z), mk3<T>(q0.w, q1.x, q1.y));
         } else {
-            gx = g2p_bwd_core<T, WarpPlaneScatter<T>, false>(P, x, gxn, gvn, gCn, grid_out, sc, zero3<T>(), zero3<T>());
+            gx = g2p_bwd_core<T, WarpTileScatter<T>, false>(P, x, gxn, gvn, gCn, grid_out, sc, zero3<T>(), zero3<T>());
         }
-        if (valid) adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
-    } else {
-        tile_init(tile, lane);
-        int key = -1;
-        if (valid) {
-            V3<T> x = load_x(fin, p);
-            WarpTileScatter<T> sc{tile, lane};
-            V3<T> gxn, gvn; M3<T> gCn;
-            load_xvC(adj_next, p, gxn, gvn, gCn);
-            V3<T> gx;
-            if (fnext) {
-                Vec4<T> q0 = fnext->A0[p], q1 = fnext->A1[p];
-                gx = g2p_bwd_core<T, WarpTileScatter<T>, true>(P, x, gxn, gvn, gCn, grid_out, sc, mk3<T>(q0.x, q0.y, q0.z), mk3<T>(q0.w, q1.x, q1.y));
-            } else {
-                gx = g2p_bwd_core<T, WarpTileScatter<T>, false>(P, x, gxn, gvn, gCn, grid_out, sc, zero3<T>(), zero3<T>());
-            }
-            adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
-            key = cell_key(x, P.inv_dx);
-        }
-        return warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode, ph);
+        adj_cur.A0[p] = mk4<T>(gx.x, gx.y, gx.z, T(0));
+        key = cell_key(x, P.inv_dx);
     }
-    return false;
+    return warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode, ph);
 }
 
 // p2g.grad of substep s (frame fs) + g2p.grad of substep s-1 (frame fprev); the adjoint of (x,v,C)[s] stays in registers and
 // the state (x,v)[s] this thread loaded anyway is what G2P(s-1) produced (clamp masks + gather sum come from it)
-template <class T, bool kPlane, bool kSvdGiven = false, bool kTwoPhase = false>
+template <class T, bool kSvdGiven = false, bool kTwoPhase = false>
 PLB_D bool t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& P, const FramePtr<T>& fs, const FramePtr<T>& fprev,
                              const FramePtr<T>& next, const FramePtr<T>& cur, const Material<T>& mat, const Vec4<T>* g_in,
                              const Vec4<T>* grid_out, Vec4<T>* g_out, int flush_mode = 0, const SvdPtr<T>* svd_kept = nullptr,
                              const PeerHalo<Vec4<T>>* ph = nullptr) {
     const bool valid = p < P.n_particles;
     if (valid) prefetch_frame_rest(fprev, p);          // for the next backward kernel (p2g.grad of substep s-1)
-    if (kPlane) {
-        if (!valid) p = P.n_particles - 1;
+    tile_init(tile, lane);
+    int key = -1;
+    if (valid) {
         V3<T> x, v; M3<T> C;
         load_xvC(fs, p, x, v, C);
         M3<T> F = load_F(fs, p);
@@ -498,43 +328,20 @@ PLB_D bool t_p2g_bwd_g2p_bwd(int p, int lane, Vec4<T>* tile, const SimConst<T>& 
         V3<T> gx, gv; M3<T> gC, gF;
         SvdRec<T> rec;
         if (kSvdGiven) rec = load_svd(*svd_kept, p);
-        p2g_bwd_core<T, kSvdGiven, kTwoPhase>(P, x, v, C, F, mu, lam, ys, g_in, kTwoPhase ? zeroM<T>() : load_F(next, p), mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF,
-                                                      &rec, &next, p, &fs);
-        if (valid) store_F(cur, p, gF);
+        const M3<T> gF_next = kTwoPhase ? zeroM<T>() : load_F(next, p);
+        pdl_wait();          // g_in (grid adjoint of this substep) is final; the particle loads above are already in flight
+        p2g_bwd_core<T, kSvdGiven, kTwoPhase>(P, x, v, C, F, mu, lam, ys, g_in, gF_next, mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF,
+                                              &rec, &next, p, &fs);
+        store_F(cur, p, gF);
         V3<T> xp = load_x(fprev, p);
-        WarpPlaneScatter<T> sc{tile, g_out, lane, valid ? cell_key(xp, P.inv_dx) : -1, P.n_grid};
-        sc.init();
-        V3<T> gxp = g2p_bwd_core<T, WarpPlaneScatter<T>, true>(P, xp, gx, gv, gC, grid_out, sc, x, v);
-        if (valid) next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
+        WarpTileScatter<T> sc{tile, lane};
+        V3<T> gxp = g2p_bwd_core<T, WarpTileScatter<T>, true>(P, xp, gx, gv, gC, grid_out, sc, x, v);
+        next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
+        key = cell_key(xp, P.inv_dx);
     } else {
-        tile_init(tile, lane);
-        int key = -1;
-        if (valid) {
-            V3<T> x, v; M3<T> C;
-            load_xvC(fs, p, x, v, C);
-            M3<T> F = load_F(fs, p);
-            T mu, lam, ys;
-            load_material(P, mat, p, mu, lam, ys);
-            Vec4<T> part = cur.A0[p];
-            V3<T> gx, gv; M3<T> gC, gF;
-            SvdRec<T> rec;
-            if (kSvdGiven) rec = load_svd(*svd_kept, p);
-            const M3<T> gF_next = kTwoPhase ? zeroM<T>() : load_F(next, p);
-            pdl_wait();          // g_in (grid adjoint of this substep) is final; the particle loads above are already in flight
-            p2g_bwd_core<T, kSvdGiven, kTwoPhase>(P, x, v, C, F, mu, lam, ys, g_in, gF_next, mk3<T>(part.x, part.y, part.z), gx, gv, gC, gF,
-                                                  &rec, &next, p, &fs);
-            store_F(cur, p, gF);
-            V3<T> xp = load_x(fprev, p);
-            WarpTileScatter<T> sc{tile, lane};
-            V3<T> gxp = g2p_bwd_core<T, WarpTileScatter<T>, true>(P, xp, gx, gv, gC, grid_out, sc, x, v);
-            next.A0[p] = mk4<T>(gxp.x, gxp.y, gxp.z, T(0));
-            key = cell_key(xp, P.inv_dx);
-        } else {
-            pdl_wait();
-        }
-        return warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode, ph);
+        pdl_wait();
     }
-    return false;
+    return warp_tile_flush_sel(tile, lane, key, P.n_grid, g_out, flush_mode, ph);
 }
 
 // mass-only scatter of the loss (scalar payload, full tile of scalars)

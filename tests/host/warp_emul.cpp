@@ -78,13 +78,13 @@ template <class T> struct World {
     }
 };
 
-template <class T, bool kPlane>
+template <class T, bool kTwoPhase>
 int check(const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x, const double* v, const double* F,
           const double* C, const double* pose0, const double* pose1, const double* gx, const double* gv, const double* gF,
           const double* gC, int stored_next, int flush_mode, int svd_store, double* out) {
     World<T> R(*c, pd, softness, pose0, pose1), W(*c, pd, softness, pose0, pose1);
     const int n = c->n_particles;
-    const int tile_elems = kPlane ? kPlaneVec4 : kTileVec4;
+    const int tile_elems = kTileVec4;
     int o = 0;
     // ------------------------------------------------ reference: sequential direct-scatter bodies
     R.pack(R.f[0], x, v, F, C);
@@ -123,7 +123,7 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     SvdPtr<T> sv0 = svd_at(svd.data(), 0, W.n_pad), sv1 = svd_at(svd.data(), 1, W.n_pad);
     // (1) P2G of substep 0
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), true, W.mat, W.grid_in.data(), W.flags.data(), flush_mode, svd_store ? &sv0 : nullptr);
+        t_p2g<T>(p, lane, tile, W.P, W.fr(0), W.fr(1), true, W.mat, W.grid_in.data(), W.flags.data(), flush_mode, svd_store ? &sv0 : nullptr);
     });
     out[o++] = rel_dev(W.grid_in, ref_in0);
     {   // flags: exactly the blocks touched by a particle stencil
@@ -134,7 +134,7 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     W.grid_op(W.grid_out[0]);
     // (2) fused G2P(0) + P2G(1)
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_g2p_p2g<T, kPlane>(p, lane, tile, W.P, W.fr(0), W.fr(1), W.fr(2), W.mat, W.grid_out[0].data(), W.grid_in.data(), nullptr, flush_mode, svd_store ? &sv1 : nullptr);
+        t_g2p_p2g<T>(p, lane, tile, W.P, W.fr(0), W.fr(1), W.fr(2), W.mat, W.grid_out[0].data(), W.grid_in.data(), nullptr, flush_mode, svd_store ? &sv1 : nullptr);
     });
     out[o++] = rel_dev(W.grid_in, ref_in1);
     out[o++] = rel_dev(W.f[1].data(), R.f[1].data(), W.f[1].size());
@@ -149,7 +149,7 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     W.pack(W.adj[2], gx, gv, gF, gC);
     FramePtr<T> wf2 = W.fr(2);
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
-        t_g2p_bwd<T, kPlane>(p, lane, tile, W.P, W.fr(1), stored_next ? &wf2 : nullptr, W.ad(2), W.ad(1), W.grid_out[1].data(), W.g_out.data(), flush_mode);
+        t_g2p_bwd<T>(p, lane, tile, W.P, W.fr(1), stored_next ? &wf2 : nullptr, W.ad(2), W.ad(1), W.grid_out[1].data(), W.g_out.data(), flush_mode);
     });
     out[o++] = rel_dev(W.g_out, ref_gout1);
     out[o++] = rel_dev(W.adj[1].data(), ref_adj1_partial.data(), W.adj[1].size());
@@ -157,9 +157,9 @@ int check(const plb_config* c, const plb_primitive_desc* pd, double softness, co
     // (4) fused p2g.grad(1) + g2p.grad(0)
     W.template launch<Vec4<T>>(tile_elems, [&](int p, int lane, Vec4<T>* tile) {
         if (svd_store)
-            t_p2g_bwd_g2p_bwd<T, kPlane, true, kPlane>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode, &sv1);
+            t_p2g_bwd_g2p_bwd<T, true, kTwoPhase>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode, &sv1);
         else
-            t_p2g_bwd_g2p_bwd<T, kPlane, false>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode);
+            t_p2g_bwd_g2p_bwd<T, false>(p, lane, tile, W.P, W.fr(1), W.fr(0), W.ad(2), W.ad(1), W.mat, W.g_in.data(), W.grid_out[0].data(), W.g_out.data(), flush_mode);
     });
     out[o++] = rel_dev(W.g_out, ref_gout0);
     {   // dF[1] (F planes of adj 1) and the partial x-adjoint of frame 0 (written into adj 2's A0 plane)
@@ -240,13 +240,13 @@ int check_grid_bwd(const plb_config* c, const plb_primitive_desc* pd, double sof
 
 }  // namespace
 
-extern "C" int wemul_check(int dtype, int plane, const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x,
+extern "C" int wemul_check(int dtype, int two_phase, const plb_config* c, const plb_primitive_desc* pd, double softness, const double* x,
                            const double* v, const double* F, const double* C, const double* pose0, const double* pose1, const double* gx,
                            const double* gv, const double* gF, const double* gC, int stored_next, int flush_mode, int svd_store, double* out) {
     if (dtype == PLB_F32)
-        return plane ? check<float, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out)
+        return two_phase ? check<float, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out)
                      : check<float, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out);
-    return plane ? check<double, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out)
+    return two_phase ? check<double, true>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out)
                  : check<double, false>(c, pd, softness, x, v, F, C, pose0, pose1, gx, gv, gF, gC, stored_next, flush_mode, svd_store, out);
 }
 

@@ -16,9 +16,9 @@ from plasticinelab_b200 import _capi
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("PLB_TEST_LARGE") == "0", reason="full-size cases switched off (PLB_TEST_LARGE=0)")]
 D = _capi.dptr
-KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE",
-        "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST", "PLB_TILE", "PLB_TILE_BWD", "PLB_TILE_FWD_MINB", "PLB_SVD_WARM"]
-CONSERVATIVE = dict(PLB_BWD_OVERLAP=0, PLB_GRID_BWD_V2=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_BWD_MINB=3, PLB_TILE=0)
+KEYS = ["PLB_BWD_OVERLAP", "PLB_FWD_MINB", "PLB_BWD_MINB", "PLB_FUSE", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_ENV_LIST", "PLB_TILE", "PLB_TILE_BWD",
+        "PLB_TILE_FWD_MINB", "PLB_SVD_WARM", "PLB_FLUSH_MODE", "PLB_PDL", "PLB_WINDOW_FOLLOW", "PLB_RESORT"]
+CONSERVATIVE = dict(PLB_BWD_OVERLAP=0, PLB_GRID_BWD_V2=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_BWD_MINB=3, PLB_TILE=0, PLB_PDL=0, PLB_FLUSH_MODE=0)
 CASES = {      # name -> (scene file, particles, quality, env steps)
     "move1m_128": ("move.yml", 1_000_000, 2, 2),          # north-star roofline size
     "rope1m_256": ("rope.yml", 1_000_000, 4, 1),          # BASELINE config 3 (about 28 particles per cell)

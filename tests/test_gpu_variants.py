@@ -1,8 +1,8 @@
 """GPU test: every selectable kernel variant of the engine produces the same episode (loss, action gradient, final state).
 
-The variants are chosen with environment switches read at plb_create (plb_engine.cu): tile shape of the scatter kernels
-(full 27-node tile / 9-node plane tile), register caps of the fused particle kernels, CTA size, the one-kernel forward grid
-stage and the forked grid pre-stage of the backward graphs.  The conservative configuration (everything serial, full tiles)
+The variants are chosen with environment switches read at plb_create (plb_engine.cu): chunked TMA-window kernels or per-thread
+gathers, register caps of the fused particle kernels, SVD records, block list per env step or per substep, flush of the scatter
+tiles, programmatic dependent launch, the forked grid pre-stage of the backward graphs, env-step re-sort.  The conservative configuration (everything serial, full tiles)
 is compared against the float64 oracle by tests/test_gpu_parity.py; here all other variants are compared with it on the
 same episode, in one process.  Tolerances: float64 1e-10 on the loss, 1e-7 on the gradient (summation order only); float32 1e-6 on the loss,
 2e-5 on the gradient, 2e-6 on positions (about 10x what a B200 measured: <= 5e-9, 1.8e-6, 1.8e-7, gpurun_out/ab/pytest_variants.log).
@@ -17,32 +17,21 @@ from test_gpu_parity import _episode_cfg, _target32
 
 pytestmark = pytest.mark.gpu
 
-KEYS = ["PLB_BWD_OVERLAP", "PLB_GRID_SCAN", "PLB_FWD_PLANE", "PLB_FWD_MINB", "PLB_BWD_PLANE", "PLB_BWD_MINB", "PLB_CTA", "PLB_FUSE", "PLB_FLUSH_RUNS", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_FLUSH_PAIRS", "PLB_ENV_LIST", "PLB_TILE", "PLB_TILE_BWD", "PLB_TILE_FWD_MINB", "PLB_SVD_WARM", "PLB_FLUSH_MODE", "PLB_PDL", "PLB_WINDOW_FOLLOW", "PLB_RESORT"]
+KEYS = ["PLB_BWD_OVERLAP", "PLB_FWD_MINB", "PLB_BWD_MINB", "PLB_FUSE", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_ENV_LIST", "PLB_TILE", "PLB_TILE_BWD",
+        "PLB_TILE_FWD_MINB", "PLB_SVD_WARM", "PLB_FLUSH_MODE", "PLB_PDL", "PLB_WINDOW_FOLLOW", "PLB_RESORT"]
 VARIANTS = {
-    "conservative": dict(PLB_BWD_OVERLAP=0, PLB_GRID_SCAN=0, PLB_FWD_PLANE=0, PLB_BWD_PLANE=0, PLB_CTA=128, PLB_FWD_MINB=5, PLB_BWD_MINB=3,
-                         PLB_GRID_BWD_V2=0, PLB_FLUSH_RUNS=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_TILE=0),
+    # everything serial and per substep: per-thread gathers, per-cell group flush, no SVD records, array-form grid adjoint, no PDL
+    "conservative": dict(PLB_BWD_OVERLAP=0, PLB_FWD_MINB=5, PLB_BWD_MINB=3, PLB_GRID_BWD_V2=0, PLB_FLUSH_MODE=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0,
+                         PLB_TILE=0, PLB_PDL=0, PLB_WINDOW_FOLLOW=0),
     "defaults": {},
-    "overlap": dict(PLB_BWD_OVERLAP=1),
-    "scan": dict(PLB_GRID_SCAN=1),
-    "plane": dict(PLB_FWD_PLANE=1, PLB_BWD_PLANE=1),
-    "tight": dict(PLB_FWD_MINB=6, PLB_BWD_MINB=4),
-    "cta64": dict(PLB_CTA=64),
-    "everything": dict(PLB_BWD_OVERLAP=1, PLB_GRID_SCAN=1, PLB_FWD_PLANE=1, PLB_FWD_MINB=6, PLB_BWD_PLANE=1, PLB_BWD_MINB=4, PLB_CTA=64),
     "unfused": dict(PLB_FUSE=0),
     "grid_bwd_arrays": dict(PLB_GRID_BWD_V2=0),
-    "runs": dict(PLB_FLUSH_RUNS=1),
-    "runs_unfused_cta64": dict(PLB_FLUSH_RUNS=1, PLB_FUSE=0, PLB_CTA=64),
-}
-
-
-# (first green run on a B200: round 2, gpurun_out/ab/pytest_variants.log; SVD store + 128-register cap + env-step block list are the defaults since)
-VARIANTS.update({
     "no_svd_store": dict(PLB_SVD_STORE=0),
     "svd_store_loose": dict(PLB_SVD_STORE=1, PLB_BWD_MINB=3),
-    "flush_pairs": dict(PLB_FLUSH_PAIRS=1),
     "substep_list": dict(PLB_ENV_LIST=0),
     # chunked TMA-window kernels (plb_tile.cuh) are the default since round 2; PLB_TILE=0 = the per-thread-gather kernels
     "no_tile": dict(PLB_TILE=0),
+    "no_tile_tight": dict(PLB_TILE=0, PLB_FWD_MINB=6),
     "tile_no_svd_store": dict(PLB_SVD_STORE=0, PLB_BWD_MINB=3),
     "tile_serial_bwd": dict(PLB_BWD_OVERLAP=0),
     "tile_bwd": dict(PLB_TILE_BWD=1),                      # chunked backward kernels too (slower on a B200, kept selectable)
@@ -51,11 +40,11 @@ VARIANTS.update({
     "svd_cold": dict(PLB_SVD_WARM=0),
     "no_pdl": dict(PLB_PDL=0),                             # env-step graphs without programmatic dependent launch edges
     "window_fixed": dict(PLB_WINDOW_FOLLOW=0),             # TMA windows fixed at the sort (default: re-centred on the material every env step)
-    "flush_groups": dict(PLB_FLUSH_MODE=0),
+    "flush_groups": dict(PLB_FLUSH_MODE=0),                # per-cell group flush in the per-warp kernels (default: runs of consecutive lanes)
     "resort": dict(PLB_RESORT=1),                          # particles re-sorted at every env-step boundary, adjoint un-permuted on the way back
-    "resort_no_tile": dict(PLB_RESORT=1, PLB_TILE=0),                # per-cell group flush in the per-warp kernels (default: unrolled runs, mode 3)
-    "substep_list_no_svd_pairs": dict(PLB_ENV_LIST=0, PLB_SVD_STORE=0, PLB_BWD_MINB=3, PLB_FLUSH_PAIRS=1),
-})
+    "resort_no_tile": dict(PLB_RESORT=1, PLB_TILE=0),
+    "substep_list_no_svd_groups": dict(PLB_ENV_LIST=0, PLB_SVD_STORE=0, PLB_BWD_MINB=3, PLB_FLUSH_MODE=0),
+}
 
 
 def _run(monkeypatch, env_vars, dtype):

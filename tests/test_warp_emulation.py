@@ -1,6 +1,6 @@
 """CPU tests of the warp-level scatter kernels (plasticinelab_b200/csrc/plb_warp.cuh).
 
-The shared-memory tile scatter, its per-cell flush (full tile and plane tile) and the thread-level kernels the __global__
+The shared-memory tile scatter, its flush (runs of consecutive lanes and per-cell groups) and the thread-level kernels the __global__
 wrappers call are executed on 32 lock-stepped host threads per warp (tests/host/warp_emul.hpp) and compared with the
 sequential direct-scatter bodies, which tests/test_host_emulation.py pins against the float64 oracle.  Differences come
 from the summation order only: 1e-12 relative in float64, 3e-4 in float32 (the SVD adjoint amplifies the 1e-7 differences of the gathered grid adjoint).
@@ -45,13 +45,14 @@ def _state(n, seed, box, sort, n_grid):
 PRIMS = [dict(shape='Sphere', radius=0.05, init_pos=(0.47, 0.5, 0.5), friction=0.9, action=dict(dim=3, scale=(0.01,) * 3))]
 
 
-@pytest.mark.parametrize('plane,flush_mode,svd_store', [(0, 0, 0), (0, 1, 0), (0, 2, 0), (1, 0, 0), (0, 0, 1), (1, 0, 1)])
+# flush_mode 3 = runs of consecutive lanes (the device default), 0 = per-cell groups; two_phase = the 128-register backward form (needs the SVD records)
+@pytest.mark.parametrize('two_phase,flush_mode,svd_store', [(0, 3, 0), (0, 0, 0), (0, 3, 1), (1, 3, 1), (1, 0, 1)])
 @pytest.mark.parametrize('dtype,tol', [('float64', 1e-12), ('float32', 3e-4)])
 @pytest.mark.parametrize('n,box,sort,stored_next', [(100, (0.40, 0.52), True, 1),     # ~2 particles per cell, ragged last warp
                                                     (70, (0.45, 0.50), True, 1),      # one or two cells per warp
                                                     (64, (0.30, 0.70), False, 0),     # unsorted: 32 one-lane groups per warp
                                                     (40, (0.02, 0.12), True, 0)])     # at the domain corner (clamps, boundary)
-def test_warp_scatter_kernels_match_direct_bodies(wemul_lib, plane, flush_mode, svd_store, dtype, tol, n, box, sort, stored_next):
+def test_warp_scatter_kernels_match_direct_bodies(wemul_lib, two_phase, flush_mode, svd_store, dtype, tol, n, box, sort, stored_next):
     cfg = H.small_cfg(PRIMS, n_particles=n, yield_stress=30.0)
     conf, parr, _ = H.c_setup(cfg, n, dtype)
     x, v, Cm, F = _state(n, 3, box, sort, conf.n_grid)
@@ -59,11 +60,11 @@ def test_warp_scatter_kernels_match_direct_bodies(wemul_lib, plane, flush_mode, 
     pose0 = H.pose_array([[0.47, 0.5, 0.5, 1, 0, 0, 0]])
     pose1 = H.pose_array([[0.4702, 0.4999, 0.5001, 1, 0, 0, 0]])
     out = np.full(16, np.nan)
-    k = wemul_lib.wemul_check(conf.dtype, plane, C.byref(conf), parr, C.c_double(666.0), D(x), D(v), D(F), D(Cm), D(pose0), D(pose1),
+    k = wemul_lib.wemul_check(conf.dtype, two_phase, C.byref(conf), parr, C.c_double(666.0), D(x), D(v), D(F), D(Cm), D(pose0), D(pose1),
                               D(gx), D(gv), D(gF), D(gC), stored_next, flush_mode, svd_store, D(out))
     assert k == len(NAMES)
     for name, dev in zip(NAMES, out[:k]):
-        assert dev <= tol, f"{name}: deviation {dev:.3e} (plane={plane}, flush_mode={flush_mode}, svd_store={svd_store}, {dtype})"
+        assert dev <= tol, f"{name}: deviation {dev:.3e} (two_phase={two_phase}, flush_mode={flush_mode}, svd_store={svd_store}, {dtype})"
 
 
 @pytest.mark.parametrize('dtype,tol', [('float64', 1e-12), ('float32', 2e-5)])
