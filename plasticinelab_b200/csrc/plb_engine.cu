@@ -240,14 +240,17 @@ struct Engine : plb_engine {
     // backward chunk kernels (PLB_TILE_BWD=1): measured slower than the per-thread-gather backward kernel on a B200 (171 vs 159 us
     // at 1M particles: the chunk -> TMA -> wait chain at CTA start and instruction-fetch stalls outweigh the shared-memory
     // gathers in a kernel that registers cap at 16 warps per SM either way), so the default backward path keeps the latter
-    // Env-step re-sort (PLB_RESORT=1): plb_step_fwd re-sorts the particles of its first frame by (block, cell) when that frame was
-    // produced by an earlier env step, so that a moving body keeps few distinct cells per warp (the scatter cost) and fresh TMA
-    // windows.  The permutation q of every re-sorted frame is kept; plb_step_bwd, once it has produced the adjoint of that frame,
-    // puts the adjoint frame, the frame itself and the materials back into the previous env step's order.  order_perm[k] = caller-side
-    // index map of ordering k (0 = the ordering of the last plb_sort_particles), slot_order[s] = ordering frame s is stored in.
-    bool resort = false;
+    // Env-step re-sort (default; PLB_RESORT=0 switches it off): plb_step_fwd re-sorts the particles of its first frame by (block, cell)
+    // when that frame was produced by an earlier env step, so that a moving body keeps few distinct cells per warp (the scatter cost:
+    // +41 % on a translating body, +4 % on a 10-step Move episode at 1M particles, neutral at 100k; profiles/r2h_resort_timeline.txt).
+    // The permutation q of every re-sorted frame is kept; plb_step_bwd, once it has produced the adjoint of that frame, puts the
+    // adjoint frame, the frame itself and the materials back into the previous env step's order.  order_perm[k] = caller-side index
+    // map of ordering k (0 = the ordering of the last plb_sort_particles), slot_order[s] = ordering frame s is stored in.
+    // Not used in slab runs, with the chunked backward kernels, or on frames that were not produced by plb_step_fwd.
+    bool resort = true;
     std::map<int, int*> resort_q;
-    std::vector<int*> q_spent;
+    std::vector<int*> q_spent;          // free list of permutation buffers (stream-ordered reuse)
+    int orders_valid = 0;               // order_perm[0 .. orders_valid) hold orderings of the current episode
     std::vector<int*> order_perm;
     std::vector<int> slot_order;
     int cur_order = 0;
@@ -510,27 +513,23 @@ struct Engine : plb_engine {
     void slot_written(int s) { stored[s] = 0; fwd_ok[s] = 0; svd_ok[s] = 0; if (s > 0) fwd_ok[s - 1] = 0; if (!slot_order.empty()) slot_order[s] = cur_order; }
     // caller-side index map of the ordering frame `slot` is stored in
     const int* perm_of_slot(int slot) const {
-        if (slot_order.empty() || order_perm.empty()) return d_perm;
+        if (slot_order.empty() || orders_valid == 0) return d_perm;
         const int k = slot_order[slot];
-        return (k == cur_order || k < 0 || k >= (int)order_perm.size()) ? d_perm : order_perm[k];
+        return (k == cur_order || k < 0 || k >= orders_valid) ? d_perm : order_perm[k];
     }
+    // (the permutation buffers are pooled: cudaMalloc / cudaFree per env step would serialise the host with the device)
     void clear_orders() {
-        for (auto& kv : resort_q) cudaFree(kv.second);
+        for (auto& kv : resort_q) q_spent.push_back(kv.second);
         resort_q.clear();
-        for (int* p : q_spent) cudaFree(p);
-        q_spent.clear();
-        for (int* p : order_perm) cudaFree(p);
-        order_perm.clear();
         cur_order = 0;
+        orders_valid = 0;
         slot_order.assign(cfg.max_frames, 0);
     }
     int push_order() {          // remember the current d_perm as ordering cur_order
-        int* copy = nullptr;
-        PLB_CUDA(cudaMalloc(&copy, n_pad * sizeof(int)));
-        PLB_CUDA(cudaMemcpyAsync(copy, d_perm, n_pad * sizeof(int), cudaMemcpyDeviceToDevice, stream));
         if ((int)order_perm.size() <= cur_order) order_perm.resize(cur_order + 1, nullptr);
-        cudaFree(order_perm[cur_order]);
-        order_perm[cur_order] = copy;
+        if (!order_perm[cur_order]) PLB_CUDA(cudaMalloc(&order_perm[cur_order], n_pad * sizeof(int)));
+        PLB_CUDA(cudaMemcpyAsync(order_perm[cur_order], d_perm, n_pad * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        orders_valid = std::max(orders_valid, cur_order + 1);
         return PLB_OK;
     }
     bool resort_applies(int slot0) const {
@@ -539,7 +538,7 @@ struct Engine : plb_engine {
     // re-sort frame `slot` (produced by the previous env step) in place; nothing is read back to the host
     int resort_frame(int slot) {
         const int n = cfg.n_particles;
-        if (order_perm.empty()) { if (int r = push_order()) return r; }          // ordering 0 = what the last plb_sort_particles left
+        if (orders_valid == 0) { if (int r = push_order()) return r; }          // ordering 0 = what the last plb_sort_particles left
         k_sort_keys<T><<<blocks(n), kBlock, 0, stream>>>(P, frame_base(slot), n_pad, d_keys, d_vals);
         int bits = 1;
         while (bits < 32 && (1ull << bits) < (unsigned long long)n_blocks * 64ull) bits++;
@@ -555,7 +554,8 @@ struct Engine : plb_engine {
         std::swap(d_perm, d_perm2);
         inv_perm_valid = false;
         int* q = nullptr;
-        PLB_CUDA(cudaMalloc(&q, (size_t)n * sizeof(int)));
+        if (!q_spent.empty()) { q = q_spent.back(); q_spent.pop_back(); }
+        else PLB_CUDA(cudaMalloc(&q, n_pad * sizeof(int)));
         PLB_CUDA(cudaMemcpyAsync(q, d_vals2, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, stream));
         resort_q[slot] = q;
         cur_order++;
@@ -587,12 +587,12 @@ struct Engine : plb_engine {
             PLB_CUDA(cudaMemcpyAsync(mats[i], frame_tmp, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
         }
         launches += 2;
-        PLB_REQUIRE(cur_order > 0 && cur_order - 1 < (int)order_perm.size() && order_perm[cur_order - 1], "env-step re-sort: ordering stack underflow");
+        PLB_REQUIRE(cur_order > 0 && cur_order - 1 < orders_valid && order_perm[cur_order - 1], "env-step re-sort: ordering stack underflow");
         cur_order--;
         PLB_CUDA(cudaMemcpyAsync(d_perm, order_perm[cur_order], n_pad * sizeof(int), cudaMemcpyDeviceToDevice, stream));
         inv_perm_valid = false;
         slot_order[slot] = cur_order;
-        q_spent.push_back(it->second);          // (still read by the kernels just enqueued: freed at the next plb_sort_particles)
+        q_spent.push_back(it->second);          // (back to the pool: the next user is enqueued behind the kernels that still read it)
         resort_q.erase(it);
         PLB_CUDA(cudaGetLastError());
         return PLB_OK;
@@ -657,6 +657,7 @@ struct Engine : plb_engine {
         if (int r = check_slot(dst)) return r;
         if (src == dst) return PLB_OK;
         slot_written(dst);
+        if (!slot_order.empty()) slot_order[dst] = slot_order[src];          // (a copy keeps the ordering it was stored in)
         PLB_CUDA(cudaMemcpyAsync(frame_base(dst), frame_base(src), (size_t)24 * n_pad * sizeof(T), cudaMemcpyDeviceToDevice, stream));
         return PLB_OK;
     }
@@ -1268,6 +1269,9 @@ struct Engine : plb_engine {
         enqueue_bwd(abs_ref(si), abs_ref(pf), stored[si] && store.vals, fwd_ok[si] != 0, svd_ok[si] && svd_store, adj[cur], adj[cur ^ 1]);
         cur ^= 1;
         PLB_CUDA(cudaGetLastError());
+        // (a forward pass made of plb_step_fwd calls may be differentiated substep by substep, like the reference's substep_grad loop:
+        //  the adjoint of a re-sorted frame goes back to the previous ordering here as well)
+        if (resort_q.count(si)) return unsort_frame(si);
         return PLB_OK;
     }
 
@@ -1346,7 +1350,6 @@ struct Engine : plb_engine {
         bool uniform = (n_stored == 0 || n_stored == n) && n_ok == n;
         if (!use_graphs || !sparse || !uniform) {
             for (int i = n - 1; i >= 0; i--) if (int r = substep_bwd(slot0 + i, pf0 + i)) return r;
-            if (resort_q.count(slot0)) return unsort_frame(slot0);
             return PLB_OK;
         }
         GraphKey key{1, n, cur, ((n_stored == n && store.vals) ? 1 : 0) | 2 | ((n_svd == n && svd_store) ? 4 : 0)};

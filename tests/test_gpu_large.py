@@ -18,7 +18,7 @@ pytestmark = [pytest.mark.gpu,
 D = _capi.dptr
 KEYS = ["PLB_BWD_OVERLAP", "PLB_FWD_MINB", "PLB_BWD_MINB", "PLB_FUSE", "PLB_GRID_BWD_V2", "PLB_SVD_STORE", "PLB_ENV_LIST", "PLB_TILE", "PLB_TILE_BWD",
         "PLB_TILE_FWD_MINB", "PLB_SVD_WARM", "PLB_FLUSH_MODE", "PLB_PDL", "PLB_WINDOW_FOLLOW", "PLB_RESORT"]
-CONSERVATIVE = dict(PLB_BWD_OVERLAP=0, PLB_GRID_BWD_V2=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_BWD_MINB=3, PLB_TILE=0, PLB_PDL=0, PLB_FLUSH_MODE=0)
+CONSERVATIVE = dict(PLB_BWD_OVERLAP=0, PLB_GRID_BWD_V2=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0, PLB_BWD_MINB=3, PLB_TILE=0, PLB_PDL=0, PLB_FLUSH_MODE=0, PLB_RESORT=0)
 CASES = {      # name -> (scene file, particles, quality, env steps)
     "move1m_128": ("move.yml", 1_000_000, 2, 2),          # north-star roofline size
     "rope1m_256": ("rope.yml", 1_000_000, 4, 1),          # BASELINE config 3 (about 28 particles per cell)

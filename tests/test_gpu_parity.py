@@ -105,6 +105,44 @@ def _target32(env):
     return t * (env.n_particles * env.simulator.p_mass / t.sum())
 
 
+def test_substep_grad_loop_equals_tape_f64():
+    """The reference's notebook differentiates an episode by hand: loss kernel adjoint, then `substep_grad(s)` for every substep in
+    reverse (`long_term_gradient.ipynb` cell 4).  Forward through `env.step` (env-step graphs, particles re-sorted at env-step
+    boundaries) + backward through that loop must give the tape's gradient: the adjoint frame is put back into the previous env
+    step's particle order on either path."""
+    from plasticinelab_b200.engine.taichi_env import TaichiEnv
+    from plasticinelab_b200.optimizer.solver import Solver
+    cfg = _episode_cfg()
+    env = TaichiEnv(cfg, dtype='float64')
+    env.initialize()
+    env.loss.load_target_density(grids=_target32(env))
+    env.loss.set_weights(10, 10, 1, False)
+    actions = np.random.RandomState(3).uniform(-1, 1, (3, 6))
+    solver = Solver(env, None, None, n_iters=1, softness=666., horizon=3)
+    solver.total_steps = 0
+    state = env.get_state()['state']
+    loss0, grad0 = solver.forward(state, actions)
+    x_mid_tape = env.simulator.get_x(env.simulator.substeps)          # a frame of the first env step, read after the sweep
+    # by hand
+    env.set_state(state, 666., False)
+    eng, S = env.simulator.engine, env.simulator.substeps
+    eng.call("plb_zero_grads")
+    for a in actions:
+        env.step(a)
+        env.compute_loss()
+    loss1 = env.loss.loss[None]
+    x_mid = env.simulator.get_x(S)                                    # ... and before it (stored in the first env step's ordering)
+    for i in reversed(range(len(actions))):
+        eng.call("plb_loss_bwd", (i + 1) * S, (i + 1) * S)
+        for s in reversed(range(i * S, (i + 1) * S)):
+            env.simulator.substep_grad(s)
+    grad1 = env.primitives.get_grad(len(actions))
+    H.record("substep_grad_loop", loss=abs(loss1 - loss0) / abs(loss0), grad=H.relerr(grad1, grad0))
+    assert abs(loss1 - loss0) < 1e-12 * abs(loss0)
+    assert H.relerr(grad1, grad0) < 1e-9
+    assert np.abs(x_mid - x_mid_tape).max() < 1e-12
+
+
 @pytest.mark.parametrize('dtype', ['float64', 'float32'])
 @pytest.mark.parametrize('contact_all', [True, False])
 def test_episode_loss_and_action_gradient(dtype, contact_all):

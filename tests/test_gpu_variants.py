@@ -22,7 +22,7 @@ KEYS = ["PLB_BWD_OVERLAP", "PLB_FWD_MINB", "PLB_BWD_MINB", "PLB_FUSE", "PLB_GRID
 VARIANTS = {
     # everything serial and per substep: per-thread gathers, per-cell group flush, no SVD records, array-form grid adjoint, no PDL
     "conservative": dict(PLB_BWD_OVERLAP=0, PLB_FWD_MINB=5, PLB_BWD_MINB=3, PLB_GRID_BWD_V2=0, PLB_FLUSH_MODE=0, PLB_SVD_STORE=0, PLB_ENV_LIST=0,
-                         PLB_TILE=0, PLB_PDL=0, PLB_WINDOW_FOLLOW=0),
+                         PLB_TILE=0, PLB_PDL=0, PLB_WINDOW_FOLLOW=0, PLB_RESORT=0),
     "defaults": {},
     "unfused": dict(PLB_FUSE=0),
     "grid_bwd_arrays": dict(PLB_GRID_BWD_V2=0),
@@ -41,8 +41,8 @@ VARIANTS = {
     "no_pdl": dict(PLB_PDL=0),                             # env-step graphs without programmatic dependent launch edges
     "window_fixed": dict(PLB_WINDOW_FOLLOW=0),             # TMA windows fixed at the sort (default: re-centred on the material every env step)
     "flush_groups": dict(PLB_FLUSH_MODE=0),                # per-cell group flush in the per-warp kernels (default: runs of consecutive lanes)
-    "resort": dict(PLB_RESORT=1),                          # particles re-sorted at every env-step boundary, adjoint un-permuted on the way back
-    "resort_no_tile": dict(PLB_RESORT=1, PLB_TILE=0),
+    "no_resort": dict(PLB_RESORT=0),                       # (default: particles re-sorted at every env-step boundary, adjoint un-permuted on the way back)
+    "no_resort_no_tile": dict(PLB_RESORT=0, PLB_TILE=0),
     "substep_list_no_svd_groups": dict(PLB_ENV_LIST=0, PLB_SVD_STORE=0, PLB_BWD_MINB=3, PLB_FLUSH_MODE=0),
 }
 
