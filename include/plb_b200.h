@@ -117,7 +117,11 @@ int  plb_kinematics(plb_engine* e, int pf, int n);
 /* ---- simulation ----------------------------------------------------------------------------------------- */
 /* MPMSimulator.substep(s), mpm_simulator.py:245-257: state[slot_in] -> state[slot_out] with poses pf, pf+1 */
 int  plb_substep_fwd(plb_engine* e, int slot_in, int slot_out, int pf);
-/* n consecutive substeps slot0+i -> slot0+i+1, poses pf0+i (MPMSimulator.step's loop, mpm_simulator.py:373-374) */
+/* n consecutive substeps slot0+i -> slot0+i+1, poses pf0+i (MPMSimulator.step's loop, mpm_simulator.py:373-374): one CUDA graph
+   launch.  If frame slot0 was produced by an earlier plb_step_fwd, its particles are first re-sorted spatially in place (like
+   plb_sort_particles, nothing read back); the engine keeps the permutation and plb_step_bwd / plb_substep_bwd of slot0 put the
+   adjoint frame, frame slot0 and the per-particle materials back into the previous order, so callers never see it: every getter
+   and setter maps through the ordering the frame is stored in.  PLB_RESORT=0 in the environment switches the re-sort off. */
 int  plb_step_fwd(plb_engine* e, int slot0, int pf0, int n);
 /* MPMSimulator.substep_grad(s), mpm_simulator.py:260-278: adjoint(frame s+1) -> adjoint(frame s); adds the pose
    adjoints of frames pf, pf+1 to the primitive-gradient buffer */
@@ -190,9 +194,10 @@ int  plb_device_buffer(plb_engine* e, int which, void** ptr, long long* bytes);
 /* Peer-memory halo (preferred): every rank exports a CUDA-IPC handle of its per-side inbox, the host hands it to the
  * neighbour on that side (torch.distributed all_gather_object), the neighbour imports it.  Once all neighbours are
  * imported, plb_substep_fwd/bwd and plb_step_fwd/bwd do the halo themselves: after the scatter each rank stores ONLY its
- * active 4^3 blocks inside the zone into the neighbour's inbox (P2P stores over NVLink), stamps them with a sequence
- * number, publishes the number in a flag, spins on its own flag, adds what arrived -- all in-stream, so whole env steps
- * are CUDA graphs again.  handle64: 64 bytes (cudaIpcMemHandle_t). */
+ * listed 4^3 blocks inside the zone into the neighbour's inbox (P2P stores over NVLink), stamps them with a sequence
+ * number, publishes the number in a flag, waits for its own flag, adds what arrived -- all in-stream, so whole env steps
+ * are CUDA graphs again.  Inside plb_step_fwd/bwd the grid kernels do all of this themselves (push, interior blocks, wait,
+ * zone blocks; no extra launches).  handle64: 64 bytes (cudaIpcMemHandle_t). */
 int  plb_slab_ipc_export(plb_engine* e, int side, void* handle64);
 int  plb_slab_ipc_import(plb_engine* e, int side, const void* handle64);
 /* Unmaps the neighbours' inboxes (cudaIpcCloseMemHandle) and returns to the host-driven halo.  Every rank must call this --
