@@ -67,8 +67,19 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // 0/1 have flushed.  The hand-off is an mbarrier per tile (hand[0..1], arrival count 1, initialised with the TMA barrier): the
 // first version used named barriers (bar.sync / bar.arrive 1, 2), and the 16 hardware barriers of an SM then capped the kernel
 // at 4 resident CTAs (ncu "Block Limit Barriers 4") -- below the 5 the registers allow, which is the point of sharing tiles.
+// (the hand-off lasts ~600 warp instructions of the other warp pair: polling it back to back took 14.6 % of the forward kernel's issue
+//  slots, profiles/r2j_slab1m_fwd_chunk_by_source.txt -- the waiting warp sleeps between polls instead)
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned phase) {
+    unsigned ok = 0;
+    for (;;) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        if (ok) break;
+        __nanosleep(160);
+    }
+}
 template <class T, int kTiles> __device__ __forceinline__ Vec4<T>* shared_tile_acquire(unsigned char* smem_raw, unsigned long long* hand, int w) {
-    if (kTiles == 2 && w >= 2) mbar_wait(&hand[w & 1], 0);
+    if (kTiles == 2 && w >= 2) mbar_wait_backoff(&hand[w & 1], 0);
     return reinterpret_cast<Vec4<T>*>(smem_raw) + (w % kTiles) * kTileVec4;
 }
 template <int kTiles> __device__ __forceinline__ void shared_tile_release(unsigned long long* hand, int w, int lane) {
