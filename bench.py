@@ -93,8 +93,8 @@ KERNEL_BYTES = {
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the fused kernels from `ncu --set full` captures of
 # this bench at the named workload (profiles/r2_*_ncu_full_summary.md); `roofline.traffic` is null for anything else.
-NCU_TRAFFIC = {("slab1m", "p2g_bwd_g2p_bwd"): 372.7e6, ("slab1m", "g2p_p2g"): 212.2e6}
-NCU_TRAFFIC_SOURCE = {"slab1m": "profiles/r2c_slab1m_{bwd_warp,fwd_chunk}_ncu_full_raw.csv.gz (dram__bytes_read.sum + dram__bytes_write.sum per launch; "
+NCU_TRAFFIC = {("slab1m", "p2g_bwd_g2p_bwd"): 370.6e6, ("slab1m", "g2p_p2g"): 212.1e6}
+NCU_TRAFFIC_SOURCE = {"slab1m": "profiles/r2j_slab1m_{bwd_warp,fwd_chunk}_ncu_full_raw.csv.gz (dram__bytes_read.sum + dram__bytes_write.sum per launch; "
                                 "above the algorithmic figure because the SVD store adds 84 B written / 84 B read per particle and substep)"}
 
 

@@ -111,9 +111,19 @@ def inv_trans(pos, position, rotation):
 # --------------------------------------------------------------------------------------
 # SVD with the reference's backward
 # --------------------------------------------------------------------------------------
+# UNVERIFIED Taichi behaviour (SURVEY.md 8c caveat 1): `ti.svd(A)` without `dt` may run its float32 routine on the float64 data.
+# SVD_INTERNAL_F32 = True makes the oracle decompose in float32 and cast back, which is how large the effect of that would be
+# (tests/test_oracle.py::test_f32_internal_svd_sensitivity); the default is the exact float64 decomposition.
+SVD_INTERNAL_F32 = False
+
+
 def svd_sifakis_convention(A: torch.Tensor):
     """LAPACK SVD moved to det(U)=det(V)=+1, |sigma| descending, sign on the last one."""
-    U, S, Vh = torch.linalg.svd(A)
+    if SVD_INTERNAL_F32 and A.dtype == torch.float64:
+        U, S, Vh = torch.linalg.svd(A.float())
+        U, S, Vh = U.double(), S.double(), Vh.double()
+    else:
+        U, S, Vh = torch.linalg.svd(A)
     V = Vh.transpose(-1, -2).clone()
     U = U.clone()
     S = S.clone()

@@ -79,6 +79,27 @@ def test_oracle_gradient_matches_finite_differences():
         assert abs(fd - g[i, j]) < 1e-6 * max(abs(fd), 1e-3), (i, j, fd, g[i, j])
 
 
+def test_f32_internal_svd_sensitivity():
+    """SURVEY.md 8c caveat (1), UNVERIFIED: Taichi 0.7's `ti.svd(A)` may decompose float64 matrices with its float32 routine.
+    The reference cannot be run here, so this only MEASURES how far such a reference would sit from the exact-SVD oracle on a
+    small episode (2 env steps, two spheres, yield branch active): loss 2e-10 relative, action gradient 7e-7 relative -- two
+    orders of magnitude inside the 1e-4 parity tolerance, i.e. whichever way Taichi decomposes, a gradient comparison at 1e-4
+    would not be decided by it.  (DESIGN.md 2 quotes the numbers.)"""
+    env = _small_env('taichi')
+    A = np.random.RandomState(0).uniform(-1, 1, (2, 9)) * 0.5
+    exact = env.rollout(A)
+    O.SVD_INTERNAL_F32 = True
+    try:
+        f32 = env.rollout(A)
+    finally:
+        O.SVD_INTERNAL_F32 = False
+    dl = abs(f32['loss'] - exact['loss']) / abs(exact['loss'])
+    dg = np.linalg.norm(f32['grad'] - exact['grad']) / np.linalg.norm(exact['grad'])
+    print(f"f32-internal SVD: loss rel {dl:.3e}, action-gradient rel {dg:.3e}")
+    assert dl < 1e-7
+    assert dg < 1e-4
+
+
 def test_oracle_policy_gradient_matches_finite_differences():
     """Policy path (plb/engine/nn/mlp.py + solver_nn.py): the oracle's tape replay with the state-feedback MLP -- kinematics chain
     per env step, clamp, dense layers, observation adjoint into x, v and the primitive poses -- equals central differences of its
