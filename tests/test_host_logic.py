@@ -115,3 +115,38 @@ def test_taichi_shim_exposes_tape():
     mod = shim.install()
     import taichi as ti
     assert ti is mod and ti.Tape is Tape and ti.init(arch=ti.gpu) is None
+
+
+@pytest.mark.parametrize('workload,worlds', [('slab1m', (1, 2, 4, 8)), ('torus4m', (1, 2, 4)), ('block16m', (1, 2, 8)), ('move100k', (1,)),
+                                             ('move1m', (1,)), ('rope1m', (1,)), ('fly1m', (1,))])
+def test_bench_workloads_build_valid_configs_and_slabs(workload, worlds):
+    """The configurations `bench.py` (and the driver's 1 -> 8 scaling run) builds: substep counts of SURVEY.md 8 (19 / 39 / 79 / 159 at
+    64^3 / 128^3 / 256^3 / 512^3), and for the slab workloads boundaries on 4-plane blocks, slabs at least two halos thick, every
+    rank owning particles, every stencil inside its slab +- halo at partition time.  (Particle counts are scaled down: the
+    geometry decides the boundaries, not the count.)"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('plb_bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from plasticinelab_b200 import _capi
+    from plasticinelab_b200.engine import sharding
+    from plasticinelab_b200.engine.shapes import Shapes
+    w = dict(bench.WORKLOADS[workload], n=20_000)
+    for world in worlds:
+        cfg, S = bench.build_cfg(w, world)
+        k = _capi.sim_constants(dict(cfg.SIMULATOR))
+        assert S == {64: 19, 128: 39, 256: 79, 512: 159}[k['n_grid']]
+        assert cfg.SIMULATOR.max_steps >= w['horizon'] * S + 2 or w.get('checkpoint')
+        if world == 1:
+            continue
+        x0, _ = Shapes(cfg.SHAPES).get()
+        hw = w.get('halo_w', 8)
+        b = sharding.slab_bounds(x0[:, 0], k['n_grid'], world, hw)
+        assert len(b) == world + 1 and all(v % 4 == 0 for v in b)
+        for r in range(world):
+            idx = sharding.owned_index(x0[:, 0], k['n_grid'], b, r)
+            assert len(idx) > 0.5 * len(x0) / world, (workload, world, r, len(idx))
+            interior = 0 < r < world - 1
+            assert b[r + 1] - b[r] >= (2 * hw if interior else hw)
+            assert sharding.check_margin(x0[idx, 0], k['n_grid'], b, r, hw)
